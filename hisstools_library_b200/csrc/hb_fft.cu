@@ -1,0 +1,463 @@
+// hb_fft.cu -- the FFT family of the C ABI (include/hisstools_b200.h) and its kernels.
+//
+// Replaces HISSTools_FFT (reference: HISSTools_FFT/HISSTools_FFT.h:87-369, .cpp:111-248, Core:1293-1374)
+// with one CTA per transform: the whole complex array lives in shared memory, a Stockham radix-8/4/2
+// FFT runs in place (hb_fft_block.cuh), and the even/odd (un)zip, zero padding and the real split
+// pass are folded into the load / store stages, so every transform is one pass over global memory.
+#include "hb_common.cuh"
+#include "hb_fft_block.cuh"
+
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+namespace hb
+{
+
+// ---------------------------------------------------------------------------------------------
+// process-wide bookkeeping
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int use_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        set_error("no CUDA device available (%s); libhisstools_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return HB_ERR_CUDA;
+    }
+    if (device < 0 || device >= count)
+    {
+        set_error("device %d out of range (%d devices)", device, count);
+        return HB_ERR_BAD_ARG;
+    }
+    HB_CUDA(cudaSetDevice(device));
+    return HB_OK;
+}
+
+int make_twiddles(int dtype, int log2, void **d_out)
+{
+    if (log2 < 1) log2 = 1;
+    const size_t half = size_t(1) << (log2 - 1);
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const long double n = (long double) (size_t(1) << log2);
+    void *d = nullptr;
+    if (dtype == HB_F64)
+    {
+        std::vector<Cx<double>> h(half);
+        for (size_t q = 0; q < half; q++)
+        {
+            long double a = -2.0L * pi * (long double) q / n;
+            h[q].x = (double) cosl(a);
+            h[q].y = (double) sinl(a);
+        }
+        HB_CUDA(cudaMalloc(&d, half * sizeof(Cx<double>)));
+        HB_CUDA(cudaMemcpy(d, h.data(), half * sizeof(Cx<double>), cudaMemcpyHostToDevice));
+    }
+    else
+    {
+        std::vector<Cx<float>> h(half);
+        for (size_t q = 0; q < half; q++)
+        {
+            long double a = -2.0L * pi * (long double) q / n;
+            h[q].x = (float) cosl(a);
+            h[q].y = (float) sinl(a);
+        }
+        HB_CUDA(cudaMalloc(&d, half * sizeof(Cx<float>)));
+        HB_CUDA(cudaMemcpy(d, h.data(), half * sizeof(Cx<float>), cudaMemcpyHostToDevice));
+    }
+    *d_out = d;
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels (one CTA per transform; blockIdx.x = batch index)
+// ---------------------------------------------------------------------------------------------
+
+// complex forward (swap = 0) / planes-exchanged forward = unscaled inverse (swap = 1), in place or not
+template <class T, int EPT>
+__global__ void __launch_bounds__(1024) k_cfft(const T *re_in, const T *im_in,
+                                               T *re_out, T *im_out, int log2m, int swap,
+                                               size_t stride, const Cx<T> *__restrict__ tw, int tw_log2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
+    const uint32_t M = 1u << log2m;
+    const size_t base = size_t(blockIdx.x) * stride;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+    {
+        T a = re_in[base + i], b = im_in[base + i];
+        s[sidx<HB_PADSH>(i)] = swap ? cx<T>(b, a) : cx<T>(a, b);
+    }
+    __syncthreads();
+    block_fft<T, EPT, HB_PADSH>(s, log2m, tw, tw_log2);
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+    {
+        Cx<T> v = s[sidx<HB_PADSH>(i)];
+        re_out[base + i] = swap ? v.y : v.x;
+        im_out[base + i] = swap ? v.x : v.y;
+    }
+}
+
+// real forward.  Source is either split planes already holding the de-interleaved signal (x == nullptr;
+// HISSTools_FFT.h:154,166) or a real array of in_length samples that is de-interleaved and zero padded on
+// the way in (HISSTools_FFT.h:180-208 = unzip_zero, Core:1258-1287, + rfft).  TI = element type of x.
+template <class T, class TI, int EPT>
+__global__ void __launch_bounds__(1024) k_rfft(const TI *__restrict__ x, size_t in_length, size_t x_stride,
+                                               const T *re_in, const T *im_in,
+                                               T *re_out, T *im_out, size_t stride, int log2n,
+                                               const Cx<T> *__restrict__ tw, int tw_log2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
+    const int log2m = log2n - 1;
+    const uint32_t M = 1u << log2m;
+    const size_t base = size_t(blockIdx.x) * stride;
+    if (x)
+    {
+        const TI *xb = x + size_t(blockIdx.x) * x_stride;
+        const size_t n = size_t(1) << log2n;
+        const size_t len = in_length < n ? in_length : n;
+        const size_t pairs = len >> 1;
+        for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+        {
+            T a = 0, b = 0;
+            if (i < pairs) { a = (T) xb[2 * size_t(i)]; b = (T) xb[2 * size_t(i) + 1]; }
+            else if (i == pairs && (len & 1)) a = (T) xb[len - 1];
+            s[sidx<HB_PADSH>(i)] = cx<T>(a, b);
+        }
+    }
+    else
+    {
+        for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) s[sidx<HB_PADSH>(i)] = cx<T>(re_in[base + i], im_in[base + i]);
+    }
+    __syncthreads();
+    block_fft<T, EPT, HB_PADSH>(s, log2m, tw, tw_log2);
+    for (uint32_t k = threadIdx.x; k <= M / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, M, log2n, k, false, tw, tw_log2);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+    {
+        Cx<T> v = s[sidx<HB_PADSH>(i)];
+        re_out[base + i] = v.x;
+        im_out[base + i] = v.y;
+    }
+}
+
+// real inverse.  Result is left de-interleaved in the planes (even samples in re, odd in im:
+// HISSTools_FFT.h:244,256) and, when y != nullptr, also interleaved into the real array y
+// (HISSTools_FFT.h:269,282 = rifft + zip, Core:1228-1254).
+template <class T, int EPT>
+__global__ void __launch_bounds__(1024) k_rifft(const T *re_in, const T *im_in,
+                                                T *re_out, T *im_out, size_t stride,
+                                                T *__restrict__ y, size_t y_stride, int log2n,
+                                                const Cx<T> *__restrict__ tw, int tw_log2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
+    const int log2m = log2n - 1;
+    const uint32_t M = 1u << log2m;
+    const size_t base = size_t(blockIdx.x) * stride;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) s[sidx<HB_PADSH>(i)] = cx<T>(re_in[base + i], im_in[base + i]);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k <= M / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, M, log2n, k, true, tw, tw_log2);
+    __syncthreads();
+    // hisstools_ifft = forward transform on exchanged planes (Core:1341-1346)
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+    {
+        Cx<T> v = s[sidx<HB_PADSH>(i)];
+        s[sidx<HB_PADSH>(i)] = cx<T>(v.y, v.x);
+    }
+    __syncthreads();
+    block_fft<T, EPT, HB_PADSH>(s, log2m, tw, tw_log2);
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+    {
+        Cx<T> v = s[sidx<HB_PADSH>(i)];
+        if (re_out) { re_out[base + i] = v.y; im_out[base + i] = v.x; }
+        if (y)
+        {
+            T *yb = y + size_t(blockIdx.x) * y_stride;
+            yb[2 * size_t(i)] = v.y;
+            yb[2 * size_t(i) + 1] = v.x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+template <class T> static size_t fft_smem_bytes(int log2m) { return size_t(padded_elems<HB_PADSH>(1u << log2m)) * sizeof(Cx<T>); }
+
+template <class K> static int allow_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+    return HB_OK;
+}
+
+template <class T>
+static int launch_cfft(const T *re_in, const T *im_in, T *re_out, T *im_out, int log2m, int swap, size_t batch, size_t stride,
+                       const Cx<T> *tw, int tw_log2, cudaStream_t st)
+{
+    if (log2m > SmemFftLimit<T>::max_log2m) { set_error("complex FFT of 2^%d points exceeds the shared-memory path", log2m); return HB_ERR_UNSUPPORTED; }
+    const size_t smem = fft_smem_bytes<T>(log2m);
+    if ((1 << log2m) / 8 > 1024)
+    {
+        int rc = allow_smem(k_cfft<T, 16>, smem); if (rc) return rc;
+        k_cfft<T, 16><<<(unsigned) batch, fft_threads(log2m, 16), smem, st>>>(re_in, im_in, re_out, im_out, log2m, swap, stride, tw, tw_log2);
+    }
+    else
+    {
+        int rc = allow_smem(k_cfft<T, 8>, smem); if (rc) return rc;
+        k_cfft<T, 8><<<(unsigned) batch, fft_threads(log2m, 8), smem, st>>>(re_in, im_in, re_out, im_out, log2m, swap, stride, tw, tw_log2);
+    }
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+template <class T, class TI>
+static int launch_rfft(const TI *x, size_t in_length, size_t x_stride, const T *re_in, const T *im_in, T *re_out, T *im_out,
+                       size_t stride, int log2n, size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st)
+{
+    const int log2m = log2n - 1;
+    if (log2m > SmemFftLimit<T>::max_log2m) { set_error("real FFT of 2^%d points exceeds the shared-memory path", log2n); return HB_ERR_UNSUPPORTED; }
+    const size_t smem = fft_smem_bytes<T>(log2m);
+    if ((1 << log2m) / 8 > 1024)
+    {
+        int rc = allow_smem(k_rfft<T, TI, 16>, smem); if (rc) return rc;
+        k_rfft<T, TI, 16><<<(unsigned) batch, fft_threads(log2m, 16), smem, st>>>(x, in_length, x_stride, re_in, im_in, re_out, im_out, stride, log2n, tw, tw_log2);
+    }
+    else
+    {
+        int rc = allow_smem(k_rfft<T, TI, 8>, smem); if (rc) return rc;
+        k_rfft<T, TI, 8><<<(unsigned) batch, fft_threads(log2m, 8), smem, st>>>(x, in_length, x_stride, re_in, im_in, re_out, im_out, stride, log2n, tw, tw_log2);
+    }
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+template <class T>
+static int launch_rifft(const T *re_in, const T *im_in, T *re_out, T *im_out, size_t stride, T *y, size_t y_stride, int log2n,
+                        size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st)
+{
+    const int log2m = log2n - 1;
+    if (log2m > SmemFftLimit<T>::max_log2m) { set_error("real FFT of 2^%d points exceeds the shared-memory path", log2n); return HB_ERR_UNSUPPORTED; }
+    const size_t smem = fft_smem_bytes<T>(log2m);
+    if ((1 << log2m) / 8 > 1024)
+    {
+        int rc = allow_smem(k_rifft<T, 16>, smem); if (rc) return rc;
+        k_rifft<T, 16><<<(unsigned) batch, fft_threads(log2m, 16), smem, st>>>(re_in, im_in, re_out, im_out, stride, y, y_stride, log2n, tw, tw_log2);
+    }
+    else
+    {
+        int rc = allow_smem(k_rifft<T, 8>, smem); if (rc) return rc;
+        k_rifft<T, 8><<<(unsigned) batch, fft_threads(log2m, 8), smem, st>>>(re_in, im_in, re_out, im_out, stride, y, y_stride, log2n, tw, tw_log2);
+    }
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+} // namespace hb
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace hb;
+
+struct hb_fft_setup
+{
+    int dtype = HB_F32;
+    int device = 0;
+    int max_log2 = 0;
+    int tw_log2 = 1;
+    void *tw = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf d_a, d_b, d_c;       // planes / real array scratch
+    std::mutex lock;
+};
+
+extern "C" const char *hb_last_error(void) { return g_error; }
+extern "C" uint64_t hb_launch_count(void) { return g_launches.load(); }
+extern "C" const char *hb_version(void) { return "hisstools_b200 0.1 (sm_100a, CUDA " HB_STR(CUDART_VERSION) ")"; }
+
+extern "C" int hb_fft_setup_create(hb_fft_setup **out, int dtype, uintptr_t max_fft_log2, int device)
+{
+    if (!out || (dtype != HB_F32 && dtype != HB_F64) || max_fft_log2 > 30) { set_error("hb_fft_setup_create: bad argument"); return HB_ERR_BAD_ARG; }
+    *out = nullptr;
+    int rc = use_device(device);
+    if (rc) return rc;
+    hb_fft_setup *s = new hb_fft_setup;
+    s->dtype = dtype; s->device = device; s->max_log2 = (int) max_fft_log2;
+    // the table serves complex transforms of 2^max and real ones of 2^max (which need order-2^max roots)
+    int lim = (dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m) + 1;
+    s->tw_log2 = s->max_log2 < 1 ? 1 : (s->max_log2 > lim ? lim : s->max_log2);
+    rc = make_twiddles(dtype, s->tw_log2, &s->tw);
+    if (rc) { delete s; return rc; }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); cudaFree(s->tw); delete s; return HB_ERR_CUDA; }
+    *out = s;
+    return HB_OK;
+}
+
+extern "C" void hb_fft_setup_destroy(hb_fft_setup *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    s->d_a.release(); s->d_b.release(); s->d_c.release();
+    cudaFree(s->tw);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+namespace
+{
+enum Op { OP_FFT, OP_IFFT, OP_RFFT, OP_RIFFT };
+
+template <class T>
+int inplace_op(hb_fft_setup *s, Op op, T *re, T *im, uintptr_t log2n)
+{
+    const bool real = (op == OP_RFFT || op == OP_RIFFT);
+    if (log2n == 0) return HB_OK;                       // hisstools_fft of one point is a no-op (Core:1328-1336)
+    if ((int) log2n > s->max_log2) { set_error("log2n %d exceeds the setup's maximum %d", (int) log2n, s->max_log2); return HB_ERR_BAD_ARG; }
+    const size_t planes = real ? (size_t(1) << (log2n - 1)) : (size_t(1) << log2n);
+    const size_t bytes = planes * sizeof(T);
+    int rc;
+    if ((rc = s->d_a.ensure(bytes)) || (rc = s->d_b.ensure(bytes))) return rc;
+    T *d_re = (T *) s->d_a.p, *d_im = (T *) s->d_b.p;
+    const Cx<T> *tw = (const Cx<T> *) s->tw;
+    HB_CUDA(cudaMemcpyAsync(d_re, re, bytes, cudaMemcpyHostToDevice, s->stream));
+    HB_CUDA(cudaMemcpyAsync(d_im, im, bytes, cudaMemcpyHostToDevice, s->stream));
+    switch (op)
+    {
+        case OP_FFT:   rc = launch_cfft<T>(d_re, d_im, d_re, d_im, (int) log2n, 0, 1, 0, tw, s->tw_log2, s->stream); break;
+        case OP_IFFT:  rc = launch_cfft<T>(d_re, d_im, d_re, d_im, (int) log2n, 1, 1, 0, tw, s->tw_log2, s->stream); break;
+        case OP_RFFT:  rc = launch_rfft<T, T>(nullptr, 0, 0, d_re, d_im, d_re, d_im, 0, (int) log2n, 1, tw, s->tw_log2, s->stream); break;
+        case OP_RIFFT: rc = launch_rifft<T>(d_re, d_im, d_re, d_im, 0, nullptr, 0, (int) log2n, 1, tw, s->tw_log2, s->stream); break;
+    }
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(re, d_re, bytes, cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaMemcpyAsync(im, d_im, bytes, cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaStreamSynchronize(s->stream));
+    return HB_OK;
+}
+
+int inplace_dispatch(hb_fft_setup *s, Op op, void *re, void *im, uintptr_t log2n)
+{
+    if (!s || !re || !im) { set_error("null argument"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(s->lock);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return s->dtype == HB_F64 ? inplace_op<double>(s, op, (double *) re, (double *) im, log2n)
+                              : inplace_op<float>(s, op, (float *) re, (float *) im, log2n);
+}
+} // namespace
+
+extern "C" int hb_fft(hb_fft_setup *s, void *re, void *im, uintptr_t log2n) { return inplace_dispatch(s, OP_FFT, re, im, log2n); }
+extern "C" int hb_ifft(hb_fft_setup *s, void *re, void *im, uintptr_t log2n) { return inplace_dispatch(s, OP_IFFT, re, im, log2n); }
+extern "C" int hb_rfft(hb_fft_setup *s, void *re, void *im, uintptr_t log2n) { return inplace_dispatch(s, OP_RFFT, re, im, log2n); }
+extern "C" int hb_rifft(hb_fft_setup *s, void *re, void *im, uintptr_t log2n) { return inplace_dispatch(s, OP_RIFFT, re, im, log2n); }
+
+namespace
+{
+template <class T, class TI>
+int rfft_real_host(hb_fft_setup *s, const TI *input, T *re, T *im, uintptr_t in_length, uintptr_t log2n)
+{
+    const size_t n = size_t(1) << log2n, half = n >> 1;
+    const size_t len = in_length < n ? in_length : n;
+    int rc;
+    if ((rc = s->d_a.ensure(half * sizeof(T))) || (rc = s->d_b.ensure(half * sizeof(T))) || (rc = s->d_c.ensure((len ? len : 1) * sizeof(TI)))) return rc;
+    if (len) HB_CUDA(cudaMemcpyAsync(s->d_c.p, input, len * sizeof(TI), cudaMemcpyHostToDevice, s->stream));
+    rc = launch_rfft<T, TI>((const TI *) s->d_c.p, len, 0, nullptr, nullptr, (T *) s->d_a.p, (T *) s->d_b.p, 0, (int) log2n, 1,
+                            (const Cx<T> *) s->tw, s->tw_log2, s->stream);
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(re, s->d_a.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaMemcpyAsync(im, s->d_b.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaStreamSynchronize(s->stream));
+    return HB_OK;
+}
+
+template <class T>
+int rifft_real_host(hb_fft_setup *s, T *re, T *im, T *output, uintptr_t log2n)
+{
+    const size_t n = size_t(1) << log2n, half = n >> 1;
+    int rc;
+    if ((rc = s->d_a.ensure(half * sizeof(T))) || (rc = s->d_b.ensure(half * sizeof(T))) || (rc = s->d_c.ensure(n * sizeof(T)))) return rc;
+    HB_CUDA(cudaMemcpyAsync(s->d_a.p, re, half * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    HB_CUDA(cudaMemcpyAsync(s->d_b.p, im, half * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    rc = launch_rifft<T>((const T *) s->d_a.p, (const T *) s->d_b.p, (T *) s->d_a.p, (T *) s->d_b.p, 0, (T *) s->d_c.p, 0, (int) log2n, 1,
+                         (const Cx<T> *) s->tw, s->tw_log2, s->stream);
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(re, s->d_a.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaMemcpyAsync(im, s->d_b.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaMemcpyAsync(output, s->d_c.p, n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaStreamSynchronize(s->stream));
+    return HB_OK;
+}
+} // namespace
+
+extern "C" int hb_rfft_real(hb_fft_setup *s, const void *input, int in_dtype, void *re, void *im, uintptr_t in_length, uintptr_t log2n)
+{
+    if (!s || !re || !im || (!input && in_length) || log2n < 1) { set_error("hb_rfft_real: bad argument"); return HB_ERR_BAD_ARG; }
+    if ((int) log2n > s->max_log2) { set_error("log2n %d exceeds the setup's maximum %d", (int) log2n, s->max_log2); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(s->lock);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    if (s->dtype == HB_F64)
+        return in_dtype == HB_F32 ? rfft_real_host<double, float>(s, (const float *) input, (double *) re, (double *) im, in_length, log2n)
+                                  : rfft_real_host<double, double>(s, (const double *) input, (double *) re, (double *) im, in_length, log2n);
+    if (in_dtype != HB_F32) { set_error("double input needs a double setup"); return HB_ERR_BAD_ARG; }
+    return rfft_real_host<float, float>(s, (const float *) input, (float *) re, (float *) im, in_length, log2n);
+}
+
+extern "C" int hb_rifft_real(hb_fft_setup *s, void *re, void *im, void *output, uintptr_t log2n)
+{
+    if (!s || !re || !im || !output || log2n < 1) { set_error("hb_rifft_real: bad argument"); return HB_ERR_BAD_ARG; }
+    if ((int) log2n > s->max_log2) { set_error("log2n %d exceeds the setup's maximum %d", (int) log2n, s->max_log2); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(s->lock);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return s->dtype == HB_F64 ? rifft_real_host<double>(s, (double *) re, (double *) im, (double *) output, log2n)
+                              : rifft_real_host<float>(s, (float *) re, (float *) im, (float *) output, log2n);
+}
+
+extern "C" int hb_rfft_real_batched_dev(hb_fft_setup *s, const void *d_input, void *d_re, void *d_im, uintptr_t log2n, uintptr_t batch,
+                                        uintptr_t in_stride, uintptr_t out_stride, void *stream)
+{
+    if (!s || !d_input || !d_re || !d_im || log2n < 1 || (int) log2n > s->max_log2) { set_error("hb_rfft_real_batched_dev: bad argument"); return HB_ERR_BAD_ARG; }
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t) stream : s->stream;
+    const size_t n = size_t(1) << log2n;
+    if (s->dtype == HB_F64)
+        return launch_rfft<double, double>((const double *) d_input, n, in_stride, nullptr, nullptr, (double *) d_re, (double *) d_im, out_stride,
+                                           (int) log2n, batch, (const Cx<double> *) s->tw, s->tw_log2, st);
+    return launch_rfft<float, float>((const float *) d_input, n, in_stride, nullptr, nullptr, (float *) d_re, (float *) d_im, out_stride,
+                                     (int) log2n, batch, (const Cx<float> *) s->tw, s->tw_log2, st);
+}
+
+extern "C" int hb_rifft_real_batched_dev(hb_fft_setup *s, const void *d_re, const void *d_im, void *d_output, uintptr_t log2n, uintptr_t batch,
+                                         uintptr_t in_stride, uintptr_t out_stride, void *stream)
+{
+    if (!s || !d_output || !d_re || !d_im || log2n < 1 || (int) log2n > s->max_log2) { set_error("hb_rifft_real_batched_dev: bad argument"); return HB_ERR_BAD_ARG; }
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t) stream : s->stream;
+    if (s->dtype == HB_F64)
+        return launch_rifft<double>((const double *) d_re, (const double *) d_im, nullptr, nullptr, in_stride, (double *) d_output, out_stride,
+                                    (int) log2n, batch, (const Cx<double> *) s->tw, s->tw_log2, st);
+    return launch_rifft<float>((const float *) d_re, (const float *) d_im, nullptr, nullptr, in_stride, (float *) d_output, out_stride,
+                               (int) log2n, batch, (const Cx<float> *) s->tw, s->tw_log2, st);
+}

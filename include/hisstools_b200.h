@@ -1,0 +1,154 @@
+/* include/hisstools_b200.h -- the drop-in boundary: C ABI of libhisstools_b200.so
+ *
+ * B200-native (sm_100a) implementation of the HISSTools_Library partitioned-convolution hot path.
+ * Plain pointers and sizes only; no C++ or torch types.  The C++ headers under
+ * include/HISSTools_FFT and include/HIRT_Multichannel_Convolution are thin source-compatible
+ * wrappers over these entry points, and hisstools_library_b200/ (python, ctypes) binds the same
+ * symbols for tests and bench.py.  There is no CPU fallback anywhere behind this boundary: every
+ * compute entry point returns HB_ERR_CUDA when no device is usable.
+ *
+ * Each entry point cites the reference interface it replaces (paths under the reference tree).
+ *
+ * Conventions
+ *   - return value: a reference ConvolveError code 0..12 (HIRT_Multichannel_Convolution/ConvolveErrors.h:4-19)
+ *     or a negative hb_status for conditions the reference cannot express.
+ *   - dtype: HB_F32 (0) or HB_F64 (1).  The reference convolver classes are float-only
+ *     (PartitionedConvolve.h:38-41); HB_F64 is the double engine BASELINE config 5 asks for.
+ *   - host pointers are only read/written during the call (PartitionedConvolve.cpp:212-217);
+ *     `_dev` variants take device pointers on the handle's device and enqueue on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the handle's own stream) without synchronising.
+ */
+#ifndef HISSTOOLS_B200_H
+#define HISSTOOLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_F32 0
+#define HB_F64 1
+
+typedef enum hb_status
+{
+    HB_OK = 0,
+    HB_ERR_CUDA = -1,          /* no device / CUDA runtime failure (see hb_last_error) */
+    HB_ERR_BAD_ARG = -2,
+    HB_ERR_UNSUPPORTED = -3,   /* size outside what the library implements */
+    HB_ERR_NO_IR = -4          /* process() on an object with no impulse response: outputs untouched */
+} hb_status;
+
+/* last CUDA / argument error text of the calling thread ("" if none) */
+const char *hb_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t hb_launch_count(void);
+/* library build identification, e.g. "hisstools_b200 sm_100a" */
+const char *hb_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * FFT family -- replaces HISSTools_FFT/HISSTools_FFT.h:87-369 (hisstools_create_setup,
+ * hisstools_destroy_setup, hisstools_fft / ifft / rfft / rifft, and the out-of-place real
+ * conveniences).  Same conventions: split-complex planes, forward kernel exp(-j theta), real
+ * forward transform returns 2*DFT with DC in realp[0] and Nyquist in imagp[0], nothing is scaled
+ * (rifft(rfft(x)) = 2N x).  Host pointers; each call is one H2D, one kernel, one D2H.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hb_fft_setup hb_fft_setup;
+
+/* hisstools_create_setup(FFT_SETUP_F/D*, max_fft_log_2): HISSTools_FFT.h:87,98 */
+int hb_fft_setup_create(hb_fft_setup **out, int dtype, uintptr_t max_fft_log2, int device);
+/* hisstools_destroy_setup: HISSTools_FFT.h:108,118 */
+void hb_fft_setup_destroy(hb_fft_setup *setup);
+
+/* in-place complex transforms on split planes of 2^log2n points: HISSTools_FFT.h:130,142 (fft) 220,232 (ifft) */
+int hb_fft(hb_fft_setup *setup, void *realp, void *imagp, uintptr_t log2n);
+int hb_ifft(hb_fft_setup *setup, void *realp, void *imagp, uintptr_t log2n);
+/* in-place real transforms; planes hold 2^(log2n-1) points: HISSTools_FFT.h:154,166 (rfft) 244,256 (rifft) */
+int hb_rfft(hb_fft_setup *setup, void *realp, void *imagp, uintptr_t log2n);
+int hb_rifft(hb_fft_setup *setup, void *realp, void *imagp, uintptr_t log2n);
+/* out-of-place real forward with zero padding: HISSTools_FFT.h:180,194,208.
+ * in_dtype may be HB_F32 with an HB_F64 setup (the float->double overload, :208). */
+int hb_rfft_real(hb_fft_setup *setup, const void *input, int in_dtype, void *realp, void *imagp,
+                 uintptr_t in_length, uintptr_t log2n);
+/* out-of-place real inverse (planes are left holding the de-interleaved result, as the reference): HISSTools_FFT.h:269,282 */
+int hb_rifft_real(hb_fft_setup *setup, void *realp, void *imagp, void *output, uintptr_t log2n);
+
+/* batched device-pointer variants (benchmarking / pipelines without PCIe).  `batch` transforms,
+ * consecutive transforms `stride` elements apart in every array. */
+int hb_rfft_real_batched_dev(hb_fft_setup *setup, const void *d_input, void *d_realp, void *d_imagp,
+                             uintptr_t log2n, uintptr_t batch, uintptr_t in_stride, uintptr_t out_stride, void *stream);
+int hb_rifft_real_batched_dev(hb_fft_setup *setup, const void *d_realp, const void *d_imagp, void *d_output,
+                              uintptr_t log2n, uintptr_t batch, uintptr_t in_stride, uintptr_t out_stride, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Uniform partitioned convolution engine.  One handle = `groups` independent banks, each an
+ * `ins` x `outs` matrix of impulse responses convolved by overlap-save with hop B = fft_size/2:
+ *     out[g][o] = sum_i  IR[g][o][i] * in[g][i]        (delayed by exactly B samples)
+ *   groups=1, ins=outs=1     HISSTools::PartitionedConvolve  (PartitionedConvolve.h:23-41)
+ *   groups=1, ins=N, outs=1  HISSTools::NToMonoConvolve::process (NToMonoConvolve.cpp:35-43), uniform partitions
+ *   groups=1, ins=N, outs=M  HISSTools::Convolver, N x M mode (Convolver.cpp:5-22,138-154)
+ *   groups=K, ins=outs=1     HISSTools::Convolver, parallel mode (Convolver.cpp:24-41)
+ * Per hop and bank: `ins` forward real FFTs, one frequency-domain multiply-accumulate over
+ * (input x partition) for every output, `outs` inverse FFTs, scale 1/(4N), first B samples kept
+ * (PartitionedConvolve.cpp:352-377 with the input-sum of NToMonoConvolve.cpp:39-42 moved into
+ * the frequency domain).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hb_conv hb_conv;
+
+/* PartitionedConvolve(maxFFTSize, maxLength, offset, length): PartitionedConvolve.cpp:52-102.
+ * max_length is rounded up to a multiple of max_fft_size/2 as the reference does (:77-82).
+ * Returns the constructor-time error of setMaxFFTSize (:26-50), which the reference discards;
+ * the handle is created (with the clamped size) in every case except HB_ERR_*. */
+int hb_conv_create(hb_conv **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs,
+                   uintptr_t max_fft_size, uintptr_t max_length, uintptr_t offset, uintptr_t length, int device);
+void hb_conv_destroy(hb_conv *c);
+
+/* setFFTSize / setLength / setOffset / setResetOffset: PartitionedConvolve.cpp:131-171.
+ * A changed FFT size drops every loaded IR until hb_conv_set_ir is called again (:145-149).
+ * A negative reset offset (the reference's "random phase", :275-278) selects phase 0 here: the
+ * result is phase independent up to rounding and a fixed phase keeps runs reproducible. */
+int hb_conv_set_fft_size(hb_conv *c, uintptr_t fft_size);
+int hb_conv_set_length(hb_conv *c, uintptr_t length);
+int hb_conv_set_offset(hb_conv *c, uintptr_t offset);
+int hb_conv_set_reset_offset(hb_conv *c, intptr_t offset);
+
+/* set(input, length): PartitionedConvolve.cpp:173-225 for pair (group, in, out); ir_dtype is the
+ * element type of `ir` (HB_F32 or HB_F64; converted to the engine's type as Convolver.cpp:126-134
+ * does for double IRs).  ir == NULL or length <= offset clears the pair.  Triggers reset(). */
+int hb_conv_set_ir(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length);
+/* same, `d_ir` in device memory in the engine's dtype */
+int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *d_ir, uintptr_t length);
+/* grow / shrink the allocation to hold max_length taps per pair (the MemorySwap::equal step of
+ * MonoConvolve.cpp:100-110); all IRs are dropped. */
+int hb_conv_resize(hb_conv *c, uintptr_t max_length);
+/* reset(): PartitionedConvolve.cpp:227-230 -- takes effect at the next process call */
+int hb_conv_reset(hb_conv *c);
+
+/* number of partitions currently loaded (0 = no IR: process returns HB_ERR_NO_IR and leaves outputs untouched) */
+uintptr_t hb_conv_partitions(const hb_conv *c);
+uintptr_t hb_conv_max_length(const hb_conv *c);
+uintptr_t hb_conv_fft_size(const hb_conv *c);
+
+/* process(in, out, numSamples): PartitionedConvolve.cpp:243-385 for every bank at once.
+ * ins: groups*ins planar host pointers (bank-major), outs: groups*outs planar host pointers, any
+ * numSamples (state is carried across calls, :257,298-299,382).  accumulate != 0 adds into outs
+ * (MonoConvolve.cpp:167-177) instead of overwriting. */
+int hb_conv_process(hb_conv *c, const void *const *ins, void *const *outs, uintptr_t num_samples, int accumulate);
+/* device-resident variant: d_in is [groups*ins][in_ld] and d_out [groups*outs][out_ld] in the
+ * engine's dtype; enqueued on `stream`, no synchronisation. */
+int hb_conv_process_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out, uintptr_t out_ld,
+                        uintptr_t num_samples, int accumulate, void *stream);
+
+/* tuning / introspection used by bench.py and the tests */
+/* CTAs per SM for the multiply-accumulate kernel (0 = library default) */
+int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant);
+/* algorithmic bytes one hop moves (IR spectra + FDL + time-domain I/O) */
+uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
+/* device time in ms of the most recent hop's multiply-accumulate kernel is not measured here:
+ * bench.py brackets hb_conv_process_dev with CUDA events on the stream it passes. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HISSTOOLS_B200_H */
