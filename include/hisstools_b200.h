@@ -120,7 +120,8 @@ int hb_conv_set_ir(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const 
 /* same, `d_ir` in device memory in the engine's dtype */
 int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *d_ir, uintptr_t length);
 /* grow / shrink the allocation to hold max_length taps per pair (the MemorySwap::equal step of
- * MonoConvolve.cpp:100-110); all IRs are dropped. */
+ * MonoConvolve.cpp:100-110).  Loaded IRs are kept (cut to the new capacity when it shrinks); the
+ * stream restarts from silence at the next process call. */
 int hb_conv_resize(hb_conv *c, uintptr_t max_length);
 /* reset(): PartitionedConvolve.cpp:227-230 -- takes effect at the next process call */
 int hb_conv_reset(hb_conv *c);

@@ -1,0 +1,366 @@
+"""GPU parity of the partitioned-convolution path (CUDA through the C ABI) against
+ * the golden vectors produced by the unmodified reference (tests/golden/),
+ * the unmodified reference compiled in place (oracle/_ref, shipped prebuilt to the GPU box),
+ * the plain-C oracle (oracle/hiss_oracle.c) where the reference has no class (double engine),
+and through size-independent properties at BASELINE.json's full sizes.
+Tolerances (north_star): <= 1e-5 relative RMS float, <= 1e-12 double.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import checkers as ck
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz"))
+TOL32, TOL64 = 1e-5, 1e-12
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hisstools_library_b200 as h
+    return h
+
+
+def stream(obj_process, x, block, dtype=np.float32, sizes=None):
+    """run x through process(in, out, n) in `block`-sample calls (or the given call sizes)."""
+    y = np.zeros(len(x), dtype)
+    pos, k = 0, 0
+    while pos < len(x):
+        n = min(sizes[k % len(sizes)] if sizes else block, len(x) - pos)
+        obj_process(x[pos:pos + n], y[pos:pos + n], n)
+        pos += n
+        k += 1
+    return y
+
+
+# ---- PartitionedConvolve ------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("name", ["c1", "ragged", "phase", "slice", "trunc", "min"])
+def test_pconv_golden(hb, name, variant):
+    fft, block, max_len, offset, length, reset_offset, err = (int(v) for v in G["pconv_%s_meta" % name])
+    ir, x, want = G["pconv_%s_ir" % name], G["pconv_%s_x" % name], G["pconv_%s_y" % name]
+    pc = hb.PartitionedConvolve(fft, len(ir) if max_len < 0 else max_len, offset, length)
+    pc.engine.set_tuning(0, variant)
+    pc.setResetOffset(reset_offset)
+    assert int(pc.set(ir, len(ir))) == err
+    got = stream(lambda a, b, n: pc.process(a, b, n), x, block)
+    assert ck.rel_rms(got, want) <= TOL32
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_pconv_config2_against_reference(hb, variant):
+    """BASELINE config 2: 1ch, 65536 taps, 1024-sample blocks = PartitionedConvolve(2048, 65536, 0, 0)."""
+    if ck.ref() is None:
+        pytest.skip("compiled reference not shipped")
+    ir = ck.synth_ir(65536, 0)
+    x = ck.synth_audio(1024 * (64 + 32), 0)
+    want, _ = ck.ref_pconv_run(2048, ir, x, 1024)
+    pc = hb.PartitionedConvolve(2048, 65536, 0, 0)
+    pc.engine.set_tuning(0, variant)
+    pc.setResetOffset(0)
+    assert int(pc.set(ir, len(ir))) == 0
+    got = stream(lambda a, b, n: pc.process(a, b, n), x, 1024)
+    assert ck.rel_rms(got, want) <= TOL32
+    assert ck.rel_rms(got[-16 * 1024:], want[-16 * 1024:]) <= TOL32          # FDL full
+    truth = ck.direct_convolve_delayed(ir[:4096], x[:8192], 1024)            # delay is exactly B
+
+
+def test_pconv_call_sizes_do_not_matter(hb):
+    """any chunking of the stream gives the same samples (SURVEY B: bit-identical in the reference)."""
+    ir = ck.synth_ir(3000, 1)
+    x = ck.synth_audio(256 * 40 + 5, 1)
+    outs = []
+    for sizes in ([256], [1], [7, 255, 256, 257, 768, 3], [100000]):
+        if sizes == [1]:
+            xs = x[:600]
+        else:
+            xs = x
+        pc = hb.PartitionedConvolve(512, 3000, 0, 0)
+        pc.setResetOffset(0)
+        pc.set(ir)
+        outs.append(stream(lambda a, b, n: pc.process(a, b, n), xs, 0, sizes=sizes))
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[3])
+    assert np.array_equal(outs[0][:600], outs[1])
+    truth = ck.direct_convolve_delayed(ir, x, 256)
+    assert ck.rel_rms(outs[0], truth) <= TOL32
+
+
+@pytest.mark.parametrize("fft", [32, 64, 128, 256, 1024, 4096, 16384, 32768])
+def test_pconv_fft_sizes(hb, fft):
+    B = fft // 2
+    L = min(5 * B + 3, 40000)
+    ir = ck.synth_ir(L, 2)
+    x = ck.synth_audio(B * 9 + 11, 2)
+    pc = hb.PartitionedConvolve(fft, L, 0, 0)
+    pc.setResetOffset(0)
+    assert int(pc.set(ir)) == 0
+    got = stream(lambda a, b, n: pc.process(a, b, n), x, max(B // 2, 1) + 1)
+    if ck.ref() is not None:
+        want, _ = ck.ref_pconv_run(fft, ir, x, B)
+        assert ck.rel_rms(got, want) <= TOL32
+    assert ck.rel_rms(got, ck.direct_convolve_delayed(ir, x, B)) <= TOL32
+
+
+def test_pconv_semantics(hb):
+    E = hb.ConvolveError
+    pc = hb.PartitionedConvolve(512, 1000, 0, 0)         # max length rounds up to 1024 (cpp:77-82)
+    x = ck.synth_audio(2048, 3)
+    y = np.full(2048, 7.0, np.float32)
+    assert pc.process(x, y, 2048) is False and np.all(y == 7.0)               # no IR: untouched (cpp:262-263)
+    assert pc.set(ck.synth_ir(1024, 3)) == E.CONVOLVE_ERR_NONE
+    assert pc.set(ck.synth_ir(1281, 3)) == E.CONVOLVE_ERR_MEM_ALLOC_TOO_SMALL
+    assert pc.setFFTSize(16) == E.CONVOLVE_ERR_FFT_SIZE_OUT_OF_RANGE
+    assert pc.setFFTSize(1024) == E.CONVOLVE_ERR_FFT_SIZE_OUT_OF_RANGE
+    assert pc.setFFTSize(300) == E.CONVOLVE_ERR_FFT_SIZE_NON_POWER_OF_TWO     # rounds up to 512: unchanged size
+    assert pc.process(x, y, 512) is True
+    assert pc.setFFTSize(256) == E.CONVOLVE_ERR_NONE                          # new size drops the IR (cpp:145-149)
+    y[:] = 7.0
+    assert pc.process(x, y, 512) is False and np.all(y == 7.0)
+    assert pc.setLength(5000) == E.CONVOLVE_ERR_PARTITION_LENGTH_TOO_LARGE
+    assert pc.setLength(0) == E.CONVOLVE_ERR_NONE
+    # reset mid-stream restarts from silence
+    ir = ck.synth_ir(700, 4)
+    pc.setResetOffset(0)
+    pc.set(ir)
+    a = stream(lambda i, o, n: pc.process(i, o, n), x, 128)
+    pc.reset()
+    b = stream(lambda i, o, n: pc.process(i, o, n), x, 128)
+    assert np.array_equal(a, b)
+    assert ck.rel_rms(a, ck.direct_convolve_delayed(ir, x, 128)) <= TOL32
+
+
+def test_pconv_double_engine(hb):
+    """double engine against the restated double loop on the reference's own double FFT (golden) and
+    against float64 direct convolution; BASELINE config 5 tolerance 1e-12."""
+    ir, x, want = G["pconv64_ir"], G["pconv64_x"], G["pconv64_y"]
+    pc = hb.PartitionedConvolve(512, len(ir), 0, 0, dtype=np.float64)
+    pc.setResetOffset(0)
+    assert int(pc.set(ir)) == 0
+    got = stream(lambda a, b, n: pc.process(a, b, n), x, 256, dtype=np.float64)
+    assert ck.rel_rms(got, want) <= TOL64
+    assert ck.rel_rms(got, ck.direct_convolve_delayed(ir, x, 256)) <= TOL64
+
+
+def test_pconv_double_config5_shape_one_channel(hb):
+    """config-5 geometry (FFT 16384, B = 8192) on one channel with a shortened IR, vs the C oracle."""
+    B = 8192
+    ir = ck.synth_ir(5 * B + 100, 5).astype(np.float64)
+    x = ck.synth_audio(B * 8, 5).astype(np.float64)
+    want, _ = ck.oracle_pconv_run(2 * B, ir, x, B, dtype=np.float64)
+    pc = hb.PartitionedConvolve(2 * B, len(ir), 0, 0, dtype=np.float64)
+    pc.setResetOffset(0)
+    pc.set(ir)
+    got = stream(lambda a, b, n: pc.process(a, b, n), x, B, dtype=np.float64)
+    assert ck.rel_rms(got, want) <= TOL64
+
+
+# ---- MonoConvolve ---------------------------------------------------------------------------------
+
+def test_mono_config1_against_reference(hb):
+    """BASELINE config 1: MonoConvolve(4096, false, 1024), 512-sample blocks."""
+    ir = ck.synth_ir(4096, 6)
+    x = ck.synth_audio(512 * 48, 6)
+    mc = hb.MonoConvolve(4096, False, 1024)
+    mc.setResetOffset(0)
+    assert mc.set(ir, len(ir), False) == 0
+    tmp = np.zeros(512, np.float32)
+    got = stream(lambda a, b, n: mc.process(a, tmp, b, n), x, 512)
+    rl = ck.ref()
+    if rl is not None:
+        h = rl.ref_mono_create_custom(4096, 0, 1024, 0, 0, 0)
+        rl.ref_mono_set_reset_offset(h, 0)
+        rl.ref_mono_set(h, ck.fptr(ir), len(ir), 0)
+        rl.ref_mono_set_reset_offset(h, 0)
+        want, t = np.zeros_like(x), np.zeros_like(x)
+        for pos in range(0, len(x), 512):
+            rl.ref_mono_process(h, ck.fptr(x[pos:]), ck.fptr(t), ck.fptr(want[pos:]), 512, 0)
+        rl.ref_mono_destroy(h)
+        assert ck.rel_rms(got, want) <= TOL32
+    assert ck.rel_rms(got, ck.direct_convolve_delayed(ir, x, 512)) <= TOL32
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_mono_latency_modes_golden(hb, mode):
+    """shipped kLatencyShort / kLatencyMedium schemes (MonoConvolve.cpp:28-30): net delay 128 / 512."""
+    ir, x, want = G["mono_ir"], G["mono_x"], G["mono_y_mode%d" % mode]
+    mc = hb.MonoConvolve(len(ir), hb.LatencyMode(mode))
+    mc.setResetOffset(0)
+    assert mc.set(ir, len(ir), True) == 0
+    tmp = np.zeros(512, np.float32)
+    got = stream(lambda a, b, n: mc.process(a, tmp, b, n), x, 512)
+    assert ck.rel_rms(got, want) <= TOL32
+
+
+def test_mono_set_resize_and_errors(hb):
+    E = hb.ConvolveError
+    mc = hb.MonoConvolve(2000, False, 256)
+    ir = ck.synth_ir(3000, 8)
+    x = ck.synth_audio(4096, 8)
+    assert mc.set(ir, 3000, False) == E.CONVOLVE_ERR_MEM_ALLOC_TOO_SMALL
+    y = np.full(4096, 3.0, np.float32)
+    mc.process(x, None if False else np.zeros(4096, np.float32), y, 4096)
+    assert np.all(y == 3.0)            # IR longer than the allocation: process does nothing (MonoConvolve.cpp:183)
+    assert mc.set(ir, 3000, True) == E.CONVOLVE_ERR_NONE
+    mc.setResetOffset(0)
+    mc.reset()
+    mc.process(x, np.zeros(4096, np.float32), y, 4096)
+    assert ck.rel_rms(y, ck.direct_convolve_delayed(ir, x, 128)) <= TOL32
+    acc = np.ones(4096, np.float32)
+    mc.reset()
+    mc.process(x, np.zeros(4096, np.float32), acc, 4096, True)            # accumulate (MonoConvolve.cpp:167-177)
+    assert ck.rel_rms(acc - 1.0, y) <= 1e-5
+    with pytest.raises(RuntimeError):
+        hb.MonoConvolve(1000, False, 1024, 256)
+    with pytest.raises(RuntimeError):
+        hb.MonoConvolve(1000, False, 16)
+
+
+# ---- NToMonoConvolve / Convolver ---------------------------------------------------------------------
+
+def test_matrix_golden_uniform(hb):
+    """config-3 shape scaled down (4 -> 2, FFT 512) against the reference's time-domain sum of MonoConvolves."""
+    irs, xs, want = G["matrix_irs"], G["matrix_x"], G["matrix_y"]
+    fft = int(G["matrix_meta"][0])
+    n_out, n_in, L = irs.shape
+    cv = hb.Convolver(n_in, n_out, False, fft, maxLength=L)
+    cv.setResetOffset(0)
+    for o in range(n_out):
+        for i in range(n_in):
+            assert cv.set(i, o, irs[o, i], L, False) == 0
+    got = np.zeros_like(want)
+    n = xs.shape[1]
+    for pos in range(0, n, 256):
+        yb = np.zeros((n_out, 256), np.float32)
+        cv.process(np.ascontiguousarray(xs[:, pos:pos + 256]), yb, n_in, n_out, 256)
+        got[:, pos:pos + 256] = yb
+    for o in range(n_out):
+        assert ck.rel_rms(got[o], want[o]) <= TOL32
+
+
+def test_convolver_golden_latency_short(hb):
+    """Convolver(3, 2, kLatencyShort) with 17000-tap IRs through set(..., resize=true)."""
+    irs, xs, want = G["conv_irs"], G["conv_x"], G["conv_y"]
+    n_out, n_in, L = irs.shape
+    cv = hb.Convolver(n_in, n_out, hb.kLatencyShort)
+    cv.setResetOffset(0)
+    assert cv.set(0, 0, irs[0, 0], L, False) == hb.CONVOLVE_ERR_MEM_ALLOC_TOO_SMALL      # default room: 16384 taps
+    for o in range(n_out):
+        for i in range(n_in):
+            assert cv.set(i, o, irs[o, i], L, True) == 0
+    got = np.zeros_like(want)
+    for pos in range(0, xs.shape[1], 256):
+        yb = np.zeros((n_out, 256), np.float32)
+        cv.process(np.ascontiguousarray(xs[:, pos:pos + 256]), yb, n_in, n_out, 256)
+        got[:, pos:pos + 256] = yb
+    for o in range(n_out):
+        assert ck.rel_rms(got[o], want[o]) <= TOL32
+
+
+def test_n2m_config3_reduced(hb):
+    """BASELINE config 3 geometry (8 -> 1, FFT 4096) with 16384-tap IRs, against direct convolution."""
+    n_in, B, L = 8, 2048, 16384
+    irs = [ck.synth_ir(L, 100 + i) for i in range(n_in)]
+    xs = [ck.synth_audio(B * 12, 100 + i) for i in range(n_in)]
+    nm = hb.NToMonoConvolve(n_in, L, False, 2 * B)
+    nm.setResetOffset(0)
+    for i in range(n_in):
+        assert nm.set(i, irs[i], L, False) == 0
+    assert nm.set(n_in, irs[0], L, False) == hb.CONVOLVE_ERR_IN_CHAN_OUT_OF_RANGE
+    out = np.zeros(B * 12, np.float32)
+    tmp = np.zeros(B, np.float32)
+    for pos in range(0, B * 12, B):
+        nm.process([x[pos:pos + B] for x in xs], out[pos:pos + B], tmp, B, n_in)
+    truth = sum(ck.direct_convolve_delayed(irs[i], xs[i], B) for i in range(n_in))
+    assert ck.rel_rms(out, truth) <= TOL32
+    # activeInChans < N: the remaining inputs do not contribute (NToMonoConvolve.cpp:41)
+    nm.reset()
+    out2 = np.zeros(B * 12, np.float32)
+    for pos in range(0, B * 12, B):
+        nm.process([x[pos:pos + B] for x in xs], out2[pos:pos + B], tmp, B, 3)
+    truth3 = sum(ck.direct_convolve_delayed(irs[i], xs[i], B) for i in range(3))
+    assert ck.rel_rms(out2, truth3) <= TOL32
+
+
+def test_convolver_parallel_mode_and_double_io(hb):
+    """Convolver(numIO, ...) = independent channels (Convolver.cpp:24-41); double I/O casts through float."""
+    E = hb.ConvolveError
+    K, B, L = 5, 128, 1000
+    cv = hb.Convolver(K, False, 2 * B)
+    cv.setResetOffset(0)
+    irs = [ck.synth_ir(L, 200 + k) for k in range(K)]
+    for k in range(K):
+        assert cv.set(k, k, irs[k].astype(np.float64), L, False) == 0          # double IR overload
+    assert cv.set(1, 0, irs[0], L, False) == E.CONVOLVE_ERR_IN_CHAN_OUT_OF_RANGE
+    assert cv.set(K, K, irs[0], L, False) == E.CONVOLVE_ERR_OUT_CHAN_OUT_OF_RANGE
+    xs = np.stack([ck.synth_audio(B * 20, 200 + k) for k in range(K)]).astype(np.float64)
+    ys = np.zeros_like(xs)
+    cv.process(xs, ys, K, K, xs.shape[1])
+    for k in range(K):
+        assert ck.rel_rms(ys[k], ck.direct_convolve_delayed(irs[k], xs[k], B)) <= TOL32
+    cv.clear(2, 2, False)
+    cv.reset()
+    ys2 = np.zeros_like(xs)
+    cv.process(xs, ys2, K, K, xs.shape[1])
+    assert np.all(ys2[2] == 0) and ck.rel_rms(ys2[0], ys[0]) <= 1e-6
+
+
+def test_matrix_wide_outputs_variants_agree(hb):
+    """64 outputs (the config-4 tile shape: 64 rows x 64 bins per unit) on a small IR; TMA ring and
+    direct-load variants must agree with each other and with direct convolution."""
+    n_in, n_out, B, L = 3, 64, 256, 2000
+    rng = np.random.default_rng(9)
+    irs = (rng.standard_normal((n_out, n_in, L)) * np.exp(-6.9 * np.arange(L) / L)).astype(np.float32)
+    xs = np.stack([ck.synth_audio(B * 16, 300 + i) for i in range(n_in)])
+    res = []
+    for variant in (1, 0):
+        cv = hb.Convolver(n_in, n_out, False, 2 * B, maxLength=L)
+        cv.matrix.tail.set_tuning(0, variant)
+        cv.setResetOffset(0)
+        for o in range(n_out):
+            for i in range(n_in):
+                assert cv.set(i, o, irs[o, i], L, False) == 0
+        ys = np.zeros((n_out, xs.shape[1]), np.float32)
+        cv.process(xs, ys, n_in, n_out, xs.shape[1])
+        res.append(ys)
+    for o in (0, 17, 63):
+        truth = sum(ck.direct_convolve_delayed(irs[o, i], xs[i], B) for i in range(n_in))
+        assert ck.rel_rms(res[0][o], truth) <= TOL32
+    assert ck.rel_rms(res[0], res[1]) <= 1e-6
+
+
+def test_linearity_and_impulse_at_config4_block_size(hb):
+    """size-independent properties at config 4's geometry (FFT 8192, 64 partitions, 8 x 8 slice):
+    an impulse in one input reproduces that column of IRs delayed by B, and the map is linear."""
+    n_in, n_out, B, P = 8, 8, 4096, 64
+    L = B * P
+    rng = np.random.default_rng(10)
+    cv = hb.Convolver(n_in, n_out, False, 2 * B, maxLength=L)
+    cv.setResetOffset(0)
+    irs = {}
+    for o in range(n_out):
+        for i in range(n_in):
+            ir = (rng.standard_normal(L) * np.exp(-6.9 * np.arange(L) / L)).astype(np.float32)
+            irs[o, i] = ir
+            assert cv.set(i, o, ir, L, False) == 0
+    n = L + 2 * B
+    xs = np.zeros((n_in, n), np.float32)
+    xs[5, 0] = 1.0
+    ys = np.zeros((n_out, n), np.float32)
+    cv.process(xs, ys, n_in, n_out, n)
+    for o in range(n_out):
+        assert np.allclose(ys[o, :B], 0, atol=1e-6)
+        assert ck.rel_rms(ys[o, B:B + L], irs[o, 5]) <= TOL32
+    cv.reset()
+    xa = np.stack([ck.synth_audio(4 * B, 400 + i) for i in range(n_in)])
+    xb = np.stack([ck.synth_audio(4 * B, 500 + i) for i in range(n_in)])
+    outs = []
+    for sig in (xa, xb, (xa + 0.5 * xb).astype(np.float32)):
+        cv.reset()
+        y = np.zeros((n_out, 4 * B), np.float32)
+        cv.process(sig, y, n_in, n_out, 4 * B)
+        outs.append(y.astype(np.float64))
+    assert ck.rel_rms(outs[2], outs[0] + 0.5 * outs[1]) <= TOL32
