@@ -49,6 +49,8 @@ SIGNATURES = {
     "hb_conv_process_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
     "hb_conv_set_tuning": (C.c_int, [V, C.c_int, C.c_int]),
     "hb_conv_bytes_per_hop": (C.c_uint64, [V]),
+    "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
+    "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 

@@ -108,6 +108,15 @@ class _Engine:
     def set_tuning(self, ctas_per_sm=0, variant=1):
         return _abi.check(_abi.lib().hb_conv_set_tuning(self._h, int(ctas_per_sm), int(variant)))
 
+    def set_profiling(self, enable=True):
+        return _abi.check(_abi.lib().hb_conv_set_profiling(self._h, 1 if enable else 0))
+
+    def get_profile(self):
+        """(ms forward FFTs, ms multiply-accumulate, ms inverse FFTs, hops) since profiling was enabled."""
+        a, b, c_, h = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+        _abi.check(_abi.lib().hb_conv_get_profile(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(h)))
+        return a.value, b.value, c_.value, int(h.value)
+
     def process(self, in_rows, out_rows, n, accumulate=False):
         """in_rows / out_rows: lists of contiguous 1-D arrays of the engine dtype (>= n samples)."""
         ip = (C.c_void_p * len(in_rows))(*[r.ctypes.data for r in in_rows])

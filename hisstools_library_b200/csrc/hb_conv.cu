@@ -89,6 +89,13 @@ struct hb_conv
     size_t cmac_smem = 0;
     std::mutex lock;
 
+    // optional per-kernel timing (hb_conv_set_profiling): 4 events per hop on the launching stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    double prof_ms[3] = {0, 0, 0};  // forward FFTs, multiply-accumulate, inverse FFTs
+    uint64_t prof_hops = 0;
+
     size_t esize() const { return dtype_size(dtype); }
     size_t pairs() const { return size_t(groups) * ins * outs; }
 };
@@ -411,6 +418,42 @@ int do_reset(hb_conv *c, cudaStream_t st)
     return HB_OK;
 }
 
+// fold the recorded event intervals into prof_ms (synchronises on the last recorded event)
+int drain_profile(hb_conv *c)
+{
+    if (!c->ev_used) return HB_OK;
+    HB_CUDA(cudaEventSynchronize(c->ev[c->ev_used - 1]));
+    for (size_t k = 0; k + 3 < c->ev_used; k += 4)
+    {
+        for (int j = 0; j < 3; j++)
+        {
+            float ms = 0.f;
+            HB_CUDA(cudaEventElapsedTime(&ms, c->ev[k + j], c->ev[k + j + 1]));
+            c->prof_ms[j] += ms;
+        }
+        c->prof_hops++;
+    }
+    c->ev_used = 0;
+    return HB_OK;
+}
+
+int profile_mark(hb_conv *c, cudaStream_t st)
+{
+    if (c->ev_used == c->ev.size())
+    {
+        if (c->ev.size() >= 4 * 256) { int rc = drain_profile(c); if (rc) return rc; }
+        else
+            for (int k = 0; k < 4; k++)
+            {
+                cudaEvent_t e;
+                HB_CUDA(cudaEventCreate(&e));
+                c->ev.push_back(e);
+            }
+    }
+    HB_CUDA(cudaEventRecord(c->ev[c->ev_used++], st));
+    return HB_OK;
+}
+
 // core of process: device rows in, device rows out, everything enqueued on st
 template <class T>
 int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
@@ -447,9 +490,14 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
     {
         // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
         c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+        const bool prof = c->profiling;
+        if (prof && (rc = profile_mark(c, st))) return rc;
         if ((rc = launch_fwd<T>(c, xin, c->xin_ld, h * B, st))) return rc;
+        if (prof && (rc = profile_mark(c, st))) return rc;
         if ((rc = launch_cmac<T>(c, st))) return rc;
+        if (prof && (rc = profile_mark(c, st))) return rc;
         if ((rc = launch_inv<T>(c, yout, c->yout_ld, (h + 1) * B, st))) return rc;
+        if (prof && (rc = profile_mark(c, st))) return rc;
     }
     if ((rc = launch_rows<T>(d_out, out_ld, yout + rw, c->yout_ld, n, rows_out, accumulate, st))) return rc;
 
@@ -549,6 +597,7 @@ extern "C" void hb_conv_destroy(hb_conv *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_device(c);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -753,6 +802,31 @@ extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)
     c->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : (variant == 1 ? 1 : 2);
     c->variant = variant;
     c->need_reset = true;           // partial-segment geometry depends on the grid
+    return HB_OK;
+}
+
+extern "C" int hb_conv_set_profiling(hb_conv *c, int enable)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    if ((rc = drain_profile(c))) return rc;
+    c->profiling = enable != 0;
+    c->prof_ms[0] = c->prof_ms[1] = c->prof_ms[2] = 0;
+    c->prof_hops = 0;
+    return HB_OK;
+}
+
+extern "C" int hb_conv_get_profile(hb_conv *c, double *ms_forward, double *ms_cmac, double *ms_inverse, uint64_t *hops)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    if ((rc = drain_profile(c))) return rc;
+    if (ms_forward) *ms_forward = c->prof_ms[0];
+    if (ms_cmac) *ms_cmac = c->prof_ms[1];
+    if (ms_inverse) *ms_inverse = c->prof_ms[2];
+    if (hops) *hops = c->prof_hops;
     return HB_OK;
 }
 

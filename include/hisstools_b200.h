@@ -146,8 +146,12 @@ int hb_conv_process_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_o
 int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant);
 /* algorithmic bytes one hop moves (IR spectra + FDL + time-domain I/O) */
 uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
-/* device time in ms of the most recent hop's multiply-accumulate kernel is not measured here:
- * bench.py brackets hb_conv_process_dev with CUDA events on the stream it passes. */
+/* per-kernel device timing: while enabled, every hop records CUDA events around its three kernels on
+ * the launching stream.  hb_conv_get_profile waits for the recorded hops and returns the summed
+ * milliseconds of the forward-FFT, multiply-accumulate and inverse-FFT kernels and the hop count
+ * since profiling was enabled (bench.py's roofline figure). */
+int hb_conv_set_profiling(hb_conv *c, int enable);
+int hb_conv_get_profile(hb_conv *c, double *ms_forward, double *ms_cmac, double *ms_inverse, uint64_t *hops);
 
 #ifdef __cplusplus
 }
