@@ -181,10 +181,14 @@ def reference_rate(workload, steps, warmup, hops_per_step, budget_s=None):
             else "full workload"
         cleanup = lambda: lib.ref_matrix_destroy(m)
         kind = "reference"
+    # the reference only multiplies the partitions whose FDL slot has been filled (mValidPartitions,
+    # PartitionedConvolve.cpp:285,373): warm up until the delay line is full, or early steps are cheap
+    P = (taps + B - 1) // B
+    warmup = max(warmup, (P + hops_per_step) // hops_per_step + 1)
     if budget_s is not None:
-        t1 = run(1, 2) / 2
+        t1 = run(warmup, 2) / 2
         steps = int(max(3, min(400, budget_s / max(t1, 1e-6))))
-        warmup = 1
+        warmup = 0
     secs = run(warmup, steps)
     cleanup()
     return {"value": rows * n * steps / secs / 1e6, "unit": UNIT, "cores": use, "kind": kind,
@@ -251,7 +255,14 @@ def run_ours(args):
     n = B * args.hops
     P = (taps + B - 1) // B
 
-    eng = _Engine(ndt, l_groups, l_ins, outs, 2 * B, taps, 0, 0, local)
+    sharded = None
+    if mode == "inputs":
+        # the public multi-GPU class: inputs sharded over the ranks, reduce-scatter of partial outputs
+        from hisstools_library_b200.sharded import ShardedConvolver
+        sharded = ShardedConvolver(ins, outs, False, 2 * B, maxLength=taps, dtype=ndt, device=local)
+        eng = sharded.engine.m.tail
+    else:
+        eng = _Engine(ndt, l_groups, l_ins, outs, 2 * B, taps, 0, 0, local)
     eng.set_reset_offset(0)
     if args.variant is not None:
         eng.set_tuning(args.ctas_per_sm, args.variant)
@@ -275,13 +286,16 @@ def run_ours(args):
     y_part = torch.zeros(rows_out, n, device=dev, dtype=tdt)
     shard_rows = rows_out // world if mode == "inputs" else rows_out
     y_shard = torch.zeros(shard_rows, n, device=dev, dtype=tdt) if mode == "inputs" else y_part
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would mean "the engine's own stream" to the C ABI
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     def step(k):
         x = x_pool[k % n_pool]
-        eng.process_device(x.data_ptr(), n, y_part.data_ptr(), n, n, False, stream.cuda_stream)
-        if mode == "inputs":
-            dist.reduce_scatter_tensor(y_shard, y_part, op=dist.ReduceOp.SUM)
+        if sharded is not None:
+            sharded.process_device(x, y_shard, n, stream.cuda_stream)
+        else:
+            eng.process_device(x.data_ptr(), n, y_part.data_ptr(), n, n, False, stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -346,9 +360,10 @@ def run_ours(args):
 
         def e2e_step(k):
             xd.copy_(xh[k % n_pool], non_blocking=True)
-            eng.process_device(xd.data_ptr(), n, y_part.data_ptr(), n, n, False, stream.cuda_stream)
-            if mode == "inputs":
-                dist.reduce_scatter_tensor(y_shard, y_part, op=dist.ReduceOp.SUM)
+            if sharded is not None:
+                sharded.process_device(xd, y_shard, n, stream.cuda_stream)
+            else:
+                eng.process_device(xd.data_ptr(), n, y_part.data_ptr(), n, n, False, stream.cuda_stream)
             yh.copy_(y_shard, non_blocking=True)
             torch.cuda.synchronize()
         e2e_step(0)
@@ -392,12 +407,15 @@ def run_ours(args):
                                  if bytes_per_launch > 256e6 else "working set %.1f MiB is L2-resident (not an HBM-roofline case)" % (bytes_per_launch / 2 ** 20),
                            "collective": "nccl reduce_scatter of partial output blocks" if mode == "inputs" else "none"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "api": "hb_conv_process (host pointers)" if world == 1 else "pinned H2D + hb_conv_process_dev + reduce_scatter + D2H"},
+                        "api": "hb_conv_process (host pointers)" if world == 1 else "pinned H2D + ShardedConvolver.process_device (hb_matrix_process_dev + NCCL reduce_scatter) + D2H"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    eng.close()
+    if sharded is not None:
+        sharded.close()
+    else:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

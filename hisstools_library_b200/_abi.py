@@ -10,7 +10,7 @@ import os
 from . import build as _build
 
 HB_F32, HB_F64 = 0, 1
-HB_OK, HB_ERR_CUDA, HB_ERR_BAD_ARG, HB_ERR_UNSUPPORTED, HB_ERR_NO_IR = 0, -1, -2, -3, -4
+HB_OK, HB_ERR_CUDA, HB_ERR_BAD_ARG, HB_ERR_UNSUPPORTED, HB_ERR_NO_IR, HB_ERR_BUSY = 0, -1, -2, -3, -4, -5
 
 UP = C.c_size_t        # uintptr_t
 IP = C.c_ssize_t       # intptr_t
@@ -49,6 +49,18 @@ SIGNATURES = {
     "hb_conv_process_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
     "hb_conv_set_tuning": (C.c_int, [V, C.c_int, C.c_int]),
     "hb_conv_bytes_per_hop": (C.c_uint64, [V]),
+    "hb_matrix_create": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, U32, U32, U32, U32, C.c_int]),
+    "hb_matrix_create_latency": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, C.c_int]),
+    "hb_matrix_destroy": (None, [V]),
+    "hb_matrix_set_reset_offset": (C.c_int, [V, IP]),
+    "hb_matrix_resize": (C.c_int, [V, U32, U32, U32, UP]),
+    "hb_matrix_set": (C.c_int, [V, U32, U32, U32, V, C.c_int, UP, C.c_int]),
+    "hb_matrix_reset": (C.c_int, [V]),
+    "hb_matrix_process": (C.c_int, [V, C.POINTER(V), C.POINTER(V), UP, C.c_int]),
+    "hb_matrix_process_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
+    "hb_matrix_parts": (U32, [V]),
+    "hb_matrix_part": (V, [V, U32]),
+    "hb_matrix_head_taps": (U32, [V]),
     "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
     "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
@@ -84,7 +96,7 @@ def last_error():
 
 
 def check(code):
-    """Pass reference ConvolveError codes (>= 0) through; raise on library failures (< 0, except NO_IR)."""
-    if code < 0 and code != HB_ERR_NO_IR:
+    """Pass reference ConvolveError codes (>= 0) through; raise on library failures (< 0, except NO_IR / BUSY)."""
+    if code < 0 and code not in (HB_ERR_NO_IR, HB_ERR_BUSY):
         raise HissError(code, last_error())
     return code

@@ -36,19 +36,24 @@ def _hb_dtype(dtype):
 class _Engine:
     """One hb_conv handle: `groups` banks of an ins x outs matrix, uniform partitions."""
 
-    def __init__(self, dtype, groups, ins, outs, max_fft, max_length, offset, length, device=0):
+    def __init__(self, dtype, groups, ins, outs, max_fft, max_length, offset, length, device=0, borrowed=None):
         self.dtype = np.dtype(dtype)
         self.groups, self.ins, self.outs = int(groups), int(ins), int(outs)
         self.device = device
+        self._owned = borrowed is None
+        if borrowed is not None:
+            self._h = C.c_void_p(borrowed)          # a part of an hb_matrix: the matrix owns it
+            self.ctor_error = 0
+            return
         self._h = C.c_void_p()
         code = _abi.lib().hb_conv_create(C.byref(self._h), _hb_dtype(dtype), self.groups, self.ins, self.outs,
                                          int(max_fft), int(max_length), int(offset), int(length), int(device))
         self.ctor_error = _abi.check(code)
 
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             _abi.lib().hb_conv_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -236,104 +241,70 @@ _LATENCY_SIZES = {
 
 
 class _Matrix:
-    """groups x (ins x outs) convolution matrix with one partition scheme: the shared machinery
-    behind MonoConvolve, NToMonoConvolve and Convolver."""
+    """groups x (ins x outs) convolution matrix with one partition scheme: one hb_matrix handle, the
+    shared machinery behind MonoConvolve, NToMonoConvolve and Convolver (host logic in csrc/hb_matrix.cu)."""
 
     def __init__(self, groups, ins, outs, maxLength, scheme, dtype, device):
         zero, A, B, C_, D = scheme
         self.dtype = np.dtype(dtype)
         self.groups, self.ins, self.outs = groups, ins, outs
-        self.sizes, self.head_taps, fixed, tail = partition_scheme(zero, A, B, C_, D)
-        if self.head_taps:
-            raise NotImplementedError("zero-latency time-domain head (TimeDomainConvolve) is not built yet (SURVEY 8f-2)")
-        self.engines = [_Engine(dtype, groups, ins, outs, fft, taps, off, taps, device) for fft, off, taps in fixed]
-        self.tail_fft, self.tail_offset = tail
-        # allocator of MonoConvolve.cpp:247-250: PartitionedConvolve(largest, max(size, largest) - offset, offset, 0)
-        self.tail = _Engine(dtype, groups, ins, outs, self.tail_fft, max(int(maxLength), self.tail_fft) - self.tail_offset,
-                            self.tail_offset, 0, device)
-        self.engines.append(self.tail)
-        shape = (groups, outs, ins)
-        self.pair_size = np.full(shape, int(maxLength), dtype=np.int64)     # part4.getSize()
-        self.pair_len = np.zeros(shape, dtype=np.int64)                     # mLength
-        self._need_reset_offsets(0)
-
-    def _need_reset_offsets(self, offset):
-        # staggered phases of MonoConvolve::setResetOffset (MonoConvolve.cpp:85-98); a negative
-        # (random) request selects phase 0 so that runs are reproducible
-        if offset < 0:
-            offset = 0
-        n = len(self.sizes)
-        fixed = self.engines[:-1]
-        sizes_for_fixed = self.sizes[n - 1 - len(fixed):n - 1]
-        for e, s in zip(fixed, sizes_for_fixed):
-            e.set_reset_offset(offset + (s >> 3))
-        self.tail.set_reset_offset(offset)
+        self.sizes, _, _, _ = partition_scheme(zero, A, B, C_, D)       # raises RuntimeError like the reference
+        self._h = C.c_void_p()
+        code = _abi.lib().hb_matrix_create(C.byref(self._h), _hb_dtype(dtype), groups, ins, outs, int(maxLength),
+                                           1 if zero else 0, int(A), int(B), int(C_), int(D), int(device))
+        _abi.check(code)
+        lib = _abi.lib()
+        self.head_taps = int(lib.hb_matrix_head_taps(self._h))
+        self.engines = [_Engine(dtype, groups, ins, outs, 0, 0, 0, 0, device, borrowed=lib.hb_matrix_part(self._h, k))
+                        for k in range(lib.hb_matrix_parts(self._h))]
+        self.tail = self.engines[-1]
 
     def setResetOffset(self, offset=-1):
-        self._need_reset_offsets(int(offset))
-
-    def _grow_tail(self, size):
-        need = max(int(size), self.tail_fft) - self.tail_offset
-        if need > self.tail.max_length:
-            return self.tail.resize(need)
-        return 0
+        _abi.check(_abi.lib().hb_matrix_set_reset_offset(self._h, int(offset)))
 
     def resize(self, g, i, o, length):
         """MonoConvolve::resize (MonoConvolve.cpp:100-110): drops the pair's IR, sets its allocation."""
-        self.pair_len[g, o, i] = 0
-        code = self._grow_tail(length)
-        for e in self.engines:
-            e.set_ir(g, i, o, None)
-        if code:
-            return _ERR.CONVOLVE_ERR_MEM_UNAVAILABLE
-        self.pair_size[g, o, i] = int(length)
-        return _ERR.CONVOLVE_ERR_NONE
+        return _ERR(_abi.check(_abi.lib().hb_matrix_resize(self._h, g, i, o, int(length))))
 
     def set(self, g, i, o, ir, length, requestResize):
         """MonoConvolve::set (MonoConvolve.cpp:118-140)."""
-        length = 0 if ir is None else int(length)
-        self.pair_len[g, o, i] = 0
-        if requestResize and length != self.pair_size[g, o, i]:
-            if self._grow_tail(length):
-                for e in self.engines:
-                    e.set_ir(g, i, o, None)
-                return _ERR.CONVOLVE_ERR_MEM_UNAVAILABLE if length else _ERR.CONVOLVE_ERR_NONE
-            self.pair_size[g, o, i] = length
-        size = int(self.pair_size[g, o, i])
-        # process() ignores a pair whose IR is longer than its allocation (MonoConvolve.cpp:183)
-        active = length and length <= size
-        for e in self.engines:
-            e.set_ir(g, i, o, ir if active else None, length if active else 0)
-        self.pair_len[g, o, i] = length
-        return _ERR.CONVOLVE_ERR_MEM_ALLOC_TOO_SMALL if length > size else _ERR.CONVOLVE_ERR_NONE
+        if ir is None:
+            return _ERR(_abi.check(_abi.lib().hb_matrix_set(self._h, g, i, o, None, _abi.HB_F32, 0, 1 if requestResize else 0)))
+        ir = np.ascontiguousarray(ir)
+        if ir.dtype not in (np.float32, np.float64):
+            ir = ir.astype(self.dtype)
+        if int(length) > ir.size:
+            raise ValueError("length exceeds the impulse response array")
+        return _ERR(_abi.check(_abi.lib().hb_matrix_set(self._h, g, i, o, ir.ctypes.data_as(C.c_void_p), _hb_dtype(ir.dtype),
+                                                        int(length), 1 if requestResize else 0)))
 
     def reset(self):
-        for e in self.engines:
-            e.reset()
+        _abi.check(_abi.lib().hb_matrix_reset(self._h))
         return _ERR.CONVOLVE_ERR_NONE
 
     def process(self, in_rows, out_rows, n, accumulate):
-        """Sum of all parts into out_rows; returns True when anything was written."""
-        wrote = bool(accumulate)
-        any_out = False
-        for e in self.engines:
-            if e.process(in_rows, out_rows, n, wrote) == _abi.HB_OK:
-                wrote = True
-                any_out = True
-        return any_out
+        """Sum of all parts into out_rows (None rows: silent input / unwanted output); True when written."""
+        ip = (C.c_void_p * len(in_rows))(*[None if r is None else r.ctypes.data for r in in_rows])
+        op = (C.c_void_p * len(out_rows))(*[None if r is None else r.ctypes.data for r in out_rows])
+        return _abi.check(_abi.lib().hb_matrix_process(self._h, ip, op, int(n), 1 if accumulate else 0)) == _abi.HB_OK
 
     def process_device(self, in_ptr, in_ld, out_ptr, out_ld, n, accumulate=False, stream=0):
-        wrote = bool(accumulate)
-        any_out = False
-        for e in self.engines:
-            if e.process_device(in_ptr, in_ld, out_ptr, out_ld, n, wrote, stream) == _abi.HB_OK:
-                wrote = True
-                any_out = True
-        return any_out
+        code = _abi.lib().hb_matrix_process_dev(self._h, C.c_void_p(in_ptr), int(in_ld), C.c_void_p(out_ptr), int(out_ld),
+                                                int(n), 1 if accumulate else 0, C.c_void_p(stream))
+        return _abi.check(code) == _abi.HB_OK
 
     def close(self):
-        for e in self.engines:
-            e.close()
+        if self._h:
+            for e in self.engines:
+                e.close()
+            _abi.lib().hb_matrix_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _scheme(args):
@@ -422,9 +393,7 @@ class NToMonoConvolve:
         n = int(numSamples)
         active = min(int(activeInChans), self.mNumInChans)
         rin, _ = _rows(ins, active, n, self.dtype)
-        if active < self.mNumInChans:
-            z = np.zeros(n, self.dtype)
-            rin = rin + [z] * (self.mNumInChans - active)
+        rin = rin + [None] * (self.mNumInChans - active)
         rout, back = _rows([out], 1, n, self.dtype, writable=True)
         rout[0][:n] = 0
         self._m.process(rin, rout, n, True)
@@ -517,16 +486,12 @@ class Convolver:
         n = int(numSamples)
         numIns = min(int(numIns), self.mNumIns)
         numOuts = min(int(numOuts), self.mNumOuts)
-        zero = None
         rin, _ = _rows(ins, numIns, n, self.dtype)
-        if numIns < self.mNumIns:
-            zero = np.zeros(n, self.dtype)
-            rin = rin + [zero] * (self.mNumIns - numIns)
+        rin = rin + [None] * (self.mNumIns - numIns)
         rout, back = _rows(outs, numOuts, n, self.dtype, writable=True)
-        if numOuts < self.mNumOuts:
-            rout = rout + [np.zeros(n, self.dtype) for _ in range(self.mNumOuts - numOuts)]
         for r in rout:
             r[:n] = 0
+        rout = rout + [None] * (self.mNumOuts - numOuts)
         self._m.process(rin, rout, n, True)
         for t, a in back:
             a[:n] = t

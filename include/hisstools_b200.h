@@ -37,7 +37,8 @@ typedef enum hb_status
     HB_ERR_CUDA = -1,          /* no device / CUDA runtime failure (see hb_last_error) */
     HB_ERR_BAD_ARG = -2,
     HB_ERR_UNSUPPORTED = -3,   /* size outside what the library implements */
-    HB_ERR_NO_IR = -4          /* process() on an object with no impulse response: outputs untouched */
+    HB_ERR_NO_IR = -4,         /* process() on an object with no impulse response: outputs untouched */
+    HB_ERR_BUSY = -5           /* process() while set()/resize() holds the object: block skipped, outputs untouched */
 } hb_status;
 
 /* last CUDA / argument error text of the calling thread ("" if none) */
@@ -152,6 +153,45 @@ uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
  * since profiling was enabled (bench.py's roofline figure). */
 int hb_conv_set_profiling(hb_conv *c, int enable);
 int hb_conv_get_profile(hb_conv *c, double *ms_forward, double *ms_cmac, double *ms_inverse, uint64_t *hops);
+
+/* ---------------------------------------------------------------------------------------------
+ * Non-uniform partition scheme for a whole channel matrix -- what MonoConvolve (MonoConvolve.h:30-48)
+ * is for one pair, for `groups` banks of ins x outs pairs at once.  This is the object the C++
+ * classes MonoConvolve (1x1), NToMonoConvolve (N x 1) and Convolver (N x M, or K parallel banks of
+ * 1x1) under include/HIRT_Multichannel_Convolution forward to.
+ *   scheme: a direct-form zero-latency head of A/2 taps when zero_latency (TimeDomainConvolve.cpp:69-163),
+ *   fixed parts of FFT size A, B, C covering (next - size)/2 taps each and a resizable tail of the
+ *   largest size (MonoConvolve.cpp:203-258).  Net delay: 0 with zero_latency, A/2 otherwise.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hb_matrix hb_matrix;
+
+/* MonoConvolve(maxLength, zeroLatency, A, B, C, D): MonoConvolve.cpp:36-45.  An invalid size list
+ * (the reference throws std::runtime_error, :212,229) returns HB_ERR_BAD_ARG. */
+int hb_matrix_create(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                     int zero_latency, uint32_t A, uint32_t B, uint32_t C, uint32_t D, int device);
+/* MonoConvolve(maxLength, LatencyMode): MonoConvolve.cpp:18-32; latency_mode 0 zero, 1 short, 2 medium (MonoConvolve.h:14-19) */
+int hb_matrix_create_latency(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                             int latency_mode, int device);
+void hb_matrix_destroy(hb_matrix *m);
+/* MonoConvolve::setResetOffset: MonoConvolve.cpp:80-98 (staggered per part; negative selects phase 0) */
+int hb_matrix_set_reset_offset(hb_matrix *m, intptr_t offset);
+/* MonoConvolve::resize / set / reset for pair (group, in, out): MonoConvolve.cpp:100-152.  Return the
+ * reference ConvolveError (0, 3, 4) or a negative hb_status.  set/resize block process (MemorySwap.h:174-178). */
+int hb_matrix_resize(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out, uintptr_t length);
+int hb_matrix_set(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length, int request_resize);
+int hb_matrix_reset(hb_matrix *m);
+/* MonoConvolve::process / NToMonoConvolve::process / Convolver::process (MonoConvolve.cpp:179-201,
+ * NToMonoConvolve.cpp:35-43, Convolver.cpp:138-154): ins = groups*ins planar host rows (NULL row =
+ * inactive input, silence), outs = groups*outs planar host rows (NULL row = not wanted).
+ * HB_OK: outs written (accumulate != 0: added to).  HB_ERR_NO_IR: nothing loaded, outs untouched.
+ * HB_ERR_BUSY: set/resize in progress on another thread, block skipped (MonoConvolve.cpp:181-183). */
+int hb_matrix_process(hb_matrix *m, const void *const *ins, void *const *outs, uintptr_t num_samples, int accumulate);
+int hb_matrix_process_dev(hb_matrix *m, const void *d_in, uintptr_t in_ld, void *d_out, uintptr_t out_ld,
+                          uintptr_t num_samples, int accumulate, void *stream);
+/* introspection: the uniform engines behind the scheme (borrowed handles; the tail is the last) */
+uint32_t hb_matrix_parts(const hb_matrix *m);
+hb_conv *hb_matrix_part(hb_matrix *m, uint32_t index);
+uint32_t hb_matrix_head_taps(const hb_matrix *m);
 
 #ifdef __cplusplus
 }

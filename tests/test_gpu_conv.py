@@ -183,9 +183,9 @@ def test_mono_config1_against_reference(hb):
     assert ck.rel_rms(got, ck.direct_convolve_delayed(ir, x, 512)) <= TOL32
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_mono_latency_modes_golden(hb, mode):
-    """shipped kLatencyShort / kLatencyMedium schemes (MonoConvolve.cpp:28-30): net delay 128 / 512."""
+    """shipped kLatencyZero / Short / Medium schemes (MonoConvolve.cpp:28-30): net delay 0 / 128 / 512."""
     ir, x, want = G["mono_ir"], G["mono_x"], G["mono_y_mode%d" % mode]
     mc = hb.MonoConvolve(len(ir), hb.LatencyMode(mode))
     mc.setResetOffset(0)
@@ -364,3 +364,60 @@ def test_linearity_and_impulse_at_config4_block_size(hb):
         cv.process(sig, y, n_in, n_out, 4 * B)
         outs.append(y.astype(np.float64))
     assert ck.rel_rms(outs[2], outs[0] + 0.5 * outs[1]) <= TOL32
+
+
+def test_convolver_zero_latency_head(hb):
+    """Convolver(2, 2, kLatencyZero): the direct-form head (TimeDomainConvolve.cpp:69-163) plus the four
+    FFT parts give the undelayed convolution for any call sizes, including calls shorter than the head."""
+    n_in, n_out, L = 2, 2, 9000
+    irs = [[ck.synth_ir(L, 700 + 10 * o + i) for i in range(n_in)] for o in range(n_out)]
+    xs = np.stack([ck.synth_audio(20000, 700 + i) for i in range(n_in)])
+    cv = hb.Convolver(n_in, n_out, hb.kLatencyZero)
+    cv.setResetOffset(0)
+    for o in range(n_out):
+        for i in range(n_in):
+            assert cv.set(i, o, irs[o][i], L, False) == 0
+    got = np.zeros((n_out, xs.shape[1]), np.float32)
+    pos, k = 0, 0
+    sizes = [64, 1, 100, 128, 300, 4096, 17]
+    while pos < xs.shape[1]:
+        n = min(sizes[k % len(sizes)], xs.shape[1] - pos)
+        yb = np.zeros((n_out, n), np.float32)
+        cv.process(np.ascontiguousarray(xs[:, pos:pos + n]), yb, n_in, n_out, n)
+        got[:, pos:pos + n] = yb
+        pos += n
+        k += 1
+    for o in range(n_out):
+        truth = sum(ck.direct_convolve_delayed(irs[o][i], xs[i], 0) for i in range(n_in))
+        assert ck.rel_rms(got[o], truth) <= TOL32
+    # an IR shorter than the head lives in the head alone
+    mc = hb.MonoConvolve(100, hb.kLatencyZero)
+    short = ck.synth_ir(100, 720)
+    assert mc.set(short, 100, False) == 0
+    y = np.zeros(5000, np.float32)
+    for pos in range(0, 5000, 50):
+        mc.process(xs[0][pos:pos + 50], np.zeros(50, np.float32), y[pos:pos + 50], 50)
+    assert ck.rel_rms(y, ck.direct_convolve_delayed(short, xs[0][:5000], 0)) <= TOL32
+
+
+def test_mono_zero_latency_against_oracle(hb):
+    """custom zero-latency scheme MonoConvolve(L, true, 64, 512) against the plain-C oracle's MonoConvolve."""
+    lib = ck.oracle()
+    L = 3000
+    ir = ck.synth_ir(L, 730)
+    x = ck.synth_audio(6000, 730)
+    h = lib.orc_mono_create_f32(L, 1, 64, 512, 0, 0)
+    assert lib.orc_mono_set_f32(h, ck.fptr(ir), L, 0) == 0
+    want = np.zeros_like(x)
+    for pos in range(0, len(x), 96):
+        n = min(96, len(x) - pos)
+        lib.orc_mono_process_f32(h, ck.fptr(x[pos:]), ck.fptr(want[pos:]), n, 0)
+    lib.orc_mono_destroy_f32(h)
+    mc = hb.MonoConvolve(L, True, 64, 512)
+    mc.setResetOffset(0)
+    assert mc.set(ir, L, False) == 0
+    got = np.zeros_like(x)
+    for pos in range(0, len(x), 96):
+        n = min(96, len(x) - pos)
+        mc.process(x[pos:pos + n], np.zeros(n, np.float32), got[pos:pos + n], n)
+    assert ck.rel_rms(got, want) <= TOL32
