@@ -11,3 +11,4 @@ from .fft import (Split, Setup, hisstools_create_setup, hisstools_destroy_setup,
                   hisstools_ifft, hisstools_rfft, hisstools_rifft, hisstools_zip, hisstools_unzip,
                   hisstools_unzip_zero)
 from .convolve import PartitionedConvolve, MonoConvolve, NToMonoConvolve, Convolver, partition_scheme   # noqa: F401
+from .spectral import spectral_processor, EdgeMode                                                   # noqa: F401

@@ -47,6 +47,9 @@ SIGNATURES = {
     "hb_conv_fft_size": (UP, [V]),
     "hb_conv_process": (C.c_int, [V, C.POINTER(V), C.POINTER(V), UP, C.c_int]),
     "hb_conv_process_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
+    "hb_conv_shard_export": (C.c_int, [V, U32, U32, V]),
+    "hb_conv_shard_attach": (C.c_int, [V, V]),
+    "hb_conv_process_shard_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
     "hb_conv_set_tuning": (C.c_int, [V, C.c_int, C.c_int]),
     "hb_conv_bytes_per_hop": (C.c_uint64, [V]),
     "hb_matrix_create": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, U32, U32, U32, U32, C.c_int]),
@@ -61,6 +64,12 @@ SIGNATURES = {
     "hb_matrix_parts": (U32, [V]),
     "hb_matrix_part": (V, [V, U32]),
     "hb_matrix_head_taps": (U32, [V]),
+    "hb_spectral_create": (C.c_int, [C.POINTER(V), C.c_int, UP, C.c_int]),
+    "hb_spectral_destroy": (None, [V]),
+    "hb_spectral_set_max_fft_size": (C.c_int, [V, UP]),
+    "hb_spectral_max_fft_size": (UP, [V]),
+    "hb_spectral_convolved_size": (UP, [V, UP, UP, C.c_int]),
+    "hb_spectral_convolve": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
     "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }

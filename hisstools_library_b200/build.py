@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libhisstools_b200.so"
-SOURCES = ["hb_fft.cu", "hb_conv.cu", "hb_matrix.cu"]
+SOURCES = ["hb_fft.cu", "hb_conv.cu", "hb_matrix.cu", "hb_spectral.cu"]
 HEADERS = ["hb_common.cuh", "hb_fft_core.cuh", "hb_fft_block.cuh", "hb_conv_kernels.cuh",
            os.path.join("..", "..", "include", "hisstools_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -113,6 +113,20 @@ class _Engine:
     def set_tuning(self, ctas_per_sm=0, variant=1):
         return _abi.check(_abi.lib().hb_conv_set_tuning(self._h, int(ctas_per_sm), int(variant)))
 
+    # fused multi-GPU exchange (hb_conv_shard_*)
+    def shard_export(self, world, rank):
+        buf = C.create_string_buffer(64)
+        _abi.check(_abi.lib().hb_conv_shard_export(self._h, int(world), int(rank), buf))
+        return buf.raw
+
+    def shard_attach(self, handles):
+        blob = b"".join(handles)
+        _abi.check(_abi.lib().hb_conv_shard_attach(self._h, C.c_char_p(blob)))
+
+    def process_shard_device(self, in_ptr, in_ld, out_ptr, out_ld, n, accumulate=False, stream=0):
+        return _abi.check(_abi.lib().hb_conv_process_shard_dev(self._h, C.c_void_p(in_ptr), int(in_ld), C.c_void_p(out_ptr), int(out_ld),
+                                                               int(n), 1 if accumulate else 0, C.c_void_p(stream)))
+
     def set_profiling(self, enable=True):
         return _abi.check(_abi.lib().hb_conv_set_profiling(self._h, 1 if enable else 0))
 

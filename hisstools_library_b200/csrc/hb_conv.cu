@@ -89,6 +89,27 @@ struct hb_conv
     size_t cmac_smem = 0;
     std::mutex lock;
 
+    // deferred host-pointer path of hb_conv_process: the block finished by a hop is fetched to pinned host
+    // memory while the caller is away; a later call only waits on an event that completed long ago
+    bool deferred = true;
+    PinnedBuf h_blk[2], h_inq[2];
+    DevBuf d_inq[2];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;      // copies run beside the hop kernels, not between them
+    cudaEvent_t ev_blk[2] = {nullptr, nullptr}, ev_inq[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool done_pending[2] = {false, false};
+    bool blk_pending[2] = {false, false}, inq_pending[2] = {false, false};
+    int blk_cur = 0, inq_cur = 0;
+    bool blk_valid = false;         // h_blk[blk_cur] holds the last completed block (outputs are read from it at offset rw)
+    size_t blk_B = 0;
+
+    // fused multi-GPU exchange (hb_conv_shard_*): this rank's inbox and the peers' inboxes opened over CUDA IPC
+    uint32_t shard_world = 0, shard_rank = 0;
+    void *d_inbox = nullptr;
+    size_t inbox_data_bytes = 0, inbox_slot = 0;
+    void *peer_base[HB_MAX_WORLD] = {};
+    bool peers_attached = false;
+    uint32_t hop_seq = 0, parity_uses[2] = {0, 0};
+
     // optional per-kernel timing (hb_conv_set_profiling): 4 events per hop on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> ev;
@@ -139,6 +160,9 @@ void plan_geometry(hb_conv *c)
     g.tiles = g.groups * g.n_ot * g.n_bt;
     g.U = uint64_t(g.tiles) * g.upt;
     uint64_t want = uint64_t(c->sm_count) * (c->variant == 1 ? 1 : std::max(1, c->ctas_per_sm));
+    // every tile is summed by ONE inverse-FFT CTA: with few tiles (few outputs, short hops) a wide grid would
+    // hand that CTA hundreds of partial segments, so the grid is narrowed to at most 16 segments per tile
+    want = std::min<uint64_t>(want, uint64_t(g.tiles) * 16);
     g.G = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(g.U, want));
     // TMA ring depth: as many stages as fit in ~200 KB, between 2 and 6
     const size_t stage = size_t(g.Q + g.TBV) * 16;
@@ -164,6 +188,23 @@ void free_device(hb_conv *c)
     for (int k = 0; k < 2; k++) { c->d_xin[k].release(); c->d_yout[k].release(); }
     c->d_io_in.release(); c->d_io_out.release(); c->d_ir.release();
     c->h_in.release(); c->h_out.release(); c->h_ir.release();
+    for (uint32_t r = 0; r < c->shard_world; r++)
+        if (c->peers_attached && r != c->shard_rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    cudaFree(c->d_inbox);
+    c->d_inbox = nullptr; c->peers_attached = false; c->shard_world = 0;
+    for (int k = 0; k < 2; k++)
+    {
+        c->h_blk[k].release(); c->h_inq[k].release(); c->d_inq[k].release();
+        if (c->ev_blk[k]) cudaEventDestroy(c->ev_blk[k]);
+        if (c->ev_inq[k]) cudaEventDestroy(c->ev_inq[k]);
+        if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+        c->ev_blk[k] = c->ev_inq[k] = c->ev_done[k] = nullptr;
+        c->blk_pending[k] = c->inq_pending[k] = c->done_pending[k] = false;
+    }
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    c->s_h2d = c->s_d2h = nullptr;
+    c->blk_valid = false;
 }
 
 // allocate everything whose size depends on max_length (ctor and resize)
@@ -210,6 +251,9 @@ template <class K> int allow_smem(K kernel, size_t bytes)
 }
 
 template <class T> size_t fft_smem(uint32_t log2m) { return size_t(padded_elems<HB_PADSH>(1u << log2m)) * sizeof(Cx<T>); }
+// shared-memory copy of the twiddles of a real transform of 2^(log2m+1) points: 2^log2m entries behind the data
+template <class T> size_t tw_smem(uint32_t log2m) { return (size_t(1) << log2m) * sizeof(Cx<T>); }
+template <class T> int tw_fits(uint32_t log2m) { return fft_smem<T>(log2m) + tw_smem<T>(log2m) <= 200 * 1024 ? 1 : 0; }
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
 template <class T, int XA, int OB>
@@ -250,45 +294,66 @@ int launch_cmac(hb_conv *c, cudaStream_t st)
     return HB_ERR_UNSUPPORTED;
 }
 
-template <class T>
-int launch_fwd(hb_conv *c, const T *xin, size_t ld, size_t off, cudaStream_t st)
+template <class T, int EPT>
+int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
 {
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
-    const size_t smem = fft_smem<T>(log2m);
-    const unsigned grid = g.groups * g.ins;
-    if ((1u << log2m) / 8 > 1024)
-    {
-        int rc = allow_smem(k_fwd<T, 16>, smem); if (rc) return rc;
-        k_fwd<T, 16><<<grid, fft_threads(log2m, 16), smem, st>>>(g, xin, ld, off, (Cx<T> *) c->d_X, (T *) c->d_Xnyq, (const Cx<T> *) c->d_tw, c->tw_log2);
-    }
-    else
-    {
-        int rc = allow_smem(k_fwd<T, 8>, smem); if (rc) return rc;
-        k_fwd<T, 8><<<grid, fft_threads(log2m, 8), smem, st>>>(g, xin, ld, off, (Cx<T> *) c->d_X, (T *) c->d_Xnyq, (const Cx<T> *) c->d_tw, c->tw_log2);
-    }
+    const int stage_tw = tw_fits<T>(log2m);
+    const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) : 0);
+    int rc = allow_smem(k_fwd<T, EPT>, smem);
+    if (rc) return rc;
+    k_fwd<T, EPT><<<g.groups * g.ins, fft_threads(log2m, EPT), smem, st>>>(g, prev, prev_ld, newest, new_ld, save, save_ld, (Cx<T> *) c->d_X, (T *) c->d_Xnyq,
+                                                                        (const Cx<T> *) c->d_tw, c->tw_log2, stage_tw);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
 
 template <class T>
-int launch_inv(hb_conv *c, T *yout, size_t ld, size_t off, cudaStream_t st)
+int launch_fwd(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
+{
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_fwd_ept<T, EPT>(c, prev, prev_ld, newest, new_ld, save, save_ld, st));
+}
+
+// what k_inv does besides the transform: where the block goes and which finished block it hands over first
+template <class T> struct InvIO
+{
+    T *yout; size_t ld, off; int add_result;
+    const T *carry_src; size_t carry_src_ld; T *carry_dst; size_t carry_dst_ld; int add_carry;
+};
+
+template <class T, int EPT>
+int launch_inv_ept(hb_conv *c, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer)
 {
     typedef typename VecOf<T>::type V;
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
+    const int stage_tw = tw_fits<T>(log2m);
+    const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) : 0);
+    int rc = allow_smem(k_inv<T, EPT>, smem);
+    if (rc) return rc;
+    k_inv<T, EPT><<<g.groups * g.outs, fft_threads(log2m, EPT), smem, st>>>(g, (const V *) c->d_S.p, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off,
+                                                                         io.add_result, io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry,
+                                                                         (const Cx<T> *) c->d_tw, c->tw_log2, stage_tw, peer);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+template <class T>
+int launch_inv(hb_conv *c, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer = PeerOut())
+{
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, io, st, peer));
+}
+
+template <class T, int EPT>
+int launch_ir_ept(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const uint32_t log2m = g.log2n - 1;
     const size_t smem = fft_smem<T>(log2m);
-    const unsigned grid = g.groups * g.outs;
-    if ((1u << log2m) / 8 > 1024)
-    {
-        int rc = allow_smem(k_inv<T, 16>, smem); if (rc) return rc;
-        k_inv<T, 16><<<grid, fft_threads(log2m, 16), smem, st>>>(g, (const V *) c->d_S.p, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, yout, ld, off, (const Cx<T> *) c->d_tw, c->tw_log2);
-    }
-    else
-    {
-        int rc = allow_smem(k_inv<T, 8>, smem); if (rc) return rc;
-        k_inv<T, 8><<<grid, fft_threads(log2m, 8), smem, st>>>(g, (const V *) c->d_S.p, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, yout, ld, off, (const Cx<T> *) c->d_tw, c->tw_log2);
-    }
+    int rc = allow_smem(k_ir<T, EPT>, smem);
+    if (rc) return rc;
+    k_ir<T, EPT><<<nwrite, fft_threads(log2m, EPT), smem, st>>>(g, d_ir, taps, grp, in, o, (Cx<T> *) c->d_H, (T *) c->d_Hnyq, (const Cx<T> *) c->d_tw, c->tw_log2);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
@@ -296,22 +361,8 @@ int launch_inv(hb_conv *c, T *yout, size_t ld, size_t off, cudaStream_t st)
 template <class T>
 int launch_ir(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
 {
-    const Geom &g = c->g;
-    const uint32_t log2m = g.log2n - 1;
-    const size_t smem = fft_smem<T>(log2m);
     if (!nwrite) return HB_OK;
-    if ((1u << log2m) / 8 > 1024)
-    {
-        int rc = allow_smem(k_ir<T, 16>, smem); if (rc) return rc;
-        k_ir<T, 16><<<nwrite, fft_threads(log2m, 16), smem, st>>>(g, d_ir, taps, grp, in, o, (Cx<T> *) c->d_H, (T *) c->d_Hnyq, (const Cx<T> *) c->d_tw, c->tw_log2);
-    }
-    else
-    {
-        int rc = allow_smem(k_ir<T, 8>, smem); if (rc) return rc;
-        k_ir<T, 8><<<nwrite, fft_threads(log2m, 8), smem, st>>>(g, d_ir, taps, grp, in, o, (Cx<T> *) c->d_H, (T *) c->d_Hnyq, (const Cx<T> *) c->d_tw, c->tw_log2);
-    }
-    HB_LAUNCH_CHECK();
-    return HB_OK;
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_ir_ept<T, EPT>(c, d_ir, taps, grp, in, o, nwrite, st));
 }
 
 template <class T>
@@ -415,7 +466,19 @@ int do_reset(hb_conv *c, cudaStream_t st)
     if (c->yout_ld) HB_CUDA(cudaMemsetAsync(c->d_yout[c->cur].p, 0, size_t(g.groups) * g.outs * c->yout_ld * sizeof(T), st));
     c->x_tail = c->y_tail = 0;
     c->need_reset = false;
+    c->blk_valid = false;
     return HB_OK;
+}
+
+// the first thing process does after set / reset / a size change (PartitionedConvolve.cpp:267-290)
+template <class T>
+int ensure_ready(hb_conv *c, size_t n, cudaStream_t st)
+{
+    if (!c->need_reset) return HB_OK;
+    int rc;
+    plan_geometry(c);
+    if ((rc = ensure_staging<T>(c, 2 * size_t(c->g.B) + n, 2 * size_t(c->g.B) + n, false, st))) return rc;
+    return do_reset<T>(c, st);
 }
 
 // fold the recorded event intervals into prof_ms (synchronises on the last recorded event)
@@ -461,16 +524,59 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
     if (!c->P) return HB_ERR_NO_IR;
     if (!n) return HB_OK;
     int rc;
-    if (c->need_reset)
-    {
-        plan_geometry(c);
-        if ((rc = ensure_staging<T>(c, 2 * size_t(c->g.B) + n, 2 * size_t(c->g.B) + n, false, st))) return rc;
-        if ((rc = do_reset<T>(c, st))) return rc;
-    }
+    if ((rc = ensure_ready<T>(c, n, st))) return rc;
     const size_t B = c->g.B;
     const size_t rows_in = size_t(c->groups) * c->ins, rows_out = size_t(c->groups) * c->outs;
     const size_t rw = c->rw;
     const size_t nh = (rw + n) / B;
+    const bool prof = c->profiling;
+
+    auto hop = [&](const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, const InvIO<T> &io) -> int
+    {
+        int r;
+        // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
+        c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+        if (prof && (r = profile_mark(c, st))) return r;
+        if ((r = launch_fwd<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st))) return r;
+        if (prof && (r = profile_mark(c, st))) return r;
+        if ((r = launch_cmac<T>(c, st))) return r;
+        if (prof && (r = profile_mark(c, st))) return r;
+        if ((r = launch_inv<T>(c, io, st))) return r;
+        if (prof && (r = profile_mark(c, st))) return r;
+        return HB_OK;
+    };
+
+    // caller rows that overlap (in-place processing) must go through the staging copies
+    const char *ib = (const char *) d_in, *ie = (const char *) (d_in + (rows_in - 1) * in_ld + n);
+    const char *ob = (const char *) d_out, *oe = (const char *) (d_out + (rows_out - 1) * out_ld + n);
+    const bool disjoint = !d_out || ie <= ob || oe <= ib;
+    // d_out == nullptr: the caller (deferred host path) fetches the finished block itself
+    if (rw == 0 && nh * B == n && disjoint && (d_out || nh <= 1) && c->xin_ld >= B && c->yout_ld >= B)
+    {
+        // Hop-aligned call (the usual audio-callback case): no staging copies.  The forward kernel reads the
+        // caller's rows directly and saves the last block as the next call's "previous hop"; the inverse
+        // kernel of the first hop hands the block finished by the previous call to the caller (the output is
+        // the convolution delayed by exactly B) and the last hop's block stays behind for the next call.
+        const int cur = c->cur, nxt = cur ^ 1;
+        const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
+        const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
+        for (size_t h = 0; h < nh; h++)
+        {
+            const bool first = h == 0, last = h + 1 == nh;
+            InvIO<T> io;
+            io.yout = last ? (T *) c->d_yout[nxt].p : d_out; io.ld = last ? c->yout_ld : out_ld; io.off = last ? 0 : (h + 1) * B;
+            io.add_result = last ? 0 : accumulate;
+            io.carry_src = first ? y_keep : nullptr; io.carry_src_ld = c->yout_ld;
+            io.carry_dst = (first && d_out) ? d_out : nullptr; io.carry_dst_ld = out_ld; io.add_carry = accumulate;
+            rc = hop(first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                     last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, io);
+            if (rc) return rc;
+        }
+        c->cur = nxt;
+        c->x_tail = c->y_tail = 0;
+        return HB_OK;
+    }
+
     if ((rc = ensure_staging<T>(c, B + rw + n, (nh + 1) * B, true, st))) return rc;
 
     // bring the retained heads to offset 0 of the other row set when they sit further in
@@ -488,22 +594,87 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
 
     for (size_t h = 0; h < nh; h++)
     {
-        // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
-        c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
-        const bool prof = c->profiling;
-        if (prof && (rc = profile_mark(c, st))) return rc;
-        if ((rc = launch_fwd<T>(c, xin, c->xin_ld, h * B, st))) return rc;
-        if (prof && (rc = profile_mark(c, st))) return rc;
-        if ((rc = launch_cmac<T>(c, st))) return rc;
-        if (prof && (rc = profile_mark(c, st))) return rc;
-        if ((rc = launch_inv<T>(c, yout, c->yout_ld, (h + 1) * B, st))) return rc;
-        if (prof && (rc = profile_mark(c, st))) return rc;
+        InvIO<T> io = {yout, c->yout_ld, (h + 1) * B, 0, nullptr, 0, nullptr, 0, 0};
+        if ((rc = hop(xin + h * B, c->xin_ld, xin + (h + 1) * B, c->xin_ld, nullptr, 0, io))) return rc;
     }
-    if ((rc = launch_rows<T>(d_out, out_ld, yout + rw, c->yout_ld, n, rows_out, accumulate, st))) return rc;
+    if (d_out && (rc = launch_rows<T>(d_out, out_ld, yout + rw, c->yout_ld, n, rows_out, accumulate, st))) return rc;
 
     c->rw = (rw + n) - nh * B;
     c->x_tail = nh * B;
     c->y_tail = nh * B;
+    return HB_OK;
+}
+
+int core_dispatch(hb_conv *c, const void *d_in, size_t in_ld, void *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
+{
+    return c->dtype == HB_F64 ? process_core<double>(c, (const double *) d_in, in_ld, (double *) d_out, out_ld, n, accumulate, st)
+                              : process_core<float>(c, (const float *) d_in, in_ld, (float *) d_out, out_ld, n, accumulate, st);
+}
+
+// Hop-aligned call of a rank of the fused multi-GPU exchange: as the aligned path of process_core, but the
+// inverse kernel delivers every partial block into its owner's inbox and k_gather sums what arrived here.
+// d_out holds this rank's outs/world output rows.
+template <class T>
+int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
+{
+    if (!c->P) return HB_ERR_NO_IR;
+    if (!n) return HB_OK;
+    int rc;
+    if ((rc = ensure_ready<T>(c, n, st))) return rc;
+    const size_t B = c->g.B;
+    if (c->rw != 0 || n % B != 0 || c->xin_ld < B || c->yout_ld < B)
+    {
+        set_error("the fused multi-GPU exchange takes hop-aligned calls only (reset offset 0, numSamples a multiple of %zu)", B);
+        return HB_ERR_UNSUPPORTED;
+    }
+    const size_t nh = n / B;
+    const uint32_t world = c->shard_world, o_loc = c->outs / world;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
+    const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
+    const bool prof = c->profiling;
+    for (size_t h = 0; h < nh; h++)
+    {
+        const bool first = h == 0, last = h + 1 == nh;
+        PeerOut peer;
+        const size_t es = sizeof(T);
+        for (uint32_t r = 0; r < world; r++)
+        {
+            peer.data[r] = c->peer_base[r];
+            peer.count[r] = (uint32_t *) ((char *) c->peer_base[r] + c->inbox_data_bytes);
+        }
+        (void) es;
+        peer.world = world; peer.rank = c->shard_rank; peer.outs_local = o_loc;
+        peer.parity = (++c->hop_seq) & 1u;
+        peer.slot = c->inbox_slot;
+        const uint32_t expected = (++c->parity_uses[peer.parity]) * o_loc;
+        c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+        if (prof && (rc = profile_mark(c, st))) return rc;
+        if ((rc = launch_fwd<T>(c, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st))) return rc;
+        if (prof && (rc = profile_mark(c, st))) return rc;
+        if ((rc = launch_cmac<T>(c, st))) return rc;
+        if (prof && (rc = profile_mark(c, st))) return rc;
+        InvIO<T> io = {nullptr, 0, 0, 0, nullptr, 0, nullptr, 0, 0};
+        if ((rc = launch_inv<T>(c, io, st, peer))) return rc;
+        k_gather<T><<<o_loc, 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
+                                          peer.parity, peer.slot, expected, (uint32_t) B,
+                                          last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
+                                          first ? y_keep : nullptr, c->yout_ld, first ? d_out : nullptr, out_ld, accumulate);
+        HB_LAUNCH_CHECK();
+        if (prof && (rc = profile_mark(c, st))) return rc;
+    }
+    c->cur = nxt;
+    c->x_tail = c->y_tail = 0;
+    return HB_OK;
+}
+
+// wait for the copy streams of the deferred host path (before anything else touches the staging rows)
+int drain_deferred(hb_conv *c)
+{
+    if (c->s_h2d) HB_CUDA(cudaStreamSynchronize(c->s_h2d));
+    if (c->s_d2h) HB_CUDA(cudaStreamSynchronize(c->s_d2h));
+    for (int k = 0; k < 2; k++) c->blk_pending[k] = c->inq_pending[k] = c->done_pending[k] = false;
     return HB_OK;
 }
 
@@ -747,9 +918,121 @@ extern "C" int hb_conv_process_dev(hb_conv *c, const void *d_in, uintptr_t in_ld
     if ((!d_in || !d_out) && num_samples) { set_error("hb_conv_process_dev: null buffer"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
     cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
-    return c->dtype == HB_F64 ? process_core<double>(c, (const double *) d_in, in_ld, (double *) d_out, out_ld, num_samples, accumulate, st)
-                              : process_core<float>(c, (const float *) d_in, in_ld, (float *) d_out, out_ld, num_samples, accumulate, st);
+    if (c->blk_valid && (rc = drain_deferred(c))) return rc;        // host-pointer calls were in flight on this handle
+    c->blk_valid = false;
+    return core_dispatch(c, d_in, in_ld, d_out, out_ld, num_samples, accumulate, st);
 }
+
+namespace
+{
+void scatter_rows(hb_conv *c, void *const *outs, const char *src, size_t src_ld, size_t src_off, size_t n, int accumulate)
+{
+    const size_t es = c->esize(), rows_out = size_t(c->groups) * c->outs;
+    for (size_t r = 0; r < rows_out; r++)
+    {
+        if (!outs[r]) continue;
+        const char *sp = src + (r * src_ld + src_off) * es;
+        if (!accumulate) memcpy(outs[r], sp, n * es);
+        else if (c->dtype == HB_F64)
+        {
+            double *d = (double *) outs[r];
+            const double *q = (const double *) sp;
+            for (size_t k = 0; k < n; k++) d[k] += q[k];                   // MonoConvolve.cpp:167-177
+        }
+        else
+        {
+            float *d = (float *) outs[r];
+            const float *q = (const float *) sp;
+            for (size_t k = 0; k < n; k++) d[k] += q[k];
+        }
+    }
+}
+
+void gather_rows(hb_conv *c, const void *const *ins, char *dst, size_t n)
+{
+    const size_t es = c->esize(), rows_in = size_t(c->groups) * c->ins;
+    for (size_t r = 0; r < rows_in; r++)
+    {
+        // a null input row is an inactive channel: silence (NToMonoConvolve.cpp:41 stops at activeInChans)
+        if (ins[r]) memcpy(dst + r * n * es, ins[r], n * es);
+        else memset(dst + r * n * es, 0, n * es);
+    }
+}
+
+// Deferred host call, possible when every output sample of this call lies in the block finished by an
+// earlier hop (rw + n <= B; the reference reads its output ring before it transforms, PartitionedConvolve.cpp:307
+// before :352-360): copy the outputs from the host copy of that block, enqueue this call's work and return
+// without waiting for it.  A hop completed by this call is fetched to the other host block behind an event.
+int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size_t n, int accumulate)
+{
+    const size_t es = c->esize(), B = c->g.B, rw = c->rw;
+    const size_t rows_in = size_t(c->groups) * c->ins, rows_out = size_t(c->groups) * c->outs;
+    int rc;
+    for (int k = 0; k < 2; k++)
+    {
+        if (!c->ev_blk[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_blk[k], cudaEventDisableTiming));
+        if (!c->ev_inq[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_inq[k], cudaEventDisableTiming));
+        if (!c->ev_done[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    }
+    if (!c->s_h2d) HB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    if (!c->s_d2h) HB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    if (c->blk_B != B || c->h_blk[0].cap < rows_out * B * es)
+    {
+        if ((rc = c->h_blk[0].ensure(rows_out * B * es)) || (rc = c->h_blk[1].ensure(rows_out * B * es))) return rc;
+        c->blk_B = B;
+        c->blk_valid = false;
+        c->blk_pending[0] = c->blk_pending[1] = false;
+    }
+    if (!c->blk_valid)
+    {
+        // (re)join the stream: the last completed block lives at the retained head of the staging rows
+        if ((rc = drain_deferred(c))) return rc;
+        const char *src = (const char *) c->d_yout[c->cur].p + c->y_tail * es;
+        HB_CUDA(cudaMemcpy2DAsync(c->h_blk[c->blk_cur].p, B * es, src, c->yout_ld * es, B * es, rows_out, cudaMemcpyDeviceToHost, c->stream));
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        c->blk_pending[c->blk_cur] = false;
+        c->blk_valid = true;
+    }
+    // 1. this call's input and device work go out first, so that the GPU is busy while the host copies below
+    //    run; the upload and the download of finished blocks ride on their own streams beside the kernels
+    const int q = c->inq_cur, have = c->blk_cur;
+    if ((rc = c->h_inq[q].ensure(rows_in * n * es)) || (rc = c->d_inq[q].ensure(rows_in * n * es))) return rc;
+    if (c->inq_pending[q])
+    {
+        HB_CUDA(cudaEventSynchronize(c->ev_inq[q]));                        // the pinned buffer has been uploaded
+        c->inq_pending[q] = false;
+    }
+    gather_rows(c, ins, (char *) c->h_inq[q].p, n);
+    if (c->done_pending[q]) HB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_done[q], 0));   // kernels of two calls ago have read d_inq[q]
+    HB_CUDA(cudaMemcpyAsync(c->d_inq[q].p, c->h_inq[q].p, rows_in * n * es, cudaMemcpyHostToDevice, c->s_h2d));
+    HB_CUDA(cudaEventRecord(c->ev_inq[q], c->s_h2d));
+    c->inq_pending[q] = true;
+    c->inq_cur = q ^ 1;
+    HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_inq[q], 0));
+    if ((rc = core_dispatch(c, c->d_inq[q].p, n, nullptr, 0, n, 0, c->stream))) return rc;
+    HB_CUDA(cudaEventRecord(c->ev_done[q], c->stream));
+    c->done_pending[q] = true;
+    c->blk_valid = true;                    // process_core ran no reset here: ensure_ready was called by the caller
+    if (rw + n == B)
+    {
+        const int nb = have ^ 1;
+        const char *src = (const char *) c->d_yout[c->cur].p + c->y_tail * es;
+        HB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_done[q], 0));
+        HB_CUDA(cudaMemcpy2DAsync(c->h_blk[nb].p, B * es, src, c->yout_ld * es, B * es, rows_out, cudaMemcpyDeviceToHost, c->s_d2h));
+        HB_CUDA(cudaEventRecord(c->ev_blk[nb], c->s_d2h));
+        c->blk_pending[nb] = true;
+        c->blk_cur = nb;
+    }
+    // 2. the outputs of this call: samples rw .. rw+n of the block an earlier hop finished
+    if (c->blk_pending[have])
+    {
+        HB_CUDA(cudaEventSynchronize(c->ev_blk[have]));
+        c->blk_pending[have] = false;
+    }
+    scatter_rows(c, outs, (const char *) c->h_blk[have].p, B, rw, n, accumulate);
+    return HB_OK;
+}
+} // namespace
 
 extern "C" int hb_conv_process(hb_conv *c, const void *const *ins, void *const *outs, uintptr_t n, int accumulate)
 {
@@ -759,39 +1042,93 @@ extern "C" int hb_conv_process(hb_conv *c, const void *const *ins, void *const *
     std::lock_guard<std::mutex> g(c->lock);
     if (!c->P) return HB_ERR_NO_IR;
     if (!n) return HB_OK;
+    rc = c->dtype == HB_F64 ? ensure_ready<double>(c, n, c->stream) : ensure_ready<float>(c, n, c->stream);
+    if (rc) return rc;
+    if (c->deferred && c->rw + n <= c->g.B) return process_deferred(c, ins, outs, n, accumulate);
+
+    // a call that crosses a hop boundary needs that hop's result before it returns: synchronous round trip
     const size_t es = c->esize();
     const size_t rows_in = size_t(c->groups) * c->ins, rows_out = size_t(c->groups) * c->outs;
     if ((rc = c->h_in.ensure(rows_in * n * es)) || (rc = c->h_out.ensure(rows_out * n * es)) ||
         (rc = c->d_io_in.ensure(rows_in * n * es)) || (rc = c->d_io_out.ensure(rows_out * n * es))) return rc;
-    for (size_t r = 0; r < rows_in; r++)
-    {
-        if (!ins[r]) { set_error("hb_conv_process: null input row %zu", r); return HB_ERR_BAD_ARG; }
-        memcpy((char *) c->h_in.p + r * n * es, ins[r], n * es);
-    }
+    HB_CUDA(cudaStreamSynchronize(c->stream));                 // deferred work may still be reading the staging buffers
+    if ((rc = drain_deferred(c))) return rc;
+    gather_rows(c, ins, (char *) c->h_in.p, n);
     HB_CUDA(cudaMemcpyAsync(c->d_io_in.p, c->h_in.p, rows_in * n * es, cudaMemcpyHostToDevice, c->stream));
-    rc = c->dtype == HB_F64 ? process_core<double>(c, (const double *) c->d_io_in.p, n, (double *) c->d_io_out.p, n, n, 0, c->stream)
-                            : process_core<float>(c, (const float *) c->d_io_in.p, n, (float *) c->d_io_out.p, n, n, 0, c->stream);
-    if (rc) return rc;
+    if ((rc = core_dispatch(c, c->d_io_in.p, n, c->d_io_out.p, n, n, 0, c->stream))) return rc;
     HB_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_io_out.p, rows_out * n * es, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    for (size_t r = 0; r < rows_out; r++)
-    {
-        if (!outs[r]) continue;
-        if (!accumulate) memcpy(outs[r], (char *) c->h_out.p + r * n * es, n * es);
-        else if (c->dtype == HB_F64)
-        {
-            double *d = (double *) outs[r];
-            const double *s = (const double *) c->h_out.p + r * n;
-            for (size_t k = 0; k < n; k++) d[k] += s[k];                   // MonoConvolve.cpp:167-177
-        }
-        else
-        {
-            float *d = (float *) outs[r];
-            const float *s = (const float *) c->h_out.p + r * n;
-            for (size_t k = 0; k < n; k++) d[k] += s[k];
-        }
-    }
+    c->blk_valid = false;
+    scatter_rows(c, outs, (const char *) c->h_out.p, n, 0, n, accumulate);
     return HB_OK;
+}
+
+extern "C" int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, void *handle_out)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    if (!handle_out || world < 1 || world > HB_MAX_WORLD || rank >= world || c->groups != 1 || c->outs % world)
+    {
+        set_error("hb_conv_shard_export: needs 1 <= world <= %d, rank < world, one group and outs a multiple of world", HB_MAX_WORLD);
+        return HB_ERR_BAD_ARG;
+    }
+    std::lock_guard<std::mutex> g(c->lock);
+    if (c->d_inbox) { set_error("hb_conv_shard_export: already exported"); return HB_ERR_BAD_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == HB_IPC_HANDLE_BYTES, "IPC handle size");
+    const size_t slot = (size_t(1) << c->max_fft_log2) >> 1;
+    const size_t data = (size_t(2) * world * (c->outs / world) * slot * c->esize() + 255) & ~size_t(255);
+    HB_CUDA(cudaMalloc(&c->d_inbox, data + 256));
+    HB_CUDA(cudaMemset(c->d_inbox, 0, data + 256));
+    HB_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    HB_CUDA(cudaIpcGetMemHandle(&h, c->d_inbox));
+    memcpy(handle_out, &h, sizeof(h));
+    c->shard_world = world; c->shard_rank = rank;
+    c->inbox_data_bytes = data; c->inbox_slot = slot;
+    c->hop_seq = 0; c->parity_uses[0] = c->parity_uses[1] = 0;
+    return HB_OK;
+}
+
+extern "C" int hb_conv_shard_attach(hb_conv *c, const void *handles)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    if (!handles || !c->d_inbox || c->peers_attached) { set_error("hb_conv_shard_attach: export first, attach once"); return HB_ERR_BAD_ARG; }
+    for (uint32_t r = 0; r < c->shard_world; r++)
+    {
+        if (r == c->shard_rank) { c->peer_base[r] = c->d_inbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *) handles + size_t(r) * HB_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+        {
+            set_error("cudaIpcOpenMemHandle for rank %u -> %s (peer access over NVLink / PCIe is required)", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            for (uint32_t k = 0; k < r; k++)
+                if (k != c->shard_rank && c->peer_base[k]) { cudaIpcCloseMemHandle(c->peer_base[k]); c->peer_base[k] = nullptr; }
+            return HB_ERR_CUDA;
+        }
+        c->peer_base[r] = p;
+    }
+    c->peers_attached = true;
+    return HB_OK;
+}
+
+extern "C" int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out_shard, uintptr_t out_ld,
+                                         uintptr_t num_samples, int accumulate, void *stream)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    if ((!d_in || !d_out_shard) && num_samples) { set_error("hb_conv_process_shard_dev: null buffer"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    if (!c->peers_attached) { set_error("hb_conv_process_shard_dev: peers not attached"); return HB_ERR_BAD_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+    if (c->blk_valid && (rc = drain_deferred(c))) return rc;
+    c->blk_valid = false;
+    return c->dtype == HB_F64 ? process_shard<double>(c, (const double *) d_in, in_ld, (double *) d_out_shard, out_ld, num_samples, accumulate, st)
+                              : process_shard<float>(c, (const float *) d_in, in_ld, (float *) d_out_shard, out_ld, num_samples, accumulate, st);
 }
 
 extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)

@@ -374,113 +374,381 @@ template <class T> __device__ __forceinline__ uint32_t tile_bins(const Geom &g) 
 
 // ---------------------------------------------------------------------------------------------
 // k_fwd: real FFT of the newest frame of every input channel into FDL slot g.slot.
-// xin: time-ordered staging rows, row `ch` starts at xin + ch*ld; the 2B samples of this hop start at
-// `off`.  The reference transforms the rotated frame [newest B | previous B]
-// (PartitionedConvolve.cpp:304-305,357), so that the valid half of the inverse is the FIRST B samples.
+// Row `ch` of the previous hop's B samples starts at prev + ch*prev_ld, of the newest B samples at
+// newest + ch*new_ld (staging rows or the caller's own buffer).  The reference transforms the rotated
+// frame [newest B | previous B] (PartitionedConvolve.cpp:304-305,357), so that the valid half of the
+// inverse is the FIRST B samples.  `save` (optional) receives a copy of the newest samples.
 // ---------------------------------------------------------------------------------------------
+// two consecutive samples at p (vector load when the row is aligned for it)
+template <class T> struct Pair { T a, b; };
+__device__ __forceinline__ Pair<float> ld_pair(const float *p, bool vec)
+{
+    Pair<float> r;
+    if (vec) { const float2 v = *reinterpret_cast<const float2 *>(p); r.a = v.x; r.b = v.y; }
+    else { r.a = p[0]; r.b = p[1]; }
+    return r;
+}
+__device__ __forceinline__ Pair<double> ld_pair(const double *p, bool vec)
+{
+    Pair<double> r;
+    if (vec) { const double2 v = *reinterpret_cast<const double2 *>(p); r.a = v.x; r.b = v.y; }
+    else { r.a = p[0]; r.b = p[1]; }
+    return r;
+}
+__device__ __forceinline__ void st_pair(float *p, float a, float b, bool vec)
+{
+    if (vec) *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+    else { p[0] = a; p[1] = b; }
+}
+__device__ __forceinline__ void st_pair(double *p, double a, double b, bool vec)
+{
+    if (vec) *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    else { p[0] = a; p[1] = b; }
+}
+template <class T> __device__ __forceinline__ bool pair_aligned(const T *p, size_t ld)
+{
+    return ((reinterpret_cast<uintptr_t>(p) | (ld * sizeof(T))) & (2 * sizeof(T) - 1)) == 0;
+}
+
 template <class T, int EPT>
-__global__ void __launch_bounds__(1024) k_fwd(const Geom g, const T *__restrict__ xin, size_t ld, size_t off,
+__global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__ prev, size_t prev_ld,
+                                              const T *__restrict__ newest, size_t new_ld, T *__restrict__ save, size_t save_ld,
                                               Cx<T> *__restrict__ X, T *__restrict__ Xnyq,
-                                              const Cx<T> *__restrict__ tw, int tw_log2)
+                                              const Cx<T> *__restrict__ tw, int tw_log2, int stage_tw)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
     const uint32_t ch = blockIdx.x;
     const uint32_t B = g.B;
-    const T *src = xin + size_t(ch) * ld + off;
-    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x)
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    // twiddles of this transform size staged in shared memory behind the data (one global round trip
+    // instead of one per pass); the loads are issued together with the input loads below
+    Cx<T> *stw = s + padded_elems<HB_PADSH>(B);
+    Cx<T> twr[EPT];
+    if (stage_tw) twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
+    // rotated frame [newest B | previous B], de-interleaved on the way in: z[k] = frame[2k] + i frame[2k+1].
+    // Every thread issues all of its loads before the first store, so their latencies overlap.
+    const T *pn = newest + size_t(ch) * new_ld, *pp = prev + size_t(ch) * prev_ld;
+    T *ps = save ? save + size_t(ch) * save_ld : nullptr;
+    const bool vn = pair_aligned(newest, new_ld), vp = pair_aligned(prev, prev_ld), vs = save && pair_aligned(save, save_ld);
+    Pair<T> v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
     {
-        uint32_t j = 2 * k;
-        uint32_t q = j < B ? j + B : j - B;
-        s[sidx<HB_PADSH>(k)] = cx<T>(src[q], src[q + 1]);
+        const uint32_t k = tid + e * nthr, j = 2 * k;
+        if (k < B) v[e] = j < B ? ld_pair(pn + j, vn) : ld_pair(pp + (j - B), vp);
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
+    {
+        const uint32_t k = tid + e * nthr, j = 2 * k;
+        if (k < B)
+        {
+            s[sidx<HB_PADSH>(k)] = cx<T>(v[e].a, v[e].b);
+            if (ps && j < B) st_pair(ps + j, v[e].a, v[e].b, vs);      // becomes the previous hop of the next call
+        }
+    }
+    if (stage_tw)
+    {
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
+        tw = stw;
+        tw_log2 = (int) g.log2n;
     }
     __syncthreads();
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, tw, tw_log2);
-    for (uint32_t k = threadIdx.x; k <= B / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, B, (int) g.log2n, k, false, tw, tw_log2);
+    block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, tw, tw_log2);
     __syncthreads();
     const uint32_t TB = tile_bins<T>(g);
     Cx<T> *xrow = X + size_t(ch) * g.n_bt * g.P * TB;
-    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x)
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
     {
-        Cx<T> v = s[sidx<HB_PADSH>(k)];
-        if (k == 0)
+        const uint32_t k = tid + e * nthr;
+        if (k < B)
         {
-            Xnyq[size_t(ch) * g.P + g.slot] = v.y;
-            v.y = T(0);
+            Cx<T> z = s[sidx<HB_PADSH>(k)];
+            if (k == 0)
+            {
+                Xnyq[size_t(ch) * g.P + g.slot] = z.y;
+                z.y = T(0);
+            }
+            const uint32_t bt = k / TB, j = k - bt * TB;
+            xrow[(size_t(bt) * g.P + g.slot) * TB + j] = z;
         }
-        uint32_t bt = k / TB, j = k - bt * TB;
-        xrow[(size_t(bt) * g.P + g.slot) * TB + j] = v;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_inv: one CTA per output channel.  Sums the stream-K partial segments of every bin tile in CTA
 // order (deterministic), adds the Nyquist dot product, inverse real FFT, scale 1/(4N)
-// (PartitionedConvolve.cpp:232-241,359-360) and store of the first B samples at yout row ch, offset off.
+// (PartitionedConvolve.cpp:232-241,359-360) and store of the first B samples at yout row ch, offset off
+// (added to what is there when add_result).  carry_dst (optional): first copy (or add) the B samples at
+// carry_src row ch to carry_dst row ch -- the output ring read of PartitionedConvolve.cpp:307.
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU exchange fused into the inverse-FFT epilogue (input channels sharded over `world` ranks, one
+// process per GPU).  Every rank holds an "inbox" [2 parities][world sources][outs/world][slot] plus arrival
+// counters [2][world]; the CTA of output o stores its partial block straight into the inbox of the rank that
+// owns o -- a plain st.global on a peer-mapped pointer, NVLink carries it -- and then bumps that rank's
+// counter for (parity, source).  k_gather on the owner waits for the counters and sums the sources in rank
+// order (deterministic).  world == 0: not sharded.
+constexpr int HB_MAX_WORLD = 16;
+struct PeerOut
+{
+    void *data[HB_MAX_WORLD];          // inbox data of every rank (own entry = local memory)
+    uint32_t *count[HB_MAX_WORLD];     // arrival counters of every rank
+    uint32_t world, rank, outs_local, parity;
+    uint64_t slot;                     // elements per inbox block (hop capacity)
+};
+
 template <class T, int EPT>
-__global__ void __launch_bounds__(1024) k_inv(const Geom g, const typename VecOf<T>::type *__restrict__ S,
+__global__ void __launch_bounds__(512) k_inv(const Geom g, const typename VecOf<T>::type *__restrict__ S,
                                               const T *__restrict__ Xnyq, const T *__restrict__ Hnyq,
-                                              T *__restrict__ yout, size_t ld, size_t off,
-                                              const Cx<T> *__restrict__ tw, int tw_log2)
+                                              T *__restrict__ yout, size_t ld, size_t off, int add_result,
+                                              const T *__restrict__ carry_src, size_t carry_src_ld,
+                                              T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
+                                              const Cx<T> *__restrict__ tw, int tw_log2, int stage_tw, const PeerOut peer)
 {
     typedef typename VecOf<T>::type V;
     constexpr int CPV = VecOf<T>::CPV;
+    constexpr int VPT = EPT / CPV;                  // 16-byte vectors of the spectrum per thread
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
     __shared__ T red[40];
     const uint32_t ch = blockIdx.x;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t grp = ch / g.outs, o = ch - grp * g.outs;
     const uint32_t ot = o / g.OT, row = o - ot * g.OT;
     const uint32_t B = g.B;
-
-    for (uint32_t v = threadIdx.x; v < B / CPV; v += blockDim.x)
+    if (stage_tw)
     {
-        const uint32_t bt = v / g.TBV, xa = v - bt * g.TBV;
-        const uint32_t tile = (grp * g.n_ot + ot) * g.n_bt + bt;
-        const uint64_t ulo = uint64_t(tile) * g.upt, uhi = ulo + g.upt - 1;
-        const uint32_t clo = (uint32_t) unit_owner(ulo, g.U, g.G), chi = (uint32_t) unit_owner(uhi, g.U, g.G);
-        V sum;
-        vzero(sum);
-        for (uint32_t c = clo; c <= chi; c++) vadd(sum, S[(uint64_t(c) + tile) * g.Q + row * g.TBV + xa]);
-        if constexpr (CPV == 2)
+        // twiddles of this transform size into shared memory (published by the barriers of block_sum below)
+        Cx<T> *stw = s + padded_elems<HB_PADSH>(B);
+        Cx<T> twr[EPT];
+        twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
+        tw = stw;
+        tw_log2 = (int) g.log2n;
+    }
+
+    if (carry_dst)
+    {
+        // hand the block computed by the previous hop to the caller before this hop's result replaces it
+        const T *cs = carry_src + size_t(ch) * carry_src_ld;
+        T *cd = carry_dst + size_t(ch) * carry_dst_ld;
+        const bool vs = pair_aligned(carry_src, carry_src_ld), vd = pair_aligned(carry_dst, carry_dst_ld);
+        Pair<T> cv[EPT / 2], dv[EPT / 2];
+#pragma unroll
+        for (int e = 0; e < EPT / 2; e++)
         {
-            s[sidx<HB_PADSH>(2 * v)] = cx<T>(sum.x, sum.y);
-            s[sidx<HB_PADSH>(2 * v + 1)] = cx<T>(sum.z, sum.w);
+            const uint32_t k = tid + e * nthr;
+            if (2 * k < B)
+            {
+                cv[e] = ld_pair(cs + 2 * k, vs);
+                if (add_carry) dv[e] = ld_pair(cd + 2 * k, vd);
+            }
         }
-        else
-            s[sidx<HB_PADSH>(v)] = cx<T>(sum.x, sum.y);
+#pragma unroll
+        for (int e = 0; e < EPT / 2; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (2 * k < B)
+            {
+                if (add_carry) st_pair(cd + 2 * k, dv[e].a + cv[e].a, dv[e].b + cv[e].b, vd);
+                else st_pair(cd + 2 * k, cv[e].a, cv[e].b, vd);
+            }
+        }
+    }
+
+    // stream-K partials of this output row, four spectrum vectors of the thread at a time: up to four
+    // segments per vector are fetched per round so that the loads overlap; the order of the additions is
+    // fixed (CTA order), so results are reproducible
+    constexpr int GV = VPT < 4 ? VPT : 4;
+#pragma unroll 1
+    for (int e0 = 0; e0 < VPT; e0 += GV)
+    {
+        V sum[GV];
+        uint32_t seg_lo[GV], seg_hi[GV];
+        uint64_t base[GV];
+        uint32_t rounds = 0;
+#pragma unroll
+        for (int e = 0; e < GV; e++)
+        {
+            const uint32_t v = tid + (e0 + e) * nthr;
+            vzero(sum[e]);
+            seg_lo[e] = 1; seg_hi[e] = 0; base[e] = 0;
+            if (v < B / CPV)
+            {
+                const uint32_t bt = v / g.TBV, xa = v - bt * g.TBV;
+                const uint32_t tile = (grp * g.n_ot + ot) * g.n_bt + bt;
+                const uint64_t ulo = uint64_t(tile) * g.upt, uhi = ulo + g.upt - 1;
+                seg_lo[e] = (uint32_t) unit_owner(ulo, g.U, g.G);
+                seg_hi[e] = (uint32_t) unit_owner(uhi, g.U, g.G);
+                base[e] = uint64_t(tile) * g.Q + row * g.TBV + xa;
+                const uint32_t need = seg_hi[e] - seg_lo[e] + 1;
+                rounds = need > rounds ? need : rounds;
+            }
+        }
+        for (uint32_t r = 0; r < rounds; r += 4)
+        {
+            V part[GV][4];
+#pragma unroll
+            for (int e = 0; e < GV; e++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const uint32_t c = seg_lo[e] + r + q;
+                    if (c <= seg_hi[e]) part[e][q] = S[uint64_t(c) * g.Q + base[e]];
+                    else vzero(part[e][q]);
+                }
+#pragma unroll
+            for (int e = 0; e < GV; e++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) vadd(sum[e], part[e][q]);
+        }
+#pragma unroll
+        for (int e = 0; e < GV; e++)
+        {
+            const uint32_t v = tid + (e0 + e) * nthr;
+            if (v < B / CPV)
+            {
+                if constexpr (CPV == 2)
+                {
+                    s[sidx<HB_PADSH>(2 * v)] = cx<T>(sum[e].x, sum[e].y);
+                    s[sidx<HB_PADSH>(2 * v + 1)] = cx<T>(sum[e].z, sum[e].w);
+                }
+                else
+                    s[sidx<HB_PADSH>(v)] = cx<T>(sum[e].x, sum[e].y);
+            }
+        }
     }
     // Nyquist bin: a real dot product over (in, partition)
     T part = T(0);
     const T *hn = Hnyq + (size_t(grp) * g.outs + o) * g.ins * g.Pcap;
     const T *xn = Xnyq + size_t(grp) * g.ins * g.P;
-    for (uint32_t idx = threadIdx.x; idx < g.upt; idx += blockDim.x)
+    for (uint32_t idx0 = tid; idx0 < g.upt; idx0 += 4 * nthr)
     {
-        uint32_t in = idx / g.P, p = idx - in * g.P;
-        uint32_t sl = g.slot + p;
-        if (sl >= g.P) sl -= g.P;
-        part += xn[size_t(in) * g.P + sl] * hn[size_t(in) * g.Pcap + p];
+        T xv[4], hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const uint32_t idx = idx0 + q * nthr;
+            xv[q] = hv[q] = T(0);
+            if (idx < g.upt)
+            {
+                const uint32_t in = idx / g.P, p = idx - in * g.P;
+                uint32_t sl = g.slot + p;
+                if (sl >= g.P) sl -= g.P;
+                xv[q] = xn[size_t(in) * g.P + sl];
+                hv[q] = hn[size_t(in) * g.Pcap + p];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) part += xv[q] * hv[q];
     }
     const T nyq = block_sum<T>(part, red);          // contains the barriers that publish s[]
-    if (threadIdx.x == 0) s[sidx<HB_PADSH>(0)].y = nyq;
+    if (tid == 0) s[sidx<HB_PADSH>(0)].y = nyq;
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k <= B / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, B, (int) g.log2n, k, true, tw, tw_log2);
+    block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, true, tw, tw_log2);
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x)
+    // hisstools_ifft = forward transform on exchanged planes (Core:1341-1346); each thread swaps its own elements
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
     {
-        Cx<T> v = s[sidx<HB_PADSH>(k)];
-        s[sidx<HB_PADSH>(k)] = cx<T>(v.y, v.x);
+        const uint32_t k = tid + e * nthr;
+        if (k < B)
+        {
+            const Cx<T> z = s[sidx<HB_PADSH>(k)];
+            s[sidx<HB_PADSH>(k)] = cx<T>(z.y, z.x);
+        }
     }
     __syncthreads();
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, tw, tw_log2);
     const T scale = T(1) / T(size_t(4) << g.log2n);
-    T *dst = yout + size_t(ch) * ld + off;
-    for (uint32_t k = threadIdx.x; k < B / 2; k += blockDim.x)
+    if (peer.world)
     {
-        Cx<T> v = s[sidx<HB_PADSH>(k)];
-        dst[2 * k] = v.y * scale;
-        dst[2 * k + 1] = v.x * scale;
+        // partial block of output `ch` -> inbox of its owner, slot (parity, this rank, local output index)
+        const uint32_t owner = ch / peer.outs_local, o_loc = ch - owner * peer.outs_local;
+        T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(peer.parity) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
+#pragma unroll
+        for (int e = 0; e < EPT / 2; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B / 2)
+            {
+                const Cx<T> z = s[sidx<HB_PADSH>(k)];
+                st_pair(pd + 2 * k, z.y * scale, z.x * scale, true);
+            }
+        }
+        // publish: every thread's stores are ordered before the arrival count at system scope
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+        {
+            __threadfence_system();
+            atomicAdd_system(peer.count[owner] + peer.parity * peer.world + peer.rank, 1u);
+        }
+        return;
+    }
+    T *dst = yout + size_t(ch) * ld + off;
+    const bool vd = pair_aligned(yout + off, ld);
+    Pair<T> old[EPT / 2];
+    if (add_result)
+    {
+#pragma unroll
+        for (int e = 0; e < EPT / 2; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B / 2) old[e] = ld_pair(dst + 2 * k, vd);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT / 2; e++)
+    {
+        const uint32_t k = tid + e * nthr;
+        if (k < B / 2)
+        {
+            const Cx<T> z = s[sidx<HB_PADSH>(k)];
+            if (add_result) st_pair(dst + 2 * k, old[e].a + z.y * scale, old[e].b + z.x * scale, vd);
+            else st_pair(dst + 2 * k, z.y * scale, z.x * scale, vd);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gather: the owner's half of the fused exchange.  One CTA per owned output: wait until every source
+// rank has delivered this hop's blocks (arrival counter >= expected; bounded wait, a lost peer traps
+// instead of hanging the device), hand the previously finished block to the caller (carry), then sum the
+// sources in rank order into `yout` (the caller's rows or the staging rows kept for the next call).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, const uint32_t *count, uint32_t world, uint32_t outs_local,
+                                                uint32_t parity, uint64_t slot, uint32_t expected, uint32_t B,
+                                                T *__restrict__ yout, size_t ld, size_t off, int add_result,
+                                                const T *__restrict__ carry_src, size_t carry_src_ld,
+                                                T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry)
+{
+    const uint32_t o = blockIdx.x;
+    if (carry_dst)
+    {
+        const T *cs = carry_src + size_t(o) * carry_src_ld;
+        T *cd = carry_dst + size_t(o) * carry_dst_ld;
+        for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) cd[k] = add_carry ? cd[k] + cs[k] : cs[k];
+    }
+    if (threadIdx.x < world)
+    {
+        const volatile uint32_t *cnt = count + parity * world + threadIdx.x;
+        const long long t0 = clock64();
+        while (int32_t(*cnt - expected) < 0)
+            if (clock64() - t0 > (4ll << 30)) __trap();            // ~2 s at 2 GHz
+        __threadfence_system();
+    }
+    __syncthreads();
+    T *dst = yout + size_t(o) * ld + off;
+    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x)
+    {
+        T sum = T(0);
+        for (uint32_t r = 0; r < world; r++) sum += __ldcg(inbox + ((size_t(parity) * world + r) * outs_local + o) * slot + k);
+        dst[k] = add_result ? dst[k] + sum : sum;
     }
 }
 
@@ -490,7 +758,7 @@ __global__ void __launch_bounds__(1024) k_inv(const Geom g, const typename VecOf
 // (offset / length clipping already applied by the host).  Partitions past the end are written as zeros.
 // ---------------------------------------------------------------------------------------------
 template <class T, int EPT>
-__global__ void __launch_bounds__(1024) k_ir(const Geom g, const T *__restrict__ ir, size_t taps,
+__global__ void __launch_bounds__(512) k_ir(const Geom g, const T *__restrict__ ir, size_t taps,
                                              uint32_t grp, uint32_t in, uint32_t o,
                                              Cx<T> *__restrict__ H, T *__restrict__ Hnyq,
                                              const Cx<T> *__restrict__ tw, int tw_log2)
@@ -513,7 +781,7 @@ __global__ void __launch_bounds__(1024) k_ir(const Geom g, const T *__restrict__
         }
         __syncthreads();
         block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, tw, tw_log2);
-        for (uint32_t k = threadIdx.x; k <= B / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, B, (int) g.log2n, k, false, tw, tw_log2);
+        block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, tw, tw_log2);
         __syncthreads();
     }
     const uint32_t TB = tile_bins<T>(g);

@@ -6,6 +6,7 @@
 // pass are folded into the load / store stages, so every transform is one pass over global memory.
 #include "hb_common.cuh"
 #include "hb_fft_block.cuh"
+#include "hb_fft_big.cuh"
 
 #include <cmath>
 #include <mutex>
@@ -91,7 +92,7 @@ int make_twiddles(int dtype, int log2, void **d_out)
 
 // complex forward (swap = 0) / planes-exchanged forward = unscaled inverse (swap = 1), in place or not
 template <class T, int EPT>
-__global__ void __launch_bounds__(1024) k_cfft(const T *re_in, const T *im_in,
+__global__ void __launch_bounds__(512) k_cfft(const T *re_in, const T *im_in,
                                                T *re_out, T *im_out, int log2m, int swap,
                                                size_t stride, const Cx<T> *__restrict__ tw, int tw_log2)
 {
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(1024) k_cfft(const T *re_in, const T *im_in,
 // HISSTools_FFT.h:154,166) or a real array of in_length samples that is de-interleaved and zero padded on
 // the way in (HISSTools_FFT.h:180-208 = unzip_zero, Core:1258-1287, + rfft).  TI = element type of x.
 template <class T, class TI, int EPT>
-__global__ void __launch_bounds__(1024) k_rfft(const TI *__restrict__ x, size_t in_length, size_t x_stride,
+__global__ void __launch_bounds__(512) k_rfft(const TI *__restrict__ x, size_t in_length, size_t x_stride,
                                                const T *re_in, const T *im_in,
                                                T *re_out, T *im_out, size_t stride, int log2n,
                                                const Cx<T> *__restrict__ tw, int tw_log2)
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(1024) k_rfft(const TI *__restrict__ x, size_t 
     }
     __syncthreads();
     block_fft<T, EPT, HB_PADSH>(s, log2m, tw, tw_log2);
-    for (uint32_t k = threadIdx.x; k <= M / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, M, log2n, k, false, tw, tw_log2);
+    block_real_split<T, EPT, HB_PADSH>(s, M, log2n, false, tw, tw_log2);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
     {
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(1024) k_rfft(const TI *__restrict__ x, size_t 
 // HISSTools_FFT.h:244,256) and, when y != nullptr, also interleaved into the real array y
 // (HISSTools_FFT.h:269,282 = rifft + zip, Core:1228-1254).
 template <class T, int EPT>
-__global__ void __launch_bounds__(1024) k_rifft(const T *re_in, const T *im_in,
+__global__ void __launch_bounds__(512) k_rifft(const T *re_in, const T *im_in,
                                                 T *re_out, T *im_out, size_t stride,
                                                 T *__restrict__ y, size_t y_stride, int log2n,
                                                 const Cx<T> *__restrict__ tw, int tw_log2)
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(1024) k_rifft(const T *re_in, const T *im_in,
     const size_t base = size_t(blockIdx.x) * stride;
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) s[sidx<HB_PADSH>(i)] = cx<T>(re_in[base + i], im_in[base + i]);
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k <= M / 2; k += blockDim.x) real_split_pair<T, HB_PADSH>(s, M, log2n, k, true, tw, tw_log2);
+    block_real_split<T, EPT, HB_PADSH>(s, M, log2n, true, tw, tw_log2);
     __syncthreads();
     // hisstools_ifft = forward transform on exchanged planes (Core:1341-1346)
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
@@ -197,6 +198,109 @@ __global__ void __launch_bounds__(1024) k_rifft(const T *re_in, const T *im_in,
     }
 }
 
+// ---- sizes above the single-CTA limit: planes / real arrays <-> the interleaved array of hb_fft_big.cuh ----
+
+// planes -> Z (exchange = 1 swaps the planes: the unscaled inverse is a forward transform of them, Core:1341-1346)
+template <class T>
+__global__ void k_big_pack_planes(const T *__restrict__ re, const T *__restrict__ im, size_t stride, Cx<T> *__restrict__ z, int m, int exchange)
+{
+    const size_t M = size_t(1) << m;
+    const size_t b = blockIdx.y;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += size_t(gridDim.x) * blockDim.x)
+    {
+        const T a = re[b * stride + i], c = im[b * stride + i];
+        z[b * M + i] = exchange ? cx<T>(c, a) : cx<T>(a, c);
+    }
+}
+
+// real array -> Z with de-interleave and zero padding (unzip_zero, Core:1258-1287)
+template <class T, class TI>
+__global__ void k_big_pack_real(const TI *__restrict__ x, size_t in_length, size_t x_stride, Cx<T> *__restrict__ z, int m)
+{
+    const size_t M = size_t(1) << m;
+    const size_t b = blockIdx.y;
+    const TI *xb = x + b * x_stride;
+    const size_t len = in_length < 2 * M ? in_length : 2 * M, pairs = len >> 1;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += size_t(gridDim.x) * blockDim.x)
+    {
+        T a = 0, c = 0;
+        if (i < pairs) { a = (T) xb[2 * i]; c = (T) xb[2 * i + 1]; }
+        else if (i == pairs && (len & 1)) a = (T) xb[len - 1];
+        z[b * M + i] = cx<T>(a, c);
+    }
+}
+
+// Z -> planes and / or an interleaved real array (exchange = 1: the result of a planes-exchanged transform)
+template <class T>
+__global__ void k_big_unpack(const Cx<T> *__restrict__ z, int m, int exchange, T *__restrict__ re, T *__restrict__ im, size_t stride,
+                             T *__restrict__ y, size_t y_stride)
+{
+    const size_t M = size_t(1) << m;
+    const size_t b = blockIdx.y;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += size_t(gridDim.x) * blockDim.x)
+    {
+        const Cx<T> v = z[b * M + i];
+        const T a = exchange ? v.y : v.x, c = exchange ? v.x : v.y;
+        if (re) { re[b * stride + i] = a; im[b * stride + i] = c; }
+        if (y) { y[b * y_stride + 2 * i] = a; y[b * y_stride + 2 * i + 1] = c; }
+    }
+}
+
+template <class T>
+static int big_cfft_planes(BigScratch *bs, const T *re_in, const T *im_in, T *re_out, T *im_out, int log2m, int swap, size_t batch, size_t stride,
+                           const Cx<T> *tw, int tw_log2, cudaStream_t st)
+{
+    if (!bs) { set_error("complex FFT of 2^%d points needs scratch memory (use a setup-based entry point)", log2m); return HB_ERR_UNSUPPORTED; }
+    int rc = bs->ensure<T>(log2m, batch);
+    if (rc) return rc;
+    Cx<T> *z1 = (Cx<T> *) bs->z1.p, *z2 = (Cx<T> *) bs->z2.p;
+    k_big_pack_planes<T><<<big_grid(log2m, batch), 256, 0, st>>>(re_in, im_in, stride, z1, log2m, swap);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_cfft<T>(z1, z2, z1, log2m, batch, tw, tw_log2, st))) return rc;
+    k_big_unpack<T><<<big_grid(log2m, batch), 256, 0, st>>>(z1, log2m, swap, re_out, im_out, stride, (T *) nullptr, 0);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+template <class T, class TI>
+static int big_rfft(BigScratch *bs, const TI *x, size_t in_length, size_t x_stride, const T *re_in, const T *im_in, T *re_out, T *im_out,
+                    size_t stride, int log2n, size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st)
+{
+    const int m = log2n - 1;
+    if (!bs) { set_error("real FFT of 2^%d points needs scratch memory", log2n); return HB_ERR_UNSUPPORTED; }
+    int rc = bs->ensure<T>(m, batch);
+    if (rc) return rc;
+    Cx<T> *z1 = (Cx<T> *) bs->z1.p, *z2 = (Cx<T> *) bs->z2.p;
+    if (x) k_big_pack_real<T, TI><<<big_grid(m, batch), 256, 0, st>>>(x, in_length, x_stride, z1, m);
+    else k_big_pack_planes<T><<<big_grid(m, batch), 256, 0, st>>>(re_in, im_in, stride, z1, m, 0);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_cfft<T>(z1, z2, z1, m, batch, tw, tw_log2, st))) return rc;
+    if ((rc = big_split<T>(z1, m, 0, batch, tw, tw_log2, st))) return rc;
+    k_big_unpack<T><<<big_grid(m, batch), 256, 0, st>>>(z1, m, 0, re_out, im_out, stride, (T *) nullptr, 0);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+template <class T>
+static int big_rifft(BigScratch *bs, const T *re_in, const T *im_in, T *re_out, T *im_out, size_t stride, T *y, size_t y_stride, int log2n,
+                     size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st)
+{
+    const int m = log2n - 1;
+    if (!bs) { set_error("real FFT of 2^%d points needs scratch memory", log2n); return HB_ERR_UNSUPPORTED; }
+    int rc = bs->ensure<T>(m, batch);
+    if (rc) return rc;
+    Cx<T> *z1 = (Cx<T> *) bs->z1.p, *z2 = (Cx<T> *) bs->z2.p;
+    k_big_pack_planes<T><<<big_grid(m, batch), 256, 0, st>>>(re_in, im_in, stride, z1, m, 0);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_split<T>(z1, m, 1, batch, tw, tw_log2, st))) return rc;
+    k_big_exchange<T><<<big_grid(m, batch).x, 256, 0, st>>>(z1, batch << m);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_cfft<T>(z1, z2, z1, m, batch, tw, tw_log2, st))) return rc;
+    k_big_unpack<T><<<big_grid(m, batch), 256, 0, st>>>(z1, m, 1, re_out, im_out, stride, y, y_stride);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------
@@ -210,62 +314,41 @@ template <class K> static int allow_smem(K kernel, size_t bytes)
 
 template <class T>
 static int launch_cfft(const T *re_in, const T *im_in, T *re_out, T *im_out, int log2m, int swap, size_t batch, size_t stride,
-                       const Cx<T> *tw, int tw_log2, cudaStream_t st)
+                       const Cx<T> *tw, int tw_log2, cudaStream_t st, BigScratch *bs = nullptr)
 {
-    if (log2m > SmemFftLimit<T>::max_log2m) { set_error("complex FFT of 2^%d points exceeds the shared-memory path", log2m); return HB_ERR_UNSUPPORTED; }
+    if (log2m > SmemFftLimit<T>::max_log2m) return big_cfft_planes<T>(bs, re_in, im_in, re_out, im_out, log2m, swap, batch, stride, tw, tw_log2, st);
     const size_t smem = fft_smem_bytes<T>(log2m);
-    if ((1 << log2m) / 8 > 1024)
-    {
-        int rc = allow_smem(k_cfft<T, 16>, smem); if (rc) return rc;
-        k_cfft<T, 16><<<(unsigned) batch, fft_threads(log2m, 16), smem, st>>>(re_in, im_in, re_out, im_out, log2m, swap, stride, tw, tw_log2);
-    }
-    else
-    {
-        int rc = allow_smem(k_cfft<T, 8>, smem); if (rc) return rc;
-        k_cfft<T, 8><<<(unsigned) batch, fft_threads(log2m, 8), smem, st>>>(re_in, im_in, re_out, im_out, log2m, swap, stride, tw, tw_log2);
-    }
+    HB_EPT_DISPATCH(log2m,
+        int rc = allow_smem(k_cfft<T, EPT>, smem); if (rc) return rc;
+        k_cfft<T, EPT><<<(unsigned) batch, fft_threads(log2m, EPT), smem, st>>>(re_in, im_in, re_out, im_out, log2m, swap, stride, tw, tw_log2));
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
 
 template <class T, class TI>
 static int launch_rfft(const TI *x, size_t in_length, size_t x_stride, const T *re_in, const T *im_in, T *re_out, T *im_out,
-                       size_t stride, int log2n, size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st)
+                       size_t stride, int log2n, size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st, BigScratch *bs = nullptr)
 {
     const int log2m = log2n - 1;
-    if (log2m > SmemFftLimit<T>::max_log2m) { set_error("real FFT of 2^%d points exceeds the shared-memory path", log2n); return HB_ERR_UNSUPPORTED; }
+    if (log2m > SmemFftLimit<T>::max_log2m) return big_rfft<T, TI>(bs, x, in_length, x_stride, re_in, im_in, re_out, im_out, stride, log2n, batch, tw, tw_log2, st);
     const size_t smem = fft_smem_bytes<T>(log2m);
-    if ((1 << log2m) / 8 > 1024)
-    {
-        int rc = allow_smem(k_rfft<T, TI, 16>, smem); if (rc) return rc;
-        k_rfft<T, TI, 16><<<(unsigned) batch, fft_threads(log2m, 16), smem, st>>>(x, in_length, x_stride, re_in, im_in, re_out, im_out, stride, log2n, tw, tw_log2);
-    }
-    else
-    {
-        int rc = allow_smem(k_rfft<T, TI, 8>, smem); if (rc) return rc;
-        k_rfft<T, TI, 8><<<(unsigned) batch, fft_threads(log2m, 8), smem, st>>>(x, in_length, x_stride, re_in, im_in, re_out, im_out, stride, log2n, tw, tw_log2);
-    }
+    HB_EPT_DISPATCH(log2m,
+        int rc = allow_smem(k_rfft<T, TI, EPT>, smem); if (rc) return rc;
+        k_rfft<T, TI, EPT><<<(unsigned) batch, fft_threads(log2m, EPT), smem, st>>>(x, in_length, x_stride, re_in, im_in, re_out, im_out, stride, log2n, tw, tw_log2));
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
 
 template <class T>
 static int launch_rifft(const T *re_in, const T *im_in, T *re_out, T *im_out, size_t stride, T *y, size_t y_stride, int log2n,
-                        size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st)
+                        size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st, BigScratch *bs = nullptr)
 {
     const int log2m = log2n - 1;
-    if (log2m > SmemFftLimit<T>::max_log2m) { set_error("real FFT of 2^%d points exceeds the shared-memory path", log2n); return HB_ERR_UNSUPPORTED; }
+    if (log2m > SmemFftLimit<T>::max_log2m) return big_rifft<T>(bs, re_in, im_in, re_out, im_out, stride, y, y_stride, log2n, batch, tw, tw_log2, st);
     const size_t smem = fft_smem_bytes<T>(log2m);
-    if ((1 << log2m) / 8 > 1024)
-    {
-        int rc = allow_smem(k_rifft<T, 16>, smem); if (rc) return rc;
-        k_rifft<T, 16><<<(unsigned) batch, fft_threads(log2m, 16), smem, st>>>(re_in, im_in, re_out, im_out, stride, y, y_stride, log2n, tw, tw_log2);
-    }
-    else
-    {
-        int rc = allow_smem(k_rifft<T, 8>, smem); if (rc) return rc;
-        k_rifft<T, 8><<<(unsigned) batch, fft_threads(log2m, 8), smem, st>>>(re_in, im_in, re_out, im_out, stride, y, y_stride, log2n, tw, tw_log2);
-    }
+    HB_EPT_DISPATCH(log2m,
+        int rc = allow_smem(k_rifft<T, EPT>, smem); if (rc) return rc;
+        k_rifft<T, EPT><<<(unsigned) batch, fft_threads(log2m, EPT), smem, st>>>(re_in, im_in, re_out, im_out, stride, y, y_stride, log2n, tw, tw_log2));
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
@@ -286,6 +369,7 @@ struct hb_fft_setup
     void *tw = nullptr;
     cudaStream_t stream = nullptr;
     DevBuf d_a, d_b, d_c;       // planes / real array scratch
+    BigScratch big;             // interleaved arrays of the four-step path
     std::mutex lock;
 };
 
@@ -302,7 +386,8 @@ extern "C" int hb_fft_setup_create(hb_fft_setup **out, int dtype, uintptr_t max_
     hb_fft_setup *s = new hb_fft_setup;
     s->dtype = dtype; s->device = device; s->max_log2 = (int) max_fft_log2;
     // the table serves complex transforms of 2^max and real ones of 2^max (which need order-2^max roots)
-    int lim = (dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m) + 1;
+    // (sizes above the shared-memory limit take the four-step path: complex up to 2^22, real up to 2^23 points)
+    int lim = BIG_MAX_LOG2 + 1;
     s->tw_log2 = s->max_log2 < 1 ? 1 : (s->max_log2 > lim ? lim : s->max_log2);
     rc = make_twiddles(dtype, s->tw_log2, &s->tw);
     if (rc) { delete s; return rc; }
@@ -317,6 +402,7 @@ extern "C" void hb_fft_setup_destroy(hb_fft_setup *s)
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     s->d_a.release(); s->d_b.release(); s->d_c.release();
+    s->big.release();
     cudaFree(s->tw);
     cudaStreamDestroy(s->stream);
     delete s;
@@ -332,6 +418,7 @@ int inplace_op(hb_fft_setup *s, Op op, T *re, T *im, uintptr_t log2n)
     const bool real = (op == OP_RFFT || op == OP_RIFFT);
     if (log2n == 0) return HB_OK;                       // hisstools_fft of one point is a no-op (Core:1328-1336)
     if ((int) log2n > s->max_log2) { set_error("log2n %d exceeds the setup's maximum %d", (int) log2n, s->max_log2); return HB_ERR_BAD_ARG; }
+    if ((int) log2n - (real ? 1 : 0) > BIG_MAX_LOG2) { set_error("transforms above 2^%d complex points are not implemented", BIG_MAX_LOG2); return HB_ERR_UNSUPPORTED; }
     const size_t planes = real ? (size_t(1) << (log2n - 1)) : (size_t(1) << log2n);
     const size_t bytes = planes * sizeof(T);
     int rc;
@@ -342,10 +429,10 @@ int inplace_op(hb_fft_setup *s, Op op, T *re, T *im, uintptr_t log2n)
     HB_CUDA(cudaMemcpyAsync(d_im, im, bytes, cudaMemcpyHostToDevice, s->stream));
     switch (op)
     {
-        case OP_FFT:   rc = launch_cfft<T>(d_re, d_im, d_re, d_im, (int) log2n, 0, 1, 0, tw, s->tw_log2, s->stream); break;
-        case OP_IFFT:  rc = launch_cfft<T>(d_re, d_im, d_re, d_im, (int) log2n, 1, 1, 0, tw, s->tw_log2, s->stream); break;
-        case OP_RFFT:  rc = launch_rfft<T, T>(nullptr, 0, 0, d_re, d_im, d_re, d_im, 0, (int) log2n, 1, tw, s->tw_log2, s->stream); break;
-        case OP_RIFFT: rc = launch_rifft<T>(d_re, d_im, d_re, d_im, 0, nullptr, 0, (int) log2n, 1, tw, s->tw_log2, s->stream); break;
+        case OP_FFT:   rc = launch_cfft<T>(d_re, d_im, d_re, d_im, (int) log2n, 0, 1, 0, tw, s->tw_log2, s->stream, &s->big); break;
+        case OP_IFFT:  rc = launch_cfft<T>(d_re, d_im, d_re, d_im, (int) log2n, 1, 1, 0, tw, s->tw_log2, s->stream, &s->big); break;
+        case OP_RFFT:  rc = launch_rfft<T, T>(nullptr, 0, 0, d_re, d_im, d_re, d_im, 0, (int) log2n, 1, tw, s->tw_log2, s->stream, &s->big); break;
+        case OP_RIFFT: rc = launch_rifft<T>(d_re, d_im, d_re, d_im, 0, nullptr, 0, (int) log2n, 1, tw, s->tw_log2, s->stream, &s->big); break;
     }
     if (rc) return rc;
     HB_CUDA(cudaMemcpyAsync(re, d_re, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -381,7 +468,7 @@ int rfft_real_host(hb_fft_setup *s, const TI *input, T *re, T *im, uintptr_t in_
     if ((rc = s->d_a.ensure(half * sizeof(T))) || (rc = s->d_b.ensure(half * sizeof(T))) || (rc = s->d_c.ensure((len ? len : 1) * sizeof(TI)))) return rc;
     if (len) HB_CUDA(cudaMemcpyAsync(s->d_c.p, input, len * sizeof(TI), cudaMemcpyHostToDevice, s->stream));
     rc = launch_rfft<T, TI>((const TI *) s->d_c.p, len, 0, nullptr, nullptr, (T *) s->d_a.p, (T *) s->d_b.p, 0, (int) log2n, 1,
-                            (const Cx<T> *) s->tw, s->tw_log2, s->stream);
+                            (const Cx<T> *) s->tw, s->tw_log2, s->stream, &s->big);
     if (rc) return rc;
     HB_CUDA(cudaMemcpyAsync(re, s->d_a.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
     HB_CUDA(cudaMemcpyAsync(im, s->d_b.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
@@ -398,7 +485,7 @@ int rifft_real_host(hb_fft_setup *s, T *re, T *im, T *output, uintptr_t log2n)
     HB_CUDA(cudaMemcpyAsync(s->d_a.p, re, half * sizeof(T), cudaMemcpyHostToDevice, s->stream));
     HB_CUDA(cudaMemcpyAsync(s->d_b.p, im, half * sizeof(T), cudaMemcpyHostToDevice, s->stream));
     rc = launch_rifft<T>((const T *) s->d_a.p, (const T *) s->d_b.p, (T *) s->d_a.p, (T *) s->d_b.p, 0, (T *) s->d_c.p, 0, (int) log2n, 1,
-                         (const Cx<T> *) s->tw, s->tw_log2, s->stream);
+                         (const Cx<T> *) s->tw, s->tw_log2, s->stream, &s->big);
     if (rc) return rc;
     HB_CUDA(cudaMemcpyAsync(re, s->d_a.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
     HB_CUDA(cudaMemcpyAsync(im, s->d_b.p, half * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
@@ -443,9 +530,9 @@ extern "C" int hb_rfft_real_batched_dev(hb_fft_setup *s, const void *d_input, vo
     const size_t n = size_t(1) << log2n;
     if (s->dtype == HB_F64)
         return launch_rfft<double, double>((const double *) d_input, n, in_stride, nullptr, nullptr, (double *) d_re, (double *) d_im, out_stride,
-                                           (int) log2n, batch, (const Cx<double> *) s->tw, s->tw_log2, st);
+                                           (int) log2n, batch, (const Cx<double> *) s->tw, s->tw_log2, st, &s->big);
     return launch_rfft<float, float>((const float *) d_input, n, in_stride, nullptr, nullptr, (float *) d_re, (float *) d_im, out_stride,
-                                     (int) log2n, batch, (const Cx<float> *) s->tw, s->tw_log2, st);
+                                     (int) log2n, batch, (const Cx<float> *) s->tw, s->tw_log2, st, &s->big);
 }
 
 extern "C" int hb_rifft_real_batched_dev(hb_fft_setup *s, const void *d_re, const void *d_im, void *d_output, uintptr_t log2n, uintptr_t batch,
@@ -457,7 +544,7 @@ extern "C" int hb_rifft_real_batched_dev(hb_fft_setup *s, const void *d_re, cons
     cudaStream_t st = stream ? (cudaStream_t) stream : s->stream;
     if (s->dtype == HB_F64)
         return launch_rifft<double>((const double *) d_re, (const double *) d_im, nullptr, nullptr, in_stride, (double *) d_output, out_stride,
-                                    (int) log2n, batch, (const Cx<double> *) s->tw, s->tw_log2, st);
+                                    (int) log2n, batch, (const Cx<double> *) s->tw, s->tw_log2, st, &s->big);
     return launch_rifft<float>((const float *) d_re, (const float *) d_im, nullptr, nullptr, in_stride, (float *) d_output, out_stride,
-                               (int) log2n, batch, (const Cx<float> *) s->tw, s->tw_log2, st);
+                               (int) log2n, batch, (const Cx<float> *) s->tw, s->tw_log2, st, &s->big);
 }

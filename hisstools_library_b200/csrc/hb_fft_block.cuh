@@ -45,6 +45,78 @@ __device__ __forceinline__ void block_fft(Cx<T> *s, int log2m, const Cx<T> *__re
     }
 }
 
+// Real <-> half-complex split pass over the whole array (pairs k and M-k, k = 0 .. M/2), every thread
+// taking up to EPT/2 + 1 pairs.  All shared-memory and twiddle loads of a thread are issued before the
+// first dependent arithmetic (the pairs are disjoint), so their latencies overlap.  Callers put a
+// barrier before and after.
+template <class T, int EPT, int PADSH>
+__device__ __forceinline__ void block_real_split(Cx<T> *s, uint32_t M, int log2N, bool inverse, const Cx<T> *__restrict__ tw, int tw_log2)
+{
+    constexpr int NP = EPT / 2 + 1;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    Cx<T> a[NP], b[NP], w[NP];
+#pragma unroll
+    for (int e = 0; e < NP; e++)
+    {
+        const uint32_t k = tid + e * nthr;
+        if (k <= M / 2)
+        {
+            a[e] = s[sidx<PADSH>(k)];
+            b[e] = s[sidx<PADSH>(k ? M - k : 0)];
+            w[e] = tw_root(tw, tw_log2, k, log2N);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NP; e++)
+    {
+        const uint32_t k = tid + e * nthr;
+        if (k <= M / 2)
+        {
+            if (k == 0)
+            {
+                const T t1 = a[e].x + a[e].y, t2 = a[e].x - a[e].y;
+                s[sidx<PADSH>(0)] = inverse ? cx<T>(t1, t2) : cx<T>(t1 + t1, t2 + t2);
+            }
+            else
+            {
+                const T sr = a[e].x + b[e].x, si = a[e].y + b[e].y, dr = a[e].x - b[e].x, di = a[e].y - b[e].y;
+                const T wr = inverse ? -w[e].x : w[e].x, wi = w[e].y;
+                const T u = wr * si + wi * dr;
+                const T v = wi * si - wr * dr;
+                s[sidx<PADSH>(k)] = cx<T>(sr + u, v + di);
+                s[sidx<PADSH>(M - k)] = cx<T>(sr - u, v - di);
+            }
+        }
+    }
+}
+
+// Roots of order 2^log2n (half circle, 2^(log2n-1) entries = one per point of the complex array of a real
+// transform) copied from the device table into shared memory, EPT per thread.  The loads are returned in
+// registers so that the caller can issue them together with its own input loads and store later.
+template <class T, int EPT>
+__device__ __forceinline__ void twiddle_stage_load(Cx<T> *r, const Cx<T> *__restrict__ tw, int tw_log2, int log2n)
+{
+    const uint32_t half = 1u << (log2n - 1);
+    const int sh = tw_log2 - log2n;
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
+    {
+        const uint32_t q = threadIdx.x + e * blockDim.x;
+        if (q < half) r[e] = tw[size_t(q) << sh];
+    }
+}
+template <class T, int EPT>
+__device__ __forceinline__ void twiddle_stage_store(Cx<T> *stw, const Cx<T> *r, int log2n)
+{
+    const uint32_t half = 1u << (log2n - 1);
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
+    {
+        const uint32_t q = threadIdx.x + e * blockDim.x;
+        if (q < half) stw[q] = r[e];
+    }
+}
+
 // default shared-memory padding: one slot per 32 elements
 #ifndef HB_PADSH
 #define HB_PADSH 5
@@ -61,5 +133,16 @@ inline int fft_threads(int log2m, int ept)
     if (t < 32) t = 32;
     return (t + 31) & ~31;
 }
+
+// Points per thread for a transform of 2^log2m complex points: 8 up to 4096 points, then as many as keep
+// the CTA at 512 threads (every FFT kernel is compiled with __launch_bounds__(512): 128 registers per thread).
+// Usage: HB_EPT_DISPATCH(log2m, launch<T, EPT>(...));
+#define HB_EPT_DISPATCH(log2m, ...)                                            \
+    do                                                                         \
+    {                                                                          \
+        if ((log2m) <= 12) { constexpr int EPT = 8; __VA_ARGS__; }             \
+        else if ((log2m) == 13) { constexpr int EPT = 16; __VA_ARGS__; }       \
+        else { constexpr int EPT = 32; __VA_ARGS__; }                          \
+    } while (0)
 
 } // namespace hb

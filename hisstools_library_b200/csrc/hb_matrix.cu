@@ -414,6 +414,9 @@ extern "C" int hb_matrix_process(hb_matrix *m, const void *const *ins, void *con
     std::unique_lock<std::mutex> g(m->lock, std::try_to_lock);
     if (!g.owns_lock()) return HB_ERR_BUSY;
     if (!n) return HB_OK;
+    // a single uniform part (no head, one FFT size) is exactly one engine: its host path defers the device
+    // work of hop-aligned calls behind the API's own one-hop latency (hb_conv_process)
+    if (!m->head_taps && m->parts.size() == 1) return hb_conv_process(m->parts[0], ins, outs, n, accumulate);
     bool loaded = m->head_count != 0;
     for (hb_conv *p : m->parts) loaded = loaded || hb_conv_partitions(p) != 0;
     if (!loaded) return HB_ERR_NO_IR;

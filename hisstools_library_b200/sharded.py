@@ -58,6 +58,21 @@ class _CudaMatrixEngine:
         """x [ins, >=n], y [outs, >=n] contiguous-row CUDA tensors; y is overwritten.  True when written."""
         return self.m.process_device(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n, False, stream)
 
+    # the exchange fused into the inverse-FFT epilogue needs ONE uniform engine (no head, one FFT size)
+    def can_fuse(self):
+        return self.m.head_taps == 0 and len(self.m.engines) == 1
+
+    def shard_export(self, world, rank):
+        return self.m.tail.shard_export(world, rank)
+
+    def shard_attach(self, handles):
+        self.m.tail.shard_attach(handles)
+
+    def process_shard_tensor(self, x, y_shard, n, stream):
+        """x [local ins, >=n]; y_shard [outs/world, >=n] receives this rank's complete output rows."""
+        from . import _abi
+        return self.m.tail.process_shard_device(x.data_ptr(), x.stride(0), y_shard.data_ptr(), y_shard.stride(0), n, False, stream) == _abi.HB_OK
+
     def close(self):
         self.m.close()
 
@@ -70,7 +85,8 @@ class ShardedConvolver:
     process_device(x_local, y_shard, n): x_local holds this rank's input rows [local_ins, n], y_shard
     receives this rank's output rows [local_outs, n] (the full sum over all inputs)."""
 
-    def __init__(self, numIns, numOuts, *scheme, maxLength=16384, dtype=np.float32, device=None, group=None, engine_factory=None):
+    def __init__(self, numIns, numOuts, *scheme, maxLength=16384, dtype=np.float32, device=None, group=None, engine_factory=None,
+                 exchange="auto"):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -85,6 +101,35 @@ class ShardedConvolver:
         self.engine = factory(self.plan.local_ins, self.plan.num_outs, maxLength, _scheme(scheme), dtype, device)
         self._partial = None
         self.backend = dist.get_backend(group) if dist.is_initialized() else None
+        # exchange: "fused" = partial blocks stored straight into the owner's memory by the inverse-FFT kernel
+        # (peer-mapped inboxes over NVLink, hb_conv_shard_*); "nccl" = reduce-scatter of a local partial buffer;
+        # "auto" = fused when the engine and the topology allow it
+        self.exchange = "nccl"
+        if exchange not in ("auto", "fused", "nccl"):
+            raise ValueError("exchange must be auto, fused or nccl")
+        if exchange != "nccl" and self.world > 1 and self.backend == "nccl" and getattr(self.engine, "can_fuse", lambda: False)():
+            ok = 1
+            try:
+                handle = self.engine.shard_export(self.world, self.rank)
+            except Exception:
+                handle, ok = b"", 0
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (ok, handle), group=group)
+            if all(h[0] for h in handles):
+                try:
+                    self.engine.shard_attach([h[1] for h in handles])
+                except Exception:
+                    ok = 0
+            else:
+                ok = 0
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok, group=group)
+            if all(flags):
+                self.exchange = "fused"
+            elif exchange == "fused":
+                raise RuntimeError("fused exchange requested but peer memory could not be mapped on every rank")
+        elif exchange == "fused":
+            raise RuntimeError("fused exchange needs world > 1, the nccl backend and a single uniform partition size")
 
     def setResetOffset(self, offset=-1):
         self.engine.set_reset_offset(offset)
@@ -114,6 +159,8 @@ class ShardedConvolver:
         """One block: local partial outputs for every output channel, then the sum over ranks.
         Returns True when y_shard was written (some rank had an IR loaded)."""
         dist = self.dist
+        if self.exchange == "fused":
+            return self.engine.process_shard_tensor(x_local, y_shard, n, stream)
         part = self._partial_like(y_shard, n)
         pv = part[:, :n] if part.shape[1] != n else part
         wrote = self.engine.process_tensor(x_local, part, n, stream)

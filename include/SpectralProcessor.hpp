@@ -1,0 +1,65 @@
+// SpectralProcessor.hpp -- B200 drop-in for the convolution part of the reference's
+// spectral_processor<T> (SpectralProcessor.hpp:11-683): convolve(T*, in_ptr, in_ptr, EdgeMode),
+// convolved_size, set_max_fft_size / max_fft_size.  The transforms, the per-bin product
+// (SpectralFunctions.hpp:63-84,274-281) and the edge-mode arrangement (:445-481) run on the GPU through
+// hb_spectral_* of hisstools_b200.h.  correlate / change_phase / the complex-input overloads are not
+// part of the convolution path and are not provided.
+#ifndef HISSTOOLS_B200_SPECTRALPROCESSOR_HPP
+#define HISSTOOLS_B200_SPECTRALPROCESSOR_HPP
+
+#include <cstdint>
+#include <type_traits>
+
+#include "HISSTools_FFT/HISSTools_FFT.h"
+
+template <typename T>
+class spectral_processor
+{
+    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value, "float or double");
+
+public:
+
+    enum class EdgeMode { Linear, Wrap, WrapCentre, Fold, FoldRepeat };
+
+    struct in_ptr
+    {
+        in_ptr(const T* ptr, uintptr_t size) : m_ptr(ptr), m_size(size) {}
+
+        const T* m_ptr;
+        const uintptr_t m_size;
+    };
+
+    spectral_processor(uintptr_t max_fft_size = 32768, int device = 0) : m_handle(nullptr)
+    {
+        hisstools_b200_detail::check(hb_spectral_create(&m_handle, std::is_same<T, double>::value ? HB_F64 : HB_F32, max_fft_size, device));
+    }
+    ~spectral_processor() { hb_spectral_destroy(m_handle); }
+
+    spectral_processor(const spectral_processor&) = delete;
+    spectral_processor &operator =(const spectral_processor&) = delete;
+    spectral_processor(spectral_processor&& b) : m_handle(b.m_handle) { b.m_handle = nullptr; }
+    spectral_processor &operator =(spectral_processor&& b)
+    {
+        if (this != &b) { hb_spectral_destroy(m_handle); m_handle = b.m_handle; b.m_handle = nullptr; }
+        return *this;
+    }
+
+    void set_max_fft_size(uintptr_t size) { hisstools_b200_detail::check(hb_spectral_set_max_fft_size(m_handle, size)); }
+    uintptr_t max_fft_size() const { return hb_spectral_max_fft_size(m_handle); }
+
+    void convolve(T *output, in_ptr in1, in_ptr in2, EdgeMode mode)
+    {
+        hisstools_b200_detail::check(hb_spectral_convolve(m_handle, output, in1.m_ptr, in1.m_size, in2.m_ptr, in2.m_size, static_cast<int>(mode), nullptr));
+    }
+
+    uintptr_t convolved_size(uintptr_t size1, uintptr_t size2, EdgeMode mode) const
+    {
+        return hb_spectral_convolved_size(m_handle, size1, size2, static_cast<int>(mode));
+    }
+
+private:
+
+    hb_spectral *m_handle;
+};
+
+#endif

@@ -142,6 +142,22 @@ int hb_conv_process(hb_conv *c, const void *const *ins, void *const *outs, uintp
 int hb_conv_process_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out, uintptr_t out_ld,
                         uintptr_t num_samples, int accumulate, void *stream);
 
+/* Multi-GPU: the N x M matrix with its INPUT channels sharded over `world` ranks (one process per GPU).
+ * The sum over inputs of NToMonoConvolve.cpp:39-42 then crosses devices; it is fused into the inverse-FFT
+ * epilogue: every rank stores each partial output block straight into the inbox of the rank that owns
+ * that output (peer-mapped memory, NVLink) and the owner sums the arrivals in rank order.
+ *   export: allocate this rank's inbox and return its CUDA IPC handle (HB_IPC_HANDLE_BYTES bytes);
+ *   attach: after the callers exchanged the handles (any transport), open all of them (rank order);
+ *   process_shard_dev: one hop-aligned call (num_samples a multiple of fft_size/2, reset offset 0) with
+ *   this rank's `ins` input rows; d_out_shard receives this rank's outs/world output rows (outputs
+ *   rank*outs/world ...), complete sums, delayed by fft_size/2 as ever.  Every rank must make the same
+ *   calls; reset / set_ir are collective in that sense. */
+#define HB_IPC_HANDLE_BYTES 64
+int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, void *handle_out);
+int hb_conv_shard_attach(hb_conv *c, const void *handles);
+int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out_shard, uintptr_t out_ld,
+                              uintptr_t num_samples, int accumulate, void *stream);
+
 /* tuning / introspection used by bench.py and the tests */
 /* CTAs per SM for the multiply-accumulate kernel (0 = library default) */
 int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant);
@@ -192,6 +208,28 @@ int hb_matrix_process_dev(hb_matrix *m, const void *d_in, uintptr_t in_ld, void 
 uint32_t hb_matrix_parts(const hb_matrix *m);
 hb_conv *hb_matrix_part(hb_matrix *m, uint32_t index);
 uint32_t hb_matrix_head_taps(const hb_matrix *m);
+
+/* ---------------------------------------------------------------------------------------------
+ * One-shot FFT convolution of two real buffers -- replaces spectral_processor<T>::convolve(T *output,
+ * in_ptr in1, in_ptr in2, EdgeMode mode) (SpectralProcessor.hpp:169-172, 616-674) with its per-bin
+ * product ir_convolve_real (SpectralFunctions.hpp:420-424, 63-84, 274-281).
+ * mode: 0 Linear (n1+n2-1 samples), 1 Wrap, 2 WrapCentre, 3 Fold, 4 FoldRepeat (max(n1,n2) samples;
+ * SpectralProcessor.hpp:22, 445-481).  Host pointers of the handle's dtype.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hb_spectral hb_spectral;
+
+/* spectral_processor(max_fft_size = 32768): SpectralProcessor.hpp:35-42 */
+int hb_spectral_create(hb_spectral **out, int dtype, uintptr_t max_fft_size, int device);
+void hb_spectral_destroy(hb_spectral *s);
+/* set_max_fft_size / max_fft_size: SpectralProcessor.hpp:96-110 */
+int hb_spectral_set_max_fft_size(hb_spectral *s, uintptr_t max_fft_size);
+uintptr_t hb_spectral_max_fft_size(const hb_spectral *s);
+/* convolved_size: SpectralProcessor.hpp:210-213, 546-557 (0 = the operation would not run) */
+uintptr_t hb_spectral_convolved_size(const hb_spectral *s, uintptr_t n1, uintptr_t n2, int mode);
+/* convolve: *written = samples stored in output (0 when an input is empty or the FFT would exceed the
+ * maximum -- the reference silently returns, SpectralProcessor.hpp:651-652) */
+int hb_spectral_convolve(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2,
+                         int mode, uintptr_t *written);
 
 #ifdef __cplusplus
 }

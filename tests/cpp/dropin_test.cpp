@@ -5,6 +5,7 @@
 // the oracle.  Usage: dropin_test <output file>
 #include "HISSTools_FFT/HISSTools_FFT.h"
 #include "HIRT_Multichannel_Convolution/Convolver.h"
+#include "SpectralProcessor.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -149,6 +150,19 @@ int main(int argc, char **argv)
         float *outs[4] = { ys[0].data(), ys[1].data(), ys[2].data(), ys[3].data() };
         cv.process(ins, outs, 4, 4, 2048);
         for (auto &y : ys) dump(y);
+    }
+
+    // 7. spectral_processor<float>::convolve, Linear and WrapCentre
+    {
+        spectral_processor<float> sp;
+        std::vector<float> a = noise(900, 90), b = decaying(250, 91), lin(1149), wc(900);
+        dump_code(int(sp.convolved_size(900, 250, spectral_processor<float>::EdgeMode::Linear)));
+        sp.convolve(lin.data(), spectral_processor<float>::in_ptr(a.data(), a.size()), spectral_processor<float>::in_ptr(b.data(), b.size()),
+                    spectral_processor<float>::EdgeMode::Linear);
+        dump(lin);
+        sp.convolve(wc.data(), spectral_processor<float>::in_ptr(a.data(), a.size()), spectral_processor<float>::in_ptr(b.data(), b.size()),
+                    spectral_processor<float>::EdgeMode::WrapCentre);
+        dump(wc);
     }
 
     fclose(out_file);

@@ -128,4 +128,11 @@ def test_cpp_dropin_results():
     assert [code() for _ in range(5)] == [0, 0, 0, 0, 1]
     for i in range(4):
         assert ck.rel_rms(take(2048), ck.direct_convolve_delayed(irs[i], xs[i], 128)) <= TOL32
+    # 7. spectral_processor<float>::convolve
+    a, b = lcg_noise(900, 90), decaying(250, 91)
+    assert code() == 1149
+    assert ck.rel_rms(take(1149), np.convolve(a.astype(np.float64), b.astype(np.float64))) <= TOL32
+    want = np.zeros(1200, np.float32)
+    size = lib.orc_spectral_convolve_f32(ck.fptr(want), ck.fptr(a), 900, ck.fptr(b), 250, 2, 32768)
+    assert size == 900 and ck.rel_rms(take(900), want[:900]) <= TOL32
     assert pos[0] == len(data)

@@ -16,8 +16,9 @@ pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz"))
 TOL = {"_f32": 1e-5, "_f64": 1e-12}
 DT = {"_f32": np.float32, "_f64": np.float64}
-# largest transform of the single-CTA shared-memory path (complex points): 2^14 float, 2^13 double
-MAX_C = {"_f32": 14, "_f64": 13}
+# largest complex transform exercised here (the reference's FFT_Tester runs every log2n up to 21): sizes above
+# 2^14 float / 2^13 double leave the single-CTA shared-memory path for the four-step global-memory path
+MAX_C = {"_f32": 20, "_f64": 20}
 
 
 @pytest.fixture(scope="module")
@@ -28,7 +29,7 @@ def hb():
 
 @pytest.fixture(scope="module")
 def setups(hb):
-    s = {"_f32": hb.hisstools_create_setup(15, np.float32), "_f64": hb.hisstools_create_setup(14, np.float64)}
+    s = {"_f32": hb.hisstools_create_setup(21, np.float32), "_f64": hb.hisstools_create_setup(21, np.float64)}
     yield s
     for v in s.values():
         hb.hisstools_destroy_setup(v)
@@ -102,7 +103,7 @@ def test_conventions_and_round_trips(hb, setups, suf):
     """2*DFT with packed DC/Nyquist, rifft(rfft(x)) = 2N x, ifft(fft(z)) = N z."""
     dt = DT[suf]
     rng = np.random.default_rng(11)
-    for log2n in (4, 7, 11, 13):
+    for log2n in (4, 7, 11, 13, 16, 19):
         n = 1 << log2n
         x = rng.uniform(-1, 1, n).astype(dt)
         sp = hb.Split.zeros(n >> 1, dt)
@@ -138,3 +139,24 @@ def test_linearity_full_size(hb, setups):
         hb.hisstools_rfft(setups["_f32"], sig, sp, n, 15)
         out.append(np.concatenate([sp.realp, sp.imagp]).astype(np.float64))
     assert ck.rel_rms(out[2], 0.5 * out[0] - 2.0 * out[1]) <= 1e-5
+
+
+@pytest.mark.parametrize("suf", ["_f32", "_f64"])
+def test_out_of_place_real_large(hb, setups, suf):
+    """zero-padded out-of-place real transform and zipped inverse on the four-step path (2^17 points)."""
+    dt = DT[suf]
+    log2n, in_length = 17, 100001
+    n = 1 << log2n
+    x = np.random.default_rng(17).uniform(-1, 1, in_length).astype(dt)
+    sp = hb.Split.zeros(n >> 1, dt)
+    hb.hisstools_rfft(setups[suf], x, sp, in_length, log2n)
+    xp = np.zeros(n)
+    xp[:in_length] = x
+    spec = 2 * np.fft.rfft(xp)
+    want = np.concatenate([spec.real[:n >> 1], spec.imag[:n >> 1]])
+    want[n >> 1] = spec.real[n >> 1]                         # Nyquist packed into imagp[0]
+    assert ck.rel_rms(np.concatenate([sp.realp, sp.imagp]), want) <= TOL[suf]
+    back = np.zeros(n, dt)
+    hb.hisstools_rifft(setups[suf], sp, back, log2n)
+    assert ck.rel_rms(back, 2.0 * n * xp) <= TOL[suf]
+    assert np.array_equal(sp.realp, back[0::2]) and np.array_equal(sp.imagp, back[1::2])

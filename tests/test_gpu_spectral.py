@@ -1,0 +1,103 @@
+"""GPU parity of the one-shot spectral convolution (spectral_processor<T>::convolve, SpectralProcessor.hpp:169-172)
+against the golden vectors produced by the unmodified reference, the plain-C oracle, the compiled
+reference where shipped, and float64 direct convolution.  Tolerances: 1e-5 float, 1e-12 double."""
+import os
+
+import numpy as np
+import pytest
+
+import checkers as ck
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz"))
+TOL = {"f32": 1e-5, "f64": 1e-12}
+DT = {"f32": np.float32, "f64": np.float64}
+# FFT sizes above 2^15 (float) / 2^14 (double) take the four-step global-memory path
+MAXFFT = {"f32": 65536, "f64": 32768}
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hisstools_library_b200 as h
+    return h
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("n1,n2", [(1000, 300), (300, 1000), (64, 64), (7, 2), (1, 9)])
+def test_golden_all_edge_modes(hb, suf, n1, n2):
+    sp = hb.spectral_processor(MAXFFT[suf], DT[suf])
+    a, b = G["spec_%s_%d_%d_a" % (suf, n1, n2)], G["spec_%s_%d_%d_b" % (suf, n1, n2)]
+    for mode in range(5):
+        want = G["spec_%s_%d_%d_m%d" % (suf, n1, n2, mode)]
+        assert sp.convolved_size(n1, n2, mode) == len(want)
+        out = np.zeros(len(want) + 3, DT[suf])
+        assert sp.convolve(out, a, b, mode) == len(want)
+        assert ck.rel_rms(out[:len(want)], want) <= TOL[suf], (suf, n1, n2, mode)
+        assert np.all(out[len(want):] == 0)
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_against_oracle_and_direct(hb, suf):
+    dt = DT[suf]
+    lib = ck.oracle()
+    fn = getattr(lib, "orc_spectral_convolve_" + suf)
+    sp = hb.spectral_processor(MAXFFT[suf], dt)
+    rng = np.random.default_rng(21)
+    for n1, n2 in [(1, 1), (1, 2), (2, 1), (2, 2), (3, 5), (16, 16), (129, 64), (4000, 4000), (12000, 3000), (20000, 12000), (40000, 20000)]:
+        a = rng.uniform(-1, 1, n1).astype(dt)
+        b = (rng.standard_normal(n2) * np.exp(-3.0 * np.arange(n2) / n2)).astype(dt)
+        for mode in range(5):
+            want = np.zeros(n1 + n2, dt)
+            size = fn(ck.fptr(want), ck.fptr(a), n1, ck.fptr(b), n2, mode, MAXFFT[suf])
+            got = np.zeros(n1 + n2, dt)
+            assert sp.convolve(got, a, b, mode) == size, (n1, n2, mode)
+            if size:
+                assert ck.rel_rms(got[:size], want[:size]) <= TOL[suf], (suf, n1, n2, mode)
+        if n1 + n2 - 1 > MAXFFT[suf]:
+            continue
+        lin = np.zeros(n1 + n2 - 1, dt)
+        sp.convolve(lin, a, b, hb.EdgeMode.Linear)
+        truth = np.convolve(a.astype(np.float64), b.astype(np.float64))
+        assert ck.rel_rms(lin, truth) <= TOL[suf]
+        # Wrap = circular convolution of period max(n1, n2)
+        mx = max(n1, n2)
+        wrap = np.zeros(mx, dt)
+        sp.convolve(wrap, a, b, hb.EdgeMode.Wrap)
+        circ = truth[:mx].copy()
+        circ[:len(truth) - mx] += truth[mx:]
+        assert ck.rel_rms(wrap, circ) <= TOL[suf]
+
+
+def test_limits_and_noops(hb):
+    sp = hb.spectral_processor(1024)
+    assert sp.max_fft_size() == 1024
+    out = np.full(2000, 5.0, np.float32)
+    a, b = ck.synth_audio(700, 1), ck.synth_audio(400, 2)
+    assert sp.convolved_size(700, 400, 0) == 0                      # needs 2048 > max 1024
+    assert sp.convolve(out, a, b, 0) == 0 and np.all(out == 5.0)    # silently does nothing (SpectralProcessor.hpp:651-652)
+    assert sp.convolve(out, a[:0], b, 0) == 0 and np.all(out == 5.0)
+    sp.set_max_fft_size(2048)
+    assert sp.convolve(out, a, b, 0) == 1099
+    assert ck.rel_rms(out[:1099], np.convolve(a.astype(np.float64), b.astype(np.float64))) <= 1e-5
+    sp.set_max_fft_size(1000)                                       # rounds up to 1024
+    assert sp.max_fft_size() == 1024
+    with pytest.raises(hb.HissError):
+        hb.spectral_processor(1 << 25)                              # beyond what this build implements
+
+
+def test_against_compiled_reference(hb):
+    rs = ck.ref_spectral()
+    if rs is None:
+        pytest.skip("compiled reference not shipped")
+    rng = np.random.default_rng(5)
+    for suf, dt in (("f32", np.float32), ("f64", np.float64)):
+        sp = hb.spectral_processor(MAXFFT[suf], dt)
+        a = rng.uniform(-1, 1, 5000).astype(dt)
+        b = rng.uniform(-1, 1, 1234).astype(dt)
+        for mode in range(5):
+            want = np.zeros(7000, dt)
+            size = getattr(rs, "ref_spectral_convolve_" + suf)(ck.fptr(want), ck.fptr(a), 5000, ck.fptr(b), 1234, mode, MAXFFT[suf])
+            got = np.zeros(7000, dt)
+            assert sp.convolve(got, a, b, mode) == size
+            assert ck.rel_rms(got[:size], want[:size]) <= TOL[suf]
