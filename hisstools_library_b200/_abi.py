@@ -51,6 +51,7 @@ SIGNATURES = {
     "hb_conv_shard_attach": (C.c_int, [V, V]),
     "hb_conv_process_shard_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
     "hb_conv_set_tuning": (C.c_int, [V, C.c_int, C.c_int]),
+    "hb_conv_set_host_pipeline": (C.c_int, [V, C.c_int]),
     "hb_conv_bytes_per_hop": (C.c_uint64, [V]),
     "hb_matrix_create": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, U32, U32, U32, U32, C.c_int]),
     "hb_matrix_create_latency": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, C.c_int]),

@@ -113,6 +113,9 @@ class _Engine:
     def set_tuning(self, ctas_per_sm=0, variant=1):
         return _abi.check(_abi.lib().hb_conv_set_tuning(self._h, int(ctas_per_sm), int(variant)))
 
+    def set_host_pipeline(self, pipelined=True):
+        return _abi.check(_abi.lib().hb_conv_set_host_pipeline(self._h, 1 if pipelined else 0))
+
     # fused multi-GPU exchange (hb_conv_shard_*)
     def shard_export(self, world, rank):
         buf = C.create_string_buffer(64)

@@ -1142,6 +1142,18 @@ extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)
     return HB_OK;
 }
 
+extern "C" int hb_conv_set_host_pipeline(hb_conv *c, int pipelined)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if ((rc = drain_deferred(c))) return rc;
+    c->blk_valid = false;
+    c->deferred = pipelined != 0;
+    return HB_OK;
+}
+
 extern "C" int hb_conv_set_profiling(hb_conv *c, int enable)
 {
     int rc = check_handle(c);

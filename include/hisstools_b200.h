@@ -161,6 +161,10 @@ int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, voi
 /* tuning / introspection used by bench.py and the tests */
 /* CTAs per SM for the multiply-accumulate kernel (0 = library default) */
 int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant);
+/* host-pointer calls (hb_conv_process) that stay inside one hop are pipelined by default: the call returns the
+ * samples an earlier hop finished (the API's own latency of fft_size/2, PartitionedConvolve.cpp:307 before
+ * :352-360) and leaves its own device work in flight.  pipelined = 0 makes every call a synchronous round trip. */
+int hb_conv_set_host_pipeline(hb_conv *c, int pipelined);
 /* algorithmic bytes one hop moves (IR spectra + FDL + time-domain I/O) */
 uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
 /* per-kernel device timing: while enabled, every hop records CUDA events around its three kernels on
