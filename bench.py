@@ -66,11 +66,11 @@ def measured_peak():
         return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def committed_traffic(workload, n_gpus):
+def committed_traffic(workload, n_gpus, overlapped):
     """DRAM bytes per launch of the multiply-accumulate kernel from the committed ncu capture, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("%s_n%d" % (workload, n_gpus))
+            return json.load(f).get("%s_n%d%s" % (workload, n_gpus, "_tail" if overlapped else ""))
     except Exception:
         return None
 
@@ -266,6 +266,8 @@ def run_ours(args):
     eng.set_reset_offset(0)
     if args.variant is not None:
         eng.set_tuning(args.ctas_per_sm, args.variant)
+    if args.schedule is not None:
+        eng.set_schedule(args.schedule == "overlapped")
     gen = torch.Generator(device=dev)
     decay = torch.exp(-6.9 * torch.arange(taps, device=dev, dtype=torch.float64) / taps).to(tdt)
     for g in range(l_groups):
@@ -329,14 +331,22 @@ def run_ours(args):
         step(k)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms_fwd, ms_cmac, ms_inv, hops = eng.get_profile()
+    prof, hops = eng.get_profile()
     eng.set_profiling(False)
-    t = torch.tensor([ms, ms_cmac / max(hops, 1), ms_fwd / max(hops, 1), ms_inv / max(hops, 1)], device=dev, dtype=torch.float64)
+    overlapped = eng.schedule == "overlapped"
+    # the dominant launch: the tail multiply-accumulate (partitions 1..P-1, second stream) in the overlapped schedule,
+    # the one multiply-accumulate over all partitions in the serial schedule
+    ms_dom = prof["tail"] if overlapped else prof["cmac"]
+    ms_head = prof["cmac"] if overlapped else 0.0
+    # the inverse-FFT launch sits behind the wait for the tail; the event between the two is not ordered after the
+    # wait, so only their sum is meaningful
+    t = torch.tensor([ms, ms_dom / max(hops, 1), prof["forward"] / max(hops, 1), (prof["wait"] + prof["inverse"]) / max(hops, 1),
+                      ms_head / max(hops, 1)], device=dev, dtype=torch.float64)
     cnt = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, cmac_ms, fwd_ms, inv_ms = [float(v) for v in t.tolist()]
+    ms, cmac_ms, fwd_ms, inv_ms, head_ms = [float(v) for v in t.tolist()]
     launches = int(cnt.item())
 
     # whole-job output samples per step: replicas each produce the full workload
@@ -395,13 +405,17 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (multiply-accumulate), per rank ---------------------------
     peak, peak_src = measured_peak()
-    bytes_per_launch = eng.bytes_per_hop                          # IR spectra + FDL + time-domain I/O of one hop
+    bytes_per_hop = eng.bytes_per_hop                             # IR spectra + FDL + time-domain I/O of one hop
+    bytes_per_launch = eng.bytes_per_launch                       # the dominant launch's share of it
     achieved = bytes_per_launch / (cmac_ms * 1e-3) / 1e9 if cmac_ms > 0 else 0.0
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": committed_traffic(args.workload, world), "kernel": "k_cmac (frequency-domain multiply-accumulate)",
-            "bytes_per_launch": bytes_per_launch, "kernel_ms": cmac_ms, "forward_fft_ms": fwd_ms, "inverse_fft_ms": inv_ms,
+            "traffic": committed_traffic(args.workload, world, overlapped),
+            "kernel": "k_cmac, tail launch: partitions 1..P-1 (frequency-domain multiply-accumulate)" if overlapped
+                      else "k_cmac (frequency-domain multiply-accumulate, all partitions)",
+            "bytes_per_launch": bytes_per_launch, "bytes_per_hop": bytes_per_hop, "kernel_ms": cmac_ms, "forward_fft_ms": fwd_ms,
+            "head_cmac_ms": head_ms, ("wait_for_tail_plus_inverse_fft_ms" if overlapped else "inverse_fft_ms"): inv_ms,
             "kernel_share_of_step": cmac_ms * args.hops / (ms / args.steps), "peak_source": peak_src,
-            "hop_frac": bytes_per_launch / ((ms / args.steps / args.hops) * 1e-3) / 1e9 / peak}
+            "hop_frac": bytes_per_hop / ((ms / args.steps / args.hops) * 1e-3) / 1e9 / peak}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -416,9 +430,9 @@ def run_ours(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if mode == "replicas" else "strong",
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": desc, "hops_per_step": args.hops, "samples_per_step_per_channel": n, "partitions": P,
-                           "sharding": mode, "local_inputs": l_ins, "outputs": outs, "groups": l_groups,
-                           "l2": "inputs larger than L2: %.2f GiB of IR spectra per rank streamed every step" % (bytes_per_launch / 2 ** 30)
-                                 if bytes_per_launch > 256e6 else "working set %.1f MiB is L2-resident (not an HBM-roofline case)" % (bytes_per_launch / 2 ** 20),
+                           "sharding": mode, "local_inputs": l_ins, "outputs": outs, "groups": l_groups, "schedule": eng.schedule,
+                           "l2": "inputs larger than L2: %.2f GiB of IR spectra per rank streamed every step" % (bytes_per_hop / 2 ** 30)
+                                 if bytes_per_hop > 256e6 else "working set %.1f MiB is L2-resident (not an HBM-roofline case)" % (bytes_per_hop / 2 ** 20),
                            "collective": ("peer stores fused into the inverse-FFT epilogue (NVLink), owner-side sum" if sharded is not None and sharded.exchange == "fused"
                                           else "nccl reduce_scatter of partial output blocks") if mode == "inputs" else "none"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -445,6 +459,7 @@ def main():
     ap.add_argument("--hops", type=int, default=1, help="hops (blocks of B samples) per step")
     ap.add_argument("--variant", type=int, default=None, help="multiply-accumulate kernel: 1 = TMA ring, 0 = direct loads")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--schedule", default=None, choices=["overlapped", "serial"], help="hop schedule (default: the library's, overlapped)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"], help="multi-GPU sum of partial outputs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -134,10 +134,23 @@ class _Engine:
         return _abi.check(_abi.lib().hb_conv_set_profiling(self._h, 1 if enable else 0))
 
     def get_profile(self):
-        """(ms forward FFTs, ms multiply-accumulate, ms inverse FFTs, hops) since profiling was enabled."""
-        a, b, c_, h = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
-        _abi.check(_abi.lib().hb_conv_get_profile(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(h)))
-        return a.value, b.value, c_.value, int(h.value)
+        """({forward, cmac, wait, inverse, tail} summed ms, hops) since profiling was enabled; `cmac` is the whole
+        multiply-accumulate in the serial schedule and the head (partition 0) in the overlapped one."""
+        ms, h = (C.c_double * 5)(), C.c_uint64()
+        _abi.check(_abi.lib().hb_conv_get_profile(self._h, ms, C.byref(h)))
+        return dict(zip(("forward", "cmac", "wait", "inverse", "tail"), [float(v) for v in ms])), int(h.value)
+
+    def set_schedule(self, overlapped=True):
+        """True: overlapped (tail of the next hop computed ahead on a second stream), False: serial, None: automatic."""
+        return _abi.check(_abi.lib().hb_conv_set_schedule(self._h, 2 if overlapped is None else (1 if overlapped else 0)))
+
+    @property
+    def schedule(self):
+        return "overlapped" if _abi.lib().hb_conv_schedule(self._h) else "serial"
+
+    @property
+    def bytes_per_launch(self):
+        return int(_abi.lib().hb_conv_bytes_per_launch(self._h))
 
     def process(self, in_rows, out_rows, n, accumulate=False):
         """in_rows / out_rows: lists of contiguous 1-D arrays of the engine dtype (>= n samples)."""

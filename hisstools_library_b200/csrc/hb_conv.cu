@@ -89,6 +89,20 @@ struct hb_conv
     size_t cmac_smem = 0;
     std::mutex lock;
 
+    // schedule of a hop (hb_conv_set_schedule).  Overlapped: partitions 1..P-1 only meet spectra that are
+    // already in the delay line, so their share of hop t+1 ("tail") is computed on a second stream as soon as
+    // the forward FFTs of hop t are done, beside the inverse FFTs of hop t and the forward FFTs of hop t+1; the
+    // critical path of a hop is then forward FFT -> partition 0 ("head") -> inverse FFT.  This is the load
+    // spreading of PartitionedConvolve.cpp:330-347 (partitions done ahead, between hops) in stream form.
+    int schedule = 2;               // requested: 0 serial, 1 overlapped, 2 overlapped where the tail is worth a stream of its own
+    bool split = false;             // in effect for the current geometry (needs P >= 2)
+    Range r_full{}, r_head{}, r_tail{};
+    DevBuf d_St[2];                 // tail partial segments, double-buffered over hops
+    cudaStream_t s_tail = nullptr;
+    cudaEvent_t ev_fwd = nullptr, ev_tail[2] = {nullptr, nullptr};
+    bool tail_valid = false;        // d_St[tail_par] holds the tail of the upcoming hop
+    int tail_par = 0;
+
     // deferred host-pointer path of hb_conv_process: the block finished by a hop is fetched to pinned host
     // memory while the caller is away; a later call only waits on an event that completed long ago
     bool deferred = true;
@@ -110,11 +124,14 @@ struct hb_conv
     bool peers_attached = false;
     uint32_t hop_seq = 0, parity_uses[2] = {0, 0};
 
-    // optional per-kernel timing (hb_conv_set_profiling): 4 events per hop on the launching stream
+    // optional per-kernel timing (hb_conv_set_profiling): PROF_EV events per hop, five on the launching stream
+    // (around the forward FFTs, the whole / head multiply-accumulate, the wait for the tail, the inverse FFTs)
+    // and two on the tail stream around the tail multiply-accumulate
     bool profiling = false;
     std::vector<cudaEvent_t> ev;
-    size_t ev_used = 0;
-    double prof_ms[3] = {0, 0, 0};  // forward FFTs, multiply-accumulate, inverse FFTs
+    std::vector<char> ev_has_tail;
+    size_t ev_used = 0;             // hops recorded and not yet drained
+    double prof_ms[5] = {0, 0, 0, 0, 0};  // forward, whole/head multiply-accumulate, wait for tail, inverse, tail
     uint64_t prof_hops = 0;
 
     size_t esize() const { return dtype_size(dtype); }
@@ -159,16 +176,55 @@ void plan_geometry(hb_conv *c)
     g.upt = g.ins * g.P;
     g.tiles = g.groups * g.n_ot * g.n_bt;
     g.U = uint64_t(g.tiles) * g.upt;
-    uint64_t want = uint64_t(c->sm_count) * (c->variant == 1 ? 1 : std::max(1, c->ctas_per_sm));
+    const uint32_t log2m = g.log2n - 1;
+    const uint64_t sms = (uint64_t) c->sm_count;
     // every tile is summed by ONE inverse-FFT CTA: with few tiles (few outputs, short hops) a wide grid would
-    // hand that CTA hundreds of partial segments, so the grid is narrowed to at most 16 segments per tile
-    want = std::min<uint64_t>(want, uint64_t(g.tiles) * 16);
-    g.G = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(g.U, want));
-    // TMA ring depth: as many stages as fit in ~200 KB, between 2 and 6
+    // hand that CTA hundreds of partial segments, so a grid is narrowed to at most 16 segments per tile
+    auto make_range = [&](uint32_t p0, uint32_t pc, uint64_t want)
+    {
+        Range r{};
+        r.p0 = p0; r.pc = pc;
+        r.upt = g.ins * pc;
+        r.U = uint64_t(g.tiles) * r.upt;
+        want = std::min<uint64_t>(want, uint64_t(g.tiles) * 16);
+        r.G = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(r.U, want));
+        return r;
+    };
+    const uint64_t per_sm = c->variant == 1 ? 1 : std::max(1, c->ctas_per_sm);
+    // automatic choice: below a few MiB of tail spectra a hop is bound by launch latency, and the extra launch and
+    // the two stream hand-overs of the overlapped schedule cost more than they hide (measured: DESIGN.md 4)
+    const uint64_t tail_bytes = uint64_t(c->pairs() + uint64_t(g.groups) * g.ins) * (g.P ? g.P - 1 : 0) * g.B * 2 * c->esize();
+    c->split = g.P >= 2 && (c->schedule == 1 || (c->schedule == 2 && tail_bytes >= (uint64_t(4) << 20)));
+    // TMA ring depth: about 96 KB in flight per SM, 3 to 6 stages.  Measured on B200 at config 4 (32.5 KB stages,
+    // profiles/r1_ring_depth.txt): 3 stages stream 7.2 TB/s, 2 stages 6.6, 5-6 stages 6.5 -- twice Little's law for
+    // the chip (7.3 TB/s x ~1 us / 148 SMs = 49 KB) is enough, and a deeper ring only lowers the DRAM efficiency.
     const size_t stage = size_t(g.Q + g.TBV) * 16;
-    int st = (int) std::min<size_t>(6, (200 * 1024) / stage);
+    int st = (int) std::max<size_t>(3, std::min<size_t>(6, (96 * 1024 + stage / 2) / stage));
+    uint64_t reserve = 0;
+    if (c->split)
+    {
+        // The tail launch runs beside the FFT kernels of the critical path.  Where an FFT CTA fits on an SM next
+        // to a multiply-accumulate CTA and its ring (shared memory; registers: 512 x 64 + 256 x 112 for transforms
+        // up to 4096 points; tools/coreside_probe.cu confirms the placement) nothing changes; otherwise the tail
+        // grid leaves as many SMs free as the FFT kernels have CTAs (stream-K: any grid size balances).
+        const size_t es = c->esize();
+        const size_t fft_data = size_t(padded_elems<HB_PADSH>(1u << log2m)) * 2 * es;
+        const size_t fft_tw = (size_t(1) << log2m) * 2 * es;
+        const size_t fft_total = fft_data + (fft_data + fft_tw <= 200 * 1024 ? fft_tw : 0) + 3 * 1024;   // static + driver reserve
+        const size_t budget = 227 * 1024 > fft_total + 2048 ? 227 * 1024 - fft_total - 2048 : 0;
+        const int st_co = (int) (budget / stage);
+        const uint64_t fft_ctas = uint64_t(g.groups) * std::max(g.ins, g.outs);
+        if (c->variant == 1 && !(log2m <= 12 && st_co >= st)) reserve = std::min<uint64_t>(fft_ctas, sms / 4);
+    }
+    static const char *env_st = getenv("HB_STAGES"), *env_rs = getenv("HB_RESERVE");          // experiments only
+    if (env_st && atoi(env_st) >= 2) st = std::min<int>(atoi(env_st), (int) ((220 * 1024) / stage));
+    if (env_rs && c->split) reserve = std::min<uint64_t>((uint64_t) atoi(env_rs), sms - 1);
     c->nstages = std::max(2, st);
     c->cmac_smem = size_t(c->nstages) * stage + size_t(c->nstages) * 8;
+    c->r_full = make_range(0, g.P, sms * per_sm);
+    c->r_head = make_range(0, g.P ? 1 : 0, sms);
+    c->r_tail = make_range(1, g.P ? g.P - 1 : 0, (sms - reserve) * per_sm);
+    g.G = c->r_full.G;
 }
 
 size_t h_vectors(const hb_conv *c)
@@ -185,6 +241,12 @@ void free_device(hb_conv *c)
     cudaFree(c->d_H); cudaFree(c->d_X); cudaFree(c->d_Hnyq); cudaFree(c->d_Xnyq); cudaFree(c->d_tw);
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = c->d_tw = nullptr;
     c->d_S.release();
+    c->d_St[0].release(); c->d_St[1].release();
+    if (c->s_tail) cudaStreamDestroy(c->s_tail);
+    if (c->ev_fwd) cudaEventDestroy(c->ev_fwd);
+    for (int k = 0; k < 2; k++) if (c->ev_tail[k]) cudaEventDestroy(c->ev_tail[k]);
+    c->s_tail = nullptr; c->ev_fwd = nullptr; c->ev_tail[0] = c->ev_tail[1] = nullptr;
+    c->tail_valid = false;
     for (int k = 0; k < 2; k++) { c->d_xin[k].release(); c->d_yout[k].release(); }
     c->d_io_in.release(); c->d_io_out.release(); c->d_ir.release();
     c->h_in.release(); c->h_out.release(); c->h_ir.release();
@@ -234,19 +296,26 @@ int alloc_capacity(hb_conv *c)
     return ERR_NONE;
 }
 
-// opt in to > 48 KB of dynamic shared memory once per (kernel, device, size)
+// opt in to > 48 KB of dynamic shared memory once per (kernel, device, size).  Every kernel of a hop also asks
+// for the largest shared-memory carveout: in the overlapped schedule FFT CTAs are placed beside a resident
+// multiply-accumulate CTA, and an SM keeps the carveout of the kernel that occupied it first -- sized for that
+// kernel alone it would leave no room for the second one.
 template <class K> int allow_smem(K kernel, size_t bytes)
 {
-    if (bytes <= 48 * 1024) return HB_OK;
     static std::mutex m;
     static std::map<std::pair<const void *, int>, size_t> done;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> g(m);
-    size_t &have = done[std::make_pair((const void *) kernel, dev)];
-    if (have >= bytes) return HB_OK;
+    auto it = done.find(std::make_pair((const void *) kernel, dev));
+    if (it == done.end())
+    {
+        HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared));
+        it = done.insert(std::make_pair(std::make_pair((const void *) kernel, dev), size_t(48 * 1024))).first;
+    }
+    if (it->second >= bytes) return HB_OK;
     HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
-    have = bytes;
+    it->second = bytes;
     return HB_OK;
 }
 
@@ -257,38 +326,44 @@ template <class T> int tw_fits(uint32_t log2m) { return fft_smem<T>(log2m) + tw_
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
 template <class T, int XA, int OB>
-int launch_cmac_inst(hb_conv *c, cudaStream_t st)
+int launch_cmac_inst(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t st)
 {
     typedef typename VecOf<T>::type V;
     const Geom &g = c->g;
-    if (c->variant == 1)
+    if (variant == 1)
     {
         int rc = allow_smem(k_cmac_tma<T, XA, OB>, c->cmac_smem);
         if (rc) return rc;
-        k_cmac_tma<T, XA, OB><<<g.G, 256, c->cmac_smem, st>>>(g, (const V *) c->d_H, (const V *) c->d_X, (V *) c->d_S.p, c->nstages);
+        k_cmac_tma<T, XA, OB><<<r.G, 256, c->cmac_smem, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, c->nstages);
     }
     else
-        k_cmac_ldg<T, XA, OB><<<g.G, 256, 0, st>>>(g, (const V *) c->d_H, (const V *) c->d_X, (V *) c->d_S.p);
+    {
+        int rc = allow_smem(k_cmac_ldg<T, XA, OB>, 0);
+        if (rc) return rc;
+        k_cmac_ldg<T, XA, OB><<<r.G, 256, 0, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S);
+    }
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
 
+// one multiply-accumulate launch over the partitions of `r` into the partial segments S
 template <class T>
-int launch_cmac(hb_conv *c, cudaStream_t st)
+int launch_cmac(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t st)
 {
+    if (!r.U) return HB_OK;
     const uint32_t key = c->g.XA * 16 + c->g.OB;
     switch (key)
     {
-        case 1 * 16 + 1: return launch_cmac_inst<T, 1, 1>(c, st);
-        case 1 * 16 + 2: return launch_cmac_inst<T, 1, 2>(c, st);
-        case 1 * 16 + 4: return launch_cmac_inst<T, 1, 4>(c, st);
-        case 1 * 16 + 8: return launch_cmac_inst<T, 1, 8>(c, st);
-        case 2 * 16 + 1: return launch_cmac_inst<T, 2, 1>(c, st);
-        case 2 * 16 + 2: return launch_cmac_inst<T, 2, 2>(c, st);
-        case 2 * 16 + 4: return launch_cmac_inst<T, 2, 4>(c, st);
-        case 4 * 16 + 1: return launch_cmac_inst<T, 4, 1>(c, st);
-        case 4 * 16 + 2: return launch_cmac_inst<T, 4, 2>(c, st);
-        case 8 * 16 + 1: return launch_cmac_inst<T, 8, 1>(c, st);
+        case 1 * 16 + 1: return launch_cmac_inst<T, 1, 1>(c, r, S, variant, st);
+        case 1 * 16 + 2: return launch_cmac_inst<T, 1, 2>(c, r, S, variant, st);
+        case 1 * 16 + 4: return launch_cmac_inst<T, 1, 4>(c, r, S, variant, st);
+        case 1 * 16 + 8: return launch_cmac_inst<T, 1, 8>(c, r, S, variant, st);
+        case 2 * 16 + 1: return launch_cmac_inst<T, 2, 1>(c, r, S, variant, st);
+        case 2 * 16 + 2: return launch_cmac_inst<T, 2, 2>(c, r, S, variant, st);
+        case 2 * 16 + 4: return launch_cmac_inst<T, 2, 4>(c, r, S, variant, st);
+        case 4 * 16 + 1: return launch_cmac_inst<T, 4, 1>(c, r, S, variant, st);
+        case 4 * 16 + 2: return launch_cmac_inst<T, 4, 2>(c, r, S, variant, st);
+        case 8 * 16 + 1: return launch_cmac_inst<T, 8, 1>(c, r, S, variant, st);
     }
     set_error("internal: no multiply-accumulate kernel for XA=%u OB=%u", c->g.XA, c->g.OB);
     return HB_ERR_UNSUPPORTED;
@@ -323,16 +398,15 @@ template <class T> struct InvIO
 };
 
 template <class T, int EPT>
-int launch_inv_ept(hb_conv *c, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer)
+int launch_inv_ept(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer)
 {
-    typedef typename VecOf<T>::type V;
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
     const int stage_tw = tw_fits<T>(log2m);
     const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) : 0);
     int rc = allow_smem(k_inv<T, EPT>, smem);
     if (rc) return rc;
-    k_inv<T, EPT><<<g.groups * g.outs, fft_threads(log2m, EPT), smem, st>>>(g, (const V *) c->d_S.p, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off,
+    k_inv<T, EPT><<<g.groups * g.outs, fft_threads(log2m, EPT), smem, st>>>(g, sets, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off,
                                                                          io.add_result, io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry,
                                                                          (const Cx<T> *) c->d_tw, c->tw_log2, stage_tw, peer);
     HB_LAUNCH_CHECK();
@@ -340,9 +414,9 @@ int launch_inv_ept(hb_conv *c, const InvIO<T> &io, cudaStream_t st, const PeerOu
 }
 
 template <class T>
-int launch_inv(hb_conv *c, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer = PeerOut())
+int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer = PeerOut())
 {
-    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, io, st, peer));
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer));
 }
 
 template <class T, int EPT>
@@ -452,10 +526,22 @@ int ensure_staging(hb_conv *c, size_t need_x, size_t need_y, bool preserve, cuda
 template <class T>
 int do_reset(hb_conv *c, cudaStream_t st)
 {
+    // a tail launched ahead for a hop that will not come any more may still be running on its stream
+    if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));
+    c->tail_valid = false;
     plan_geometry(c);
     const Geom &g = c->g;
-    int rc = c->d_S.ensure(std::max<size_t>((size_t(g.G) + g.tiles) * g.Q * 16, 16));
+    int rc = c->d_S.ensure(std::max<size_t>((size_t(std::max(c->r_full.G, c->r_head.G)) + g.tiles) * g.Q * 16, 16));
     if (rc) return rc;
+    if (c->split)
+    {
+        for (int k = 0; k < 2; k++)
+            if ((rc = c->d_St[k].ensure(std::max<size_t>((size_t(c->r_tail.G) + g.tiles) * g.Q * 16, 16)))) return rc;
+        if (!c->s_tail) HB_CUDA(cudaStreamCreateWithFlags(&c->s_tail, cudaStreamNonBlocking));
+        if (!c->ev_fwd) HB_CUDA(cudaEventCreateWithFlags(&c->ev_fwd, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++)
+            if (!c->ev_tail[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[k], cudaEventDisableTiming));
+    }
     // FDL silence: stale slots are masked in the reference by mValidPartitions (:285,373); zeros do the same
     HB_CUDA(cudaMemsetAsync(c->d_X, 0, size_t(g.groups) * g.ins * g.P * g.B * 2 * sizeof(T), st));
     HB_CUDA(cudaMemsetAsync(c->d_Xnyq, 0, size_t(g.groups) * g.ins * g.P * sizeof(T), st));
@@ -481,18 +567,27 @@ int ensure_ready(hb_conv *c, size_t n, cudaStream_t st)
     return do_reset<T>(c, st);
 }
 
-// fold the recorded event intervals into prof_ms (synchronises on the last recorded event)
+// fold the recorded event intervals into prof_ms (synchronises on the last recorded events)
+constexpr size_t PROF_EV = 7;      // per hop: 5 marks on the launching stream, 2 on the tail stream
 int drain_profile(hb_conv *c)
 {
     if (!c->ev_used) return HB_OK;
-    HB_CUDA(cudaEventSynchronize(c->ev[c->ev_used - 1]));
-    for (size_t k = 0; k + 3 < c->ev_used; k += 4)
+    HB_CUDA(cudaEventSynchronize(c->ev[(c->ev_used - 1) * PROF_EV + 4]));
+    if (c->ev_has_tail[c->ev_used - 1]) HB_CUDA(cudaEventSynchronize(c->ev[(c->ev_used - 1) * PROF_EV + 6]));
+    for (size_t h = 0; h < c->ev_used; h++)
     {
-        for (int j = 0; j < 3; j++)
+        const cudaEvent_t *e = &c->ev[h * PROF_EV];
+        for (int j = 0; j < 4; j++)
         {
             float ms = 0.f;
-            HB_CUDA(cudaEventElapsedTime(&ms, c->ev[k + j], c->ev[k + j + 1]));
+            HB_CUDA(cudaEventElapsedTime(&ms, e[j], e[j + 1]));
             c->prof_ms[j] += ms;
+        }
+        if (c->ev_has_tail[h])
+        {
+            float ms = 0.f;
+            HB_CUDA(cudaEventElapsedTime(&ms, e[5], e[6]));
+            c->prof_ms[4] += ms;
         }
         c->prof_hops++;
     }
@@ -500,20 +595,88 @@ int drain_profile(hb_conv *c)
     return HB_OK;
 }
 
-int profile_mark(hb_conv *c, cudaStream_t st)
+// events of the hop being recorded (allocates the next block of PROF_EV events)
+int profile_begin_hop(hb_conv *c, cudaEvent_t **out)
 {
-    if (c->ev_used == c->ev.size())
+    if (c->ev_used * PROF_EV == c->ev.size())
     {
-        if (c->ev.size() >= 4 * 256) { int rc = drain_profile(c); if (rc) return rc; }
+        if (c->ev_used >= 256) { int rc = drain_profile(c); if (rc) return rc; }
         else
-            for (int k = 0; k < 4; k++)
+        {
+            for (size_t k = 0; k < PROF_EV; k++)
             {
                 cudaEvent_t e;
                 HB_CUDA(cudaEventCreate(&e));
                 c->ev.push_back(e);
             }
+            c->ev_has_tail.push_back(0);
+        }
     }
-    HB_CUDA(cudaEventRecord(c->ev[c->ev_used++], st));
+    c->ev_has_tail[c->ev_used] = 0;
+    *out = &c->ev[c->ev_used * PROF_EV];
+    c->ev_used++;
+    return HB_OK;
+}
+
+// One hop: forward FFTs of the newest frame, multiply-accumulate, inverse FFTs (PartitionedConvolve.cpp:352-377).
+// Serial schedule: the three kernels in a row on st.  Overlapped schedule: see hb_conv::schedule.
+template <class T>
+int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld,
+               const InvIO<T> &io, const PeerOut &peer)
+{
+    int r;
+    cudaEvent_t *pe = nullptr;
+    if (c->profiling && (r = profile_begin_hop(c, &pe))) return r;
+    // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
+    c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+    if (pe) HB_CUDA(cudaEventRecord(pe[0], st));
+    if ((r = launch_fwd<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st))) return r;
+    if (pe) HB_CUDA(cudaEventRecord(pe[1], st));
+    SegSets sets;
+    memset(&sets, 0, sizeof(sets));
+    if (!c->split)
+    {
+        Range rf = c->r_full;
+        rf.slot = c->g.slot;
+        if ((r = launch_cmac<T>(c, rf, c->d_S.p, c->variant, st))) return r;
+        if (pe) { HB_CUDA(cudaEventRecord(pe[2], st)); HB_CUDA(cudaEventRecord(pe[3], st)); }
+        sets.n = 1;
+        sets.s[0].S = c->d_S.p; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
+    }
+    else
+    {
+        // fork: the tail of the NEXT hop needs nothing newer than the spectrum just written.  Its frame will go to
+        // slot - 1, so partition p meets slot - 1 + p: this hop's spectrum at p = 1, the oldest one kept at p = P - 1.
+        HB_CUDA(cudaEventRecord(c->ev_fwd, st));
+        const int np = c->tail_par ^ 1;
+        Range rt = c->r_tail;
+        rt.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+        HB_CUDA(cudaStreamWaitEvent(c->s_tail, c->ev_fwd, 0));
+        if (pe) { HB_CUDA(cudaEventRecord(pe[5], c->s_tail)); c->ev_has_tail[c->ev_used - 1] = 1; }
+        if ((r = launch_cmac<T>(c, rt, c->d_St[np].p, c->variant, c->s_tail))) return r;
+        if (pe) HB_CUDA(cudaEventRecord(pe[6], c->s_tail));
+        HB_CUDA(cudaEventRecord(c->ev_tail[np], c->s_tail));
+        // critical path: partition 0 against the newest spectrum (direct loads: no shared memory, so its CTAs fit
+        // beside the tail's on every SM)
+        Range rh = c->r_head;
+        rh.slot = c->g.slot;
+        if ((r = launch_cmac<T>(c, rh, c->d_S.p, 0, st))) return r;
+        if (pe) HB_CUDA(cudaEventRecord(pe[2], st));
+        sets.n = 1;
+        sets.s[0].S = c->d_S.p; sets.s[0].U = rh.U; sets.s[0].upt = rh.upt; sets.s[0].G = rh.G;
+        // join: the tail of THIS hop was launched during the previous one
+        if (c->tail_valid)
+        {
+            HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
+            sets.n = 2;
+            sets.s[1].S = c->d_St[c->tail_par].p; sets.s[1].U = c->r_tail.U; sets.s[1].upt = c->r_tail.upt; sets.s[1].G = c->r_tail.G;
+        }
+        if (pe) HB_CUDA(cudaEventRecord(pe[3], st));
+        c->tail_par = np;
+        c->tail_valid = true;
+    }
+    if ((r = launch_inv<T>(c, sets, io, st, peer))) return r;
+    if (pe) HB_CUDA(cudaEventRecord(pe[4], st));
     return HB_OK;
 }
 
@@ -529,21 +692,9 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
     const size_t rows_in = size_t(c->groups) * c->ins, rows_out = size_t(c->groups) * c->outs;
     const size_t rw = c->rw;
     const size_t nh = (rw + n) / B;
-    const bool prof = c->profiling;
-
     auto hop = [&](const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, const InvIO<T> &io) -> int
     {
-        int r;
-        // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
-        c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
-        if (prof && (r = profile_mark(c, st))) return r;
-        if ((r = launch_fwd<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st))) return r;
-        if (prof && (r = profile_mark(c, st))) return r;
-        if ((r = launch_cmac<T>(c, st))) return r;
-        if (prof && (r = profile_mark(c, st))) return r;
-        if ((r = launch_inv<T>(c, io, st))) return r;
-        if (prof && (r = profile_mark(c, st))) return r;
-        return HB_OK;
+        return launch_hop<T>(c, st, prev, prev_ld, newest, new_ld, save, save_ld, io, PeerOut());
     };
 
     // caller rows that overlap (in-place processing) must go through the staging copies
@@ -632,37 +783,27 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
     const int cur = c->cur, nxt = cur ^ 1;
     const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
     const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
-    const bool prof = c->profiling;
     for (size_t h = 0; h < nh; h++)
     {
         const bool first = h == 0, last = h + 1 == nh;
         PeerOut peer;
-        const size_t es = sizeof(T);
         for (uint32_t r = 0; r < world; r++)
         {
             peer.data[r] = c->peer_base[r];
             peer.count[r] = (uint32_t *) ((char *) c->peer_base[r] + c->inbox_data_bytes);
         }
-        (void) es;
         peer.world = world; peer.rank = c->shard_rank; peer.outs_local = o_loc;
         peer.parity = (++c->hop_seq) & 1u;
         peer.slot = c->inbox_slot;
         const uint32_t expected = (++c->parity_uses[peer.parity]) * o_loc;
-        c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
-        if (prof && (rc = profile_mark(c, st))) return rc;
-        if ((rc = launch_fwd<T>(c, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
-                                last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st))) return rc;
-        if (prof && (rc = profile_mark(c, st))) return rc;
-        if ((rc = launch_cmac<T>(c, st))) return rc;
-        if (prof && (rc = profile_mark(c, st))) return rc;
         InvIO<T> io = {nullptr, 0, 0, 0, nullptr, 0, nullptr, 0, 0};
-        if ((rc = launch_inv<T>(c, io, st, peer))) return rc;
+        if ((rc = launch_hop<T>(c, st, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, io, peer))) return rc;
         k_gather<T><<<o_loc, 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
                                           peer.parity, peer.slot, expected, (uint32_t) B,
                                           last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
                                           first ? y_keep : nullptr, c->yout_ld, first ? d_out : nullptr, out_ld, accumulate);
         HB_LAUNCH_CHECK();
-        if (prof && (rc = profile_mark(c, st))) return rc;
     }
     c->cur = nxt;
     c->x_tail = c->y_tail = 0;
@@ -860,6 +1001,7 @@ extern "C" int hb_conv_resize(hb_conv *c, uintptr_t max_length)
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));       // a tail launched ahead reads the spectra freed below
     const uintptr_t maxB = (uintptr_t(1) << c->max_fft_log2) >> 1;
     uintptr_t ml = max_length ? max_length : maxB;
     if (ml % maxB) ml = (ml / maxB + 1) * maxB;
@@ -1142,6 +1284,16 @@ extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)
     return HB_OK;
 }
 
+extern "C" int hb_conv_set_schedule(hb_conv *c, int overlapped)
+{
+    if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    if (overlapped < 0 || overlapped > 2) { set_error("schedule must be 0 (serial), 1 (overlapped) or 2 (automatic)"); return HB_ERR_BAD_ARG; }
+    c->schedule = overlapped;
+    c->need_reset = true;           // the partial-segment sets depend on the schedule
+    return HB_OK;
+}
+
 extern "C" int hb_conv_set_host_pipeline(hb_conv *c, int pipelined)
 {
     int rc = check_handle(c);
@@ -1161,22 +1313,33 @@ extern "C" int hb_conv_set_profiling(hb_conv *c, int enable)
     std::lock_guard<std::mutex> g(c->lock);
     if ((rc = drain_profile(c))) return rc;
     c->profiling = enable != 0;
-    c->prof_ms[0] = c->prof_ms[1] = c->prof_ms[2] = 0;
+    for (int k = 0; k < 5; k++) c->prof_ms[k] = 0;
     c->prof_hops = 0;
     return HB_OK;
 }
 
-extern "C" int hb_conv_get_profile(hb_conv *c, double *ms_forward, double *ms_cmac, double *ms_inverse, uint64_t *hops)
+extern "C" int hb_conv_get_profile(hb_conv *c, double *ms, uint64_t *hops)
 {
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
     if ((rc = drain_profile(c))) return rc;
-    if (ms_forward) *ms_forward = c->prof_ms[0];
-    if (ms_cmac) *ms_cmac = c->prof_ms[1];
-    if (ms_inverse) *ms_inverse = c->prof_ms[2];
+    if (ms) for (int k = 0; k < 5; k++) ms[k] = c->prof_ms[k];
     if (hops) *hops = c->prof_hops;
     return HB_OK;
+}
+
+extern "C" int hb_conv_schedule(const hb_conv *c) { return c && c->split ? 1 : 0; }
+
+extern "C" uint64_t hb_conv_bytes_per_launch(const hb_conv *c)
+{
+    if (!c || !c->P) return 0;
+    // the dominant multiply-accumulate launch: the whole hop in the serial schedule (hb_conv_bytes_per_hop), in the
+    // overlapped one the tail's IR partitions 1..P-1 and the P-1 spectra of every input they meet
+    if (!c->split) return hb_conv_bytes_per_hop(c);
+    const uint64_t s = c->esize(), B = (uint64_t(1) << c->fft_log2) >> 1, P = c->P;
+    const uint64_t I = uint64_t(c->groups) * c->ins, K = c->pairs();
+    return 2 * s * B * (P - 1) * (K + I);
 }
 
 extern "C" uint64_t hb_conv_bytes_per_hop(const hb_conv *c)

@@ -52,6 +52,20 @@ struct Geom
     uint64_t U;            // units in total = tiles*upt
 };
 
+// One launch of the multiply-accumulate kernel covers the partitions [p0, p0 + pc) of every (tile, input):
+// the whole IR (p0 = 0, pc = P) in the serial schedule; in the overlapped schedule the newest spectrum
+// against partition 0 ("head", on the critical path of a hop) and partitions 1..P-1 against the spectra that
+// are already in the delay line ("tail", computed one hop ahead, beside the FFT kernels).
+struct Range
+{
+    uint32_t p0, pc;       // first partition, partition count
+    uint32_t upt;          // units per tile = ins*pc
+    uint32_t G;            // CTAs of this launch
+    uint32_t slot;         // FDL slot of the spectrum that meets partition 0
+    uint32_t pad;
+    uint64_t U;            // units of this launch = tiles*upt
+};
+
 // ---------------------------------------------------------------------------------------------
 // vector complex multiply-accumulate
 // ---------------------------------------------------------------------------------------------
@@ -141,18 +155,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 struct Cursor
 {
     uint32_t tile, in, p;
-    __device__ __forceinline__ void seek(const Geom &g, uint64_t u)
+    __device__ __forceinline__ void seek(const Range &r, uint64_t u)
     {
-        tile = (uint32_t) (u / g.upt);
-        uint32_t rem = (uint32_t) (u - uint64_t(tile) * g.upt);
-        in = rem / g.P;
-        p = rem - in * g.P;
+        tile = (uint32_t) (u / r.upt);
+        uint32_t rem = (uint32_t) (u - uint64_t(tile) * r.upt);
+        in = rem / r.pc;
+        p = r.p0 + (rem - in * r.pc);
     }
     // returns true when the step that was just left was the last unit of its tile
-    __device__ __forceinline__ bool advance(const Geom &g)
+    __device__ __forceinline__ bool advance(const Geom &g, const Range &r)
     {
-        if (++p < g.P) return false;
-        p = 0;
+        if (++p < r.p0 + r.pc) return false;
+        p = r.p0;
         if (++in < g.ins) return false;
         in = 0;
         tile++;
@@ -164,11 +178,11 @@ struct Cursor
         return ((uint64_t(tile) * g.ins + in) * g.Pcap + p) * g.Q;
     }
     // vector offset of the matching FDL tile
-    __device__ __forceinline__ uint64_t x_off(const Geom &g) const
+    __device__ __forceinline__ uint64_t x_off(const Geom &g, const Range &r) const
     {
         uint32_t bt = tile % g.n_bt;
         uint32_t grp = tile / (g.n_bt * g.n_ot);
-        uint32_t s = g.slot + p;
+        uint32_t s = r.slot + p;
         if (s >= g.P) s -= g.P;
         return (((uint64_t(grp) * g.ins + in) * g.n_bt + bt) * g.P + s) * g.TBV;
     }
@@ -180,7 +194,7 @@ struct Cursor
 // dynamic shared memory: nstages * (Q + TBV) vectors, then nstages mbarriers.
 // ---------------------------------------------------------------------------------------------
 template <class T, int XA, int OB>
-__global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const typename VecOf<T>::type *__restrict__ H,
+__global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
                                                      const typename VecOf<T>::type *__restrict__ X,
                                                      typename VecOf<T>::type *__restrict__ S, const int nstages)
 {
@@ -194,7 +208,7 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const typenam
     const uint32_t tx = tid % g.TX, ty = tid / g.TX;
     const bool active = ty < g.TY;
 
-    const uint64_t u0 = unit_begin(blockIdx.x, g.U, g.G), u1 = unit_begin(blockIdx.x + 1, g.U, g.G);
+    const uint64_t u0 = unit_begin(blockIdx.x, rg.U, rg.G), u1 = unit_begin(blockIdx.x + 1, rg.U, rg.G);
     const uint32_t n = (uint32_t) (u1 - u0);
 
     if (tid == 0)
@@ -212,19 +226,19 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const typenam
     {
         pol_h = l2_policy_evict_first();
         pol_x = l2_policy_evict_last();
-        prod.seek(g, u0);
+        prod.seek(rg, u0);
         for (; issued < n && issued + 1 < (uint32_t) nstages; issued++)
         {
             V *dst = ring + size_t(issued) * stage_vecs;
             mbar_expect_tx(&full[issued], h_bytes + x_bytes);
             bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[issued], pol_h);
-            bulk_g2s(dst + g.Q, X + prod.x_off(g), x_bytes, &full[issued], pol_x);
-            prod.advance(g);
+            bulk_g2s(dst + g.Q, X + prod.x_off(g, rg), x_bytes, &full[issued], pol_x);
+            prod.advance(g, rg);
         }
     }
 
     Cursor cons;
-    cons.seek(g, u0);
+    cons.seek(rg, u0);
     V acc[XA * OB];
 #pragma unroll
     for (int r = 0; r < XA * OB; r++) vzero(acc[r]);
@@ -239,8 +253,8 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const typenam
             V *dst = ring + size_t(ps) * stage_vecs;
             mbar_expect_tx(&full[ps], h_bytes + x_bytes);
             bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[ps], pol_h);
-            bulk_g2s(dst + g.Q, X + prod.x_off(g), x_bytes, &full[ps], pol_x);
-            prod.advance(g);
+            bulk_g2s(dst + g.Q, X + prod.x_off(g, rg), x_bytes, &full[ps], pol_x);
+            prod.advance(g, rg);
             issued++;
         }
         mbar_wait(&full[stage], parity);
@@ -257,7 +271,7 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const typenam
                 for (int a = 0; a < XA; a++) cmac(acc[b * XA + a], xv[a], hs[(ty + g.TY * b) * g.TBV + tx + g.TX * a]);
         }
         const uint32_t tile_done = cons.tile;
-        const bool last = cons.advance(g) || (k + 1 == n);
+        const bool last = cons.advance(g, rg) || (k + 1 == n);
         if (last && active)
         {
             V *seg = S + (uint64_t(blockIdx.x) + tile_done) * g.Q;
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const typenam
 // memory (read-once, L1 bypass).  Kept as the comparison point for the TMA ring (profiles/).
 // ---------------------------------------------------------------------------------------------
 template <class T, int XA, int OB>
-__global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const typename VecOf<T>::type *__restrict__ H,
+__global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
                                                   const typename VecOf<T>::type *__restrict__ X,
                                                   typename VecOf<T>::type *__restrict__ S)
 {
@@ -289,9 +303,9 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const typename V
     const uint32_t tx = tid % g.TX, ty = tid / g.TX;
     if (ty >= g.TY) return;
 
-    const uint64_t u0 = unit_begin(blockIdx.x, g.U, g.G), u1 = unit_begin(blockIdx.x + 1, g.U, g.G);
+    const uint64_t u0 = unit_begin(blockIdx.x, rg.U, rg.G), u1 = unit_begin(blockIdx.x + 1, rg.U, rg.G);
     Cursor cur;
-    cur.seek(g, u0);
+    cur.seek(rg, u0);
     V acc[XA * OB];
 #pragma unroll
     for (int r = 0; r < XA * OB; r++) vzero(acc[r]);
@@ -301,11 +315,11 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const typename V
     while (u < u1)
     {
         // a run = consecutive partitions of one (tile, in): the IR pointer just advances by Q per step
-        uint32_t run = g.P - cur.p;
+        uint32_t run = rg.p0 + rg.pc - cur.p;
         if (uint64_t(run) > u1 - u) run = (uint32_t) (u1 - u);
         const V *hp = H + cur.h_off(g) + lane_off;
-        const V *xbase = X + cur.x_off(g) + tx;          // slot (g.slot + p) of this (group, in, bin-tile)
-        uint32_t s = g.slot + cur.p;
+        const V *xbase = X + cur.x_off(g, rg) + tx;      // slot (rg.slot + p) of this (group, in, bin-tile)
+        uint32_t s = rg.slot + cur.p;
         if (s >= g.P) s -= g.P;
         const V *xp = xbase;
         const V *xwrap = xbase - uint64_t(s) * g.TBV;    // slot 0
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const typename V
         const uint32_t tile_done = cur.tile;
         bool last = false;
         cur.p += run - 1;
-        last = cur.advance(g) || (u == u1);
+        last = cur.advance(g, rg) || (u == u1);
         if (last)
         {
             V *seg = S + (uint64_t(blockIdx.x) + tile_done) * g.Q + lane_off;
@@ -500,8 +514,21 @@ struct PeerOut
     uint64_t slot;                     // elements per inbox block (hop capacity)
 };
 
+// partial segments k_inv sums: one set per multiply-accumulate launch that contributed to this hop
+struct SegSet
+{
+    const void *S;         // [cta + tile][row][TBV] of that launch
+    uint64_t U;            // its unit count, units per tile and grid (Range)
+    uint32_t upt, G;
+};
+struct SegSets
+{
+    SegSet s[2];
+    int n;
+};
+
 template <class T, int EPT>
-__global__ void __launch_bounds__(512) k_inv(const Geom g, const typename VecOf<T>::type *__restrict__ S,
+__global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
                                               const T *__restrict__ Xnyq, const T *__restrict__ Hnyq,
                                               T *__restrict__ yout, size_t ld, size_t off, int add_result,
                                               const T *__restrict__ carry_src, size_t carry_src_ld,
@@ -567,43 +594,51 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const typename VecOf<
     for (int e0 = 0; e0 < VPT; e0 += GV)
     {
         V sum[GV];
-        uint32_t seg_lo[GV], seg_hi[GV];
-        uint64_t base[GV];
-        uint32_t rounds = 0;
 #pragma unroll
-        for (int e = 0; e < GV; e++)
+        for (int e = 0; e < GV; e++) vzero(sum[e]);
+#pragma unroll 1
+        for (int q = 0; q < sets.n; q++)
         {
-            const uint32_t v = tid + (e0 + e) * nthr;
-            vzero(sum[e]);
-            seg_lo[e] = 1; seg_hi[e] = 0; base[e] = 0;
-            if (v < B / CPV)
+            const V *__restrict__ S = reinterpret_cast<const V *>(sets.s[q].S);
+            const uint64_t sU = sets.s[q].U;
+            const uint32_t sG = sets.s[q].G, supt = sets.s[q].upt;
+            uint32_t seg_lo[GV], seg_hi[GV];
+            uint64_t base[GV];
+            uint32_t rounds = 0;
+#pragma unroll
+            for (int e = 0; e < GV; e++)
             {
-                const uint32_t bt = v / g.TBV, xa = v - bt * g.TBV;
-                const uint32_t tile = (grp * g.n_ot + ot) * g.n_bt + bt;
-                const uint64_t ulo = uint64_t(tile) * g.upt, uhi = ulo + g.upt - 1;
-                seg_lo[e] = (uint32_t) unit_owner(ulo, g.U, g.G);
-                seg_hi[e] = (uint32_t) unit_owner(uhi, g.U, g.G);
-                base[e] = uint64_t(tile) * g.Q + row * g.TBV + xa;
-                const uint32_t need = seg_hi[e] - seg_lo[e] + 1;
-                rounds = need > rounds ? need : rounds;
-            }
-        }
-        for (uint32_t r = 0; r < rounds; r += 4)
-        {
-            V part[GV][4];
-#pragma unroll
-            for (int e = 0; e < GV; e++)
-#pragma unroll
-                for (int q = 0; q < 4; q++)
+                const uint32_t v = tid + (e0 + e) * nthr;
+                seg_lo[e] = 1; seg_hi[e] = 0; base[e] = 0;
+                if (v < B / CPV)
                 {
-                    const uint32_t c = seg_lo[e] + r + q;
-                    if (c <= seg_hi[e]) part[e][q] = S[uint64_t(c) * g.Q + base[e]];
-                    else vzero(part[e][q]);
+                    const uint32_t bt = v / g.TBV, xa = v - bt * g.TBV;
+                    const uint32_t tile = (grp * g.n_ot + ot) * g.n_bt + bt;
+                    const uint64_t ulo = uint64_t(tile) * supt, uhi = ulo + supt - 1;
+                    seg_lo[e] = (uint32_t) unit_owner(ulo, sU, sG);
+                    seg_hi[e] = (uint32_t) unit_owner(uhi, sU, sG);
+                    base[e] = uint64_t(tile) * g.Q + row * g.TBV + xa;
+                    const uint32_t need = seg_hi[e] - seg_lo[e] + 1;
+                    rounds = need > rounds ? need : rounds;
                 }
+            }
+            for (uint32_t r = 0; r < rounds; r += 4)
+            {
+                V part[GV][4];
 #pragma unroll
-            for (int e = 0; e < GV; e++)
+                for (int e = 0; e < GV; e++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) vadd(sum[e], part[e][q]);
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const uint32_t c = seg_lo[e] + r + k;
+                        if (c <= seg_hi[e]) part[e][k] = S[uint64_t(c) * g.Q + base[e]];
+                        else vzero(part[e][k]);
+                    }
+#pragma unroll
+                for (int e = 0; e < GV; e++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) vadd(sum[e], part[e][k]);
+            }
         }
 #pragma unroll
         for (int e = 0; e < GV; e++)

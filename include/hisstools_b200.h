@@ -167,12 +167,27 @@ int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant);
 int hb_conv_set_host_pipeline(hb_conv *c, int pipelined);
 /* algorithmic bytes one hop moves (IR spectra + FDL + time-domain I/O) */
 uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
-/* per-kernel device timing: while enabled, every hop records CUDA events around its three kernels on
- * the launching stream.  hb_conv_get_profile waits for the recorded hops and returns the summed
- * milliseconds of the forward-FFT, multiply-accumulate and inverse-FFT kernels and the hop count
- * since profiling was enabled (bench.py's roofline figure). */
+/* Schedule of a hop.  overlapped = 1: the share of the NEXT hop that only needs spectra already in the
+ * delay line (partitions 1..P-1, "tail") is computed on a second stream as soon as this hop's forward FFTs are
+ * done, beside the inverse FFTs of this hop and the forward FFTs of the next; a hop's critical path is forward
+ * FFT -> partition 0 ("head") -> inverse FFT.  It is the stream form of the reference's spreading of partitions
+ * over the samples of a hop (PartitionedConvolve.cpp:330-347).  overlapped = 0: forward FFTs, one multiply-accumulate
+ * over all partitions, inverse FFTs, in a row.  overlapped = 2 (default): overlapped when the tail streams at least
+ * 4 MiB of spectra per hop, serial below that (launch-latency-bound hops gain nothing from a second stream).
+ * Results differ by summation order only.  Takes effect with a reset. */
+int hb_conv_set_schedule(hb_conv *c, int overlapped);
+/* schedule in effect after the last reset (1 overlapped, 0 serial: also whenever only one partition is loaded) */
+int hb_conv_schedule(const hb_conv *c);
+/* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in
+ * the overlapped one the tail's share, 2sB(P-1)(K+I) */
+uint64_t hb_conv_bytes_per_launch(const hb_conv *c);
+/* per-kernel device timing: while enabled, every hop records CUDA events around its kernels on the streams they
+ * are launched on.  hb_conv_get_profile waits for the recorded hops and returns in ms[0..4] the summed milliseconds
+ * of: forward FFTs; the whole (serial) or head (overlapped) multiply-accumulate; the wait for the tail; inverse
+ * FFTs; the tail multiply-accumulate (0 when serial) -- and the hop count since profiling was enabled.  (An event
+ * recorded straight behind a stream wait is not ordered after it: only ms[2] + ms[3] is meaningful when overlapped.) */
 int hb_conv_set_profiling(hb_conv *c, int enable);
-int hb_conv_get_profile(hb_conv *c, double *ms_forward, double *ms_cmac, double *ms_inverse, uint64_t *hops);
+int hb_conv_get_profile(hb_conv *c, double *ms, uint64_t *hops);
 
 /* ---------------------------------------------------------------------------------------------
  * Non-uniform partition scheme for a whole channel matrix -- what MonoConvolve (MonoConvolve.h:30-48)

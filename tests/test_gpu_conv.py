@@ -38,13 +38,15 @@ def stream(obj_process, x, block, dtype=np.float32, sizes=None):
 
 # ---- PartitionedConvolve ------------------------------------------------------------------------
 
+@pytest.mark.parametrize("schedule", ["overlapped", "serial"])
 @pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("name", ["c1", "ragged", "phase", "slice", "trunc", "min"])
-def test_pconv_golden(hb, name, variant):
+def test_pconv_golden(hb, name, variant, schedule):
     fft, block, max_len, offset, length, reset_offset, err = (int(v) for v in G["pconv_%s_meta" % name])
     ir, x, want = G["pconv_%s_ir" % name], G["pconv_%s_x" % name], G["pconv_%s_y" % name]
     pc = hb.PartitionedConvolve(fft, len(ir) if max_len < 0 else max_len, offset, length)
     pc.engine.set_tuning(0, variant)
+    pc.engine.set_schedule(schedule == "overlapped")
     pc.setResetOffset(reset_offset)
     assert int(pc.set(ir, len(ir))) == err
     got = stream(lambda a, b, n: pc.process(a, b, n), x, block)
@@ -67,6 +69,55 @@ def test_pconv_config2_against_reference(hb, variant):
     assert ck.rel_rms(got, want) <= TOL32
     assert ck.rel_rms(got[-16 * 1024:], want[-16 * 1024:]) <= TOL32          # FDL full
     truth = ck.direct_convolve_delayed(ir[:4096], x[:8192], 1024)            # delay is exactly B
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_schedules_agree_and_survive_mid_stream_changes(hb, dtype):
+    """Overlapped schedule (tail of the next hop computed ahead on a second stream) against the serial one on a
+    4-in x 3-out matrix: same result up to summation order, also across reset(), a new IR mid-stream (the tail
+    launched ahead must be discarded) and a ragged call pattern."""
+    from hisstools_library_b200.convolve import _Engine
+    n_in, n_out, L, B = 4, 3, 2500, 256
+    tol = TOL32 if dtype == np.float32 else TOL64
+    irs = [[ck.synth_ir(L, 500 + 10 * o + i).astype(dtype) for i in range(n_in)] for o in range(n_out)]
+    irs2 = [[ck.synth_ir(L // 2, 900 + 10 * o + i).astype(dtype) for i in range(n_in)] for o in range(n_out)]
+    xs = np.stack([ck.synth_audio(B * 40 + 77, 500 + i) for i in range(n_in)]).astype(dtype)
+    outs = {}
+    for schedule in ("overlapped", "serial"):
+        e = _Engine(dtype, 1, n_in, n_out, 2 * B, L, 0, 0, 0)
+        e.set_schedule(schedule == "overlapped")
+        e.set_reset_offset(0)
+        for o in range(n_out):
+            for i in range(n_in):
+                e.set_ir(0, i, o, irs[o][i], L)
+        y = np.zeros((n_out, xs.shape[1]), dtype)
+        pos, k = 0, 0
+        sizes = [B, B, 100, 3 * B, 1, 2 * B + 5, B]
+        while pos < xs.shape[1]:
+            n = min(sizes[k % len(sizes)], xs.shape[1] - pos)
+            if k == 9:
+                e.reset()
+            if k == 17:
+                for o in range(n_out):
+                    for i in range(n_in):
+                        e.set_ir(0, i, o, irs2[o][i], L // 2)
+            xi = [np.ascontiguousarray(xs[r, pos:pos + n]) for r in range(n_in)]
+            yo = [np.zeros(n, dtype) for _ in range(n_out)]
+            e.process(xi, yo, n)
+            for r in range(n_out):
+                y[r, pos:pos + n] = yo[r]
+            pos += n
+            k += 1
+        assert e.schedule == schedule
+        outs[schedule] = y
+        e.close()
+    for o in range(n_out):
+        assert ck.rel_rms(outs["overlapped"][o], outs["serial"][o]) <= (1e-6 if dtype == np.float32 else 1e-14)
+    # and the first stretch (before the reset) against the truth
+    first = sum([B, B, 100, 3 * B, 1, 2 * B + 5, B, B, B])
+    for o in range(n_out):
+        truth = sum(ck.direct_convolve_delayed(irs[o][i], xs[i][:first], B) for i in range(n_in))
+        assert ck.rel_rms(outs["overlapped"][o][:first], truth) <= tol * (1 if dtype == np.float32 else 10)
 
 
 def test_pconv_call_sizes_do_not_matter(hb):
