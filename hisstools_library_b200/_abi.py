@@ -73,6 +73,8 @@ SIGNATURES = {
     "hb_spectral_convolve": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
     "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "hb_conv_set_trace": (C.c_int, [V, C.c_int]),
+    "hb_conv_get_trace": (C.c_int, [V, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_conv_set_schedule": (C.c_int, [V, C.c_int]),
     "hb_conv_schedule": (C.c_int, [V]),
     "hb_conv_bytes_per_launch": (C.c_uint64, [V]),
@@ -94,7 +96,8 @@ def lib():
     """The loaded library (built on first use when missing or stale)."""
     global _lib
     if _lib is None:
-        path = _build.build()
+        # HISSTOOLS_B200_LIB: an explicit (pre-built) library instead of the in-tree one
+        path = os.environ.get("HISSTOOLS_B200_LIB") or _build.build()
         handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError = header and library disagree

@@ -140,6 +140,15 @@ class _Engine:
         _abi.check(_abi.lib().hb_conv_get_profile(self._h, ms, C.byref(h)))
         return dict(zip(("forward", "cmac", "wait", "inverse", "tail"), [float(v) for v in ms])), int(h.value)
 
+    def set_trace(self, enable=True):
+        return _abi.check(_abi.lib().hb_conv_set_trace(self._h, 1 if enable else 0))
+
+    def get_trace(self):
+        """(stamps[16 hops][5 kinds][entry/exit][256 CTAs] in ns (0 = not run), hops processed so far)."""
+        buf, hop = (C.c_uint64 * (16 * 5 * 2 * 256))(), C.c_uint64()
+        _abi.check(_abi.lib().hb_conv_get_trace(self._h, buf, C.byref(hop)))
+        return np.frombuffer(buf, dtype=np.uint64).reshape(16, 5, 2, 256).copy(), int(hop.value)
+
     def set_schedule(self, overlapped=True):
         """True: overlapped (tail of the next hop computed ahead on a second stream), False: serial, None: automatic."""
         return _abi.check(_abi.lib().hb_conv_set_schedule(self._h, 2 if overlapped is None else (1 if overlapped else 0)))

@@ -102,6 +102,7 @@ struct hb_conv
     cudaEvent_t ev_fwd = nullptr, ev_tail[2] = {nullptr, nullptr};
     bool tail_valid = false;        // d_St[tail_par] holds the tail of the upcoming hop
     int tail_par = 0;
+    DevBuf d_trace;                 // optional kernel timeline (hb_conv_set_trace)
 
     // deferred host-pointer path of hb_conv_process: the block finished by a hop is fetched to pinned host
     // memory while the caller is away; a later call only waits on an event that completed long ago
@@ -204,9 +205,9 @@ void plan_geometry(hb_conv *c)
     if (c->split)
     {
         // The tail launch runs beside the FFT kernels of the critical path.  Where an FFT CTA fits on an SM next
-        // to a multiply-accumulate CTA and its ring (shared memory; registers: 512 x 64 + 256 x 112 for transforms
-        // up to 4096 points; tools/coreside_probe.cu confirms the placement) nothing changes; otherwise the tail
-        // grid leaves as many SMs free as the FFT kernels have CTAs (stream-K: any grid size balances).
+        // to a multiply-accumulate CTA and its ring (shared memory; registers: 512 x 64 + 256 x 96 for transforms
+        // up to 4096 points, see HB_CMAC_MAXREG) nothing changes; otherwise the tail grid leaves as many SMs free
+        // as the FFT kernels have CTAs (stream-K: any grid size balances).
         const size_t es = c->esize();
         const size_t fft_data = size_t(padded_elems<HB_PADSH>(1u << log2m)) * 2 * es;
         const size_t fft_tw = (size_t(1) << log2m) * 2 * es;
@@ -241,7 +242,7 @@ void free_device(hb_conv *c)
     cudaFree(c->d_H); cudaFree(c->d_X); cudaFree(c->d_Hnyq); cudaFree(c->d_Xnyq); cudaFree(c->d_tw);
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = c->d_tw = nullptr;
     c->d_S.release();
-    c->d_St[0].release(); c->d_St[1].release();
+    c->d_St[0].release(); c->d_St[1].release(); c->d_trace.release();
     if (c->s_tail) cudaStreamDestroy(c->s_tail);
     if (c->ev_fwd) cudaEventDestroy(c->ev_fwd);
     for (int k = 0; k < 2; k++) if (c->ev_tail[k]) cudaEventDestroy(c->ev_tail[k]);
@@ -629,6 +630,8 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     if (c->profiling && (r = profile_begin_hop(c, &pe))) return r;
     // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
     c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+    c->g.hop++;
+    c->g.trace = (unsigned long long *) c->d_trace.p;
     if (pe) HB_CUDA(cudaEventRecord(pe[0], st));
     if ((r = launch_fwd<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st))) return r;
     if (pe) HB_CUDA(cudaEventRecord(pe[1], st));
@@ -637,7 +640,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     if (!c->split)
     {
         Range rf = c->r_full;
-        rf.slot = c->g.slot;
+        rf.slot = c->g.slot; rf.kind = 2;
         if ((r = launch_cmac<T>(c, rf, c->d_S.p, c->variant, st))) return r;
         if (pe) { HB_CUDA(cudaEventRecord(pe[2], st)); HB_CUDA(cudaEventRecord(pe[3], st)); }
         sets.n = 1;
@@ -651,6 +654,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
         const int np = c->tail_par ^ 1;
         Range rt = c->r_tail;
         rt.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+        rt.kind = 2;
         HB_CUDA(cudaStreamWaitEvent(c->s_tail, c->ev_fwd, 0));
         if (pe) { HB_CUDA(cudaEventRecord(pe[5], c->s_tail)); c->ev_has_tail[c->ev_used - 1] = 1; }
         if ((r = launch_cmac<T>(c, rt, c->d_St[np].p, c->variant, c->s_tail))) return r;
@@ -659,7 +663,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
         // critical path: partition 0 against the newest spectrum (direct loads: no shared memory, so its CTAs fit
         // beside the tail's on every SM)
         Range rh = c->r_head;
-        rh.slot = c->g.slot;
+        rh.slot = c->g.slot; rh.kind = 1;
         if ((r = launch_cmac<T>(c, rh, c->d_S.p, 0, st))) return r;
         if (pe) HB_CUDA(cudaEventRecord(pe[2], st));
         sets.n = 1;
@@ -802,7 +806,8 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
         k_gather<T><<<o_loc, 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
                                           peer.parity, peer.slot, expected, (uint32_t) B,
                                           last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
-                                          first ? y_keep : nullptr, c->yout_ld, first ? d_out : nullptr, out_ld, accumulate);
+                                          first ? y_keep : nullptr, c->yout_ld, first ? d_out : nullptr, out_ld, accumulate,
+                                          (unsigned long long *) c->d_trace.p, c->g.hop);
         HB_LAUNCH_CHECK();
     }
     c->cur = nxt;
@@ -1291,6 +1296,31 @@ extern "C" int hb_conv_set_schedule(hb_conv *c, int overlapped)
     if (overlapped < 0 || overlapped > 2) { set_error("schedule must be 0 (serial), 1 (overlapped) or 2 (automatic)"); return HB_ERR_BAD_ARG; }
     c->schedule = overlapped;
     c->need_reset = true;           // the partial-segment sets depend on the schedule
+    return HB_OK;
+}
+
+extern "C" int hb_conv_set_trace(hb_conv *c, int enable)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    HB_CUDA(cudaDeviceSynchronize());
+    if (!enable) { c->d_trace.release(); return HB_OK; }
+    const size_t bytes = size_t(TRACE_HOPS) * TRACE_KINDS * 2 * TRACE_CTAS * sizeof(unsigned long long);
+    if ((rc = c->d_trace.ensure(bytes))) return rc;
+    HB_CUDA(cudaMemset(c->d_trace.p, 0, bytes));
+    return HB_OK;
+}
+
+extern "C" int hb_conv_get_trace(hb_conv *c, uint64_t *out, uint64_t *hop)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    if (!c->d_trace.p || !out) { set_error("hb_conv_get_trace: tracing is off"); return HB_ERR_BAD_ARG; }
+    HB_CUDA(cudaDeviceSynchronize());
+    HB_CUDA(cudaMemcpy(out, c->d_trace.p, size_t(TRACE_HOPS) * TRACE_KINDS * 2 * TRACE_CTAS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (hop) *hop = c->g.hop;
     return HB_OK;
 }
 

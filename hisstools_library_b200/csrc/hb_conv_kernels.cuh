@@ -49,8 +49,25 @@ struct Geom
     uint32_t tiles;        // groups*n_ot*n_bt
     uint32_t G;            // CTAs of the multiply-accumulate kernel
     uint32_t slot;         // FDL slot holding the newest spectrum
+    uint32_t hop;          // hop counter (trace only)
     uint64_t U;            // units in total = tiles*upt
+    unsigned long long *trace;   // optional timeline buffer (hb_conv_set_trace), nullptr = off
 };
+
+// Timeline tracing (debug): thread 0 of every CTA stamps %globaltimer at entry and exit into
+// trace[(((hop % TRACE_HOPS) * TRACE_KINDS + kind) * 2 + exit) * TRACE_CTAS + cta]; kind 0 forward FFT, 1 head,
+// 2 tail / whole multiply-accumulate, 3 inverse FFT, 4 owner-side sum of the multi-GPU exchange.  Shows which kernels really share the machine in the overlapped schedule.
+constexpr uint32_t TRACE_HOPS = 16, TRACE_CTAS = 256, TRACE_KINDS = 5;
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, uint32_t hop, uint32_t kind, uint32_t is_exit)
+{
+    if (trace && threadIdx.x == 0 && blockIdx.x < TRACE_CTAS)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        trace[(((hop % TRACE_HOPS) * TRACE_KINDS + kind) * 2 + is_exit) * TRACE_CTAS + blockIdx.x] = t;
+    }
+}
+__device__ __forceinline__ void trace_mark(const Geom &g, uint32_t kind, uint32_t is_exit) { trace_mark(g.trace, g.hop, kind, is_exit); }
 
 // One launch of the multiply-accumulate kernel covers the partitions [p0, p0 + pc) of every (tile, input):
 // the whole IR (p0 = 0, pc = P) in the serial schedule; in the overlapped schedule the newest spectrum
@@ -62,7 +79,7 @@ struct Range
     uint32_t upt;          // units per tile = ins*pc
     uint32_t G;            // CTAs of this launch
     uint32_t slot;         // FDL slot of the spectrum that meets partition 0
-    uint32_t pad;
+    uint32_t kind;         // trace only: 1 head, 2 tail / whole
     uint64_t U;            // units of this launch = tiles*upt
 };
 
@@ -193,8 +210,16 @@ struct Cursor
 // issued by one thread; all threads consume from shared memory.  One barrier per step.
 // dynamic shared memory: nstages * (Q + TBV) vectors, then nstages mbarriers.
 // ---------------------------------------------------------------------------------------------
+// Register cap: in the overlapped schedule an FFT CTA (512 threads x 64 registers = 32 K) has to be placed on an SM
+// beside a resident multiply-accumulate CTA.  At the 111 registers ptxas picks on its own (256 x 112 = 28 K) the
+// block scheduler does not co-schedule the two although 60 K < 64 K; at <= 96 (24 K) it does (measured with
+// hb_conv_set_trace, profiles/r1_overlap_trace.txt).  No instance spills at 96 and the streaming rate is unchanged.
+#ifndef HB_CMAC_MAXREG
+#define HB_CMAC_MAXREG 96
+#endif
+#define HB_CMAC_BOUNDS __maxnreg__(HB_CMAC_MAXREG)
 template <class T, int XA, int OB>
-__global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
+__global__ void HB_CMAC_BOUNDS k_cmac_tma(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
                                                      const typename VecOf<T>::type *__restrict__ X,
                                                      typename VecOf<T>::type *__restrict__ S, const int nstages)
 {
@@ -207,6 +232,7 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const Range r
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid % g.TX, ty = tid / g.TX;
     const bool active = ty < g.TY;
+    trace_mark(g, rg.kind, 0);
 
     const uint64_t u0 = unit_begin(blockIdx.x, rg.U, rg.G), u1 = unit_begin(blockIdx.x + 1, rg.U, rg.G);
     const uint32_t n = (uint32_t) (u1 - u0);
@@ -287,6 +313,7 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma(const Geom g, const Range r
         if (++stage == (uint32_t) nstages) { stage = 0; parity ^= 1; }
         __syncthreads();
     }
+    trace_mark(g, rg.kind, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -301,6 +328,7 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg, 
     typedef typename VecOf<T>::type V;
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid % g.TX, ty = tid / g.TX;
+    trace_mark(g, rg.kind, 0);
     if (ty >= g.TY) return;
 
     const uint64_t u0 = unit_begin(blockIdx.x, rg.U, rg.G), u1 = unit_begin(blockIdx.x + 1, rg.U, rg.G);
@@ -359,6 +387,7 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg, 
                 }
         }
     }
+    trace_mark(g, rg.kind, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -435,6 +464,7 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
     const uint32_t ch = blockIdx.x;
     const uint32_t B = g.B;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    trace_mark(g, 0, 0);
     // twiddles of this transform size staged in shared memory behind the data (one global round trip
     // instead of one per pass); the loads are issued together with the input loads below
     Cx<T> *stw = s + padded_elems<HB_PADSH>(B);
@@ -490,6 +520,7 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
             xrow[(size_t(bt) * g.P + g.slot) * TB + j] = z;
         }
     }
+    trace_mark(g, 0, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,6 +577,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
     const uint32_t grp = ch / g.outs, o = ch - grp * g.outs;
     const uint32_t ot = o / g.OT, row = o - ot * g.OT;
     const uint32_t B = g.B;
+    trace_mark(g, 3, 0);
     if (stage_tw)
     {
         // twiddles of this transform size into shared memory (published by the barriers of block_sum below)
@@ -722,6 +754,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
             __threadfence_system();
             atomicAdd_system(peer.count[owner] + peer.parity * peer.world + peer.rank, 1u);
         }
+        trace_mark(g, 3, 1);
         return;
     }
     T *dst = yout + size_t(ch) * ld + off;
@@ -747,6 +780,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
             else st_pair(dst + 2 * k, z.y * scale, z.x * scale, vd);
         }
     }
+    trace_mark(g, 3, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -760,9 +794,11 @@ __global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, con
                                                 uint32_t parity, uint64_t slot, uint32_t expected, uint32_t B,
                                                 T *__restrict__ yout, size_t ld, size_t off, int add_result,
                                                 const T *__restrict__ carry_src, size_t carry_src_ld,
-                                                T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry)
+                                                T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
+                                                unsigned long long *trace, uint32_t hop)
 {
     const uint32_t o = blockIdx.x;
+    trace_mark(trace, hop, 4, 0);
     if (carry_dst)
     {
         const T *cs = carry_src + size_t(o) * carry_src_ld;
@@ -785,6 +821,7 @@ __global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, con
         for (uint32_t r = 0; r < world; r++) sum += __ldcg(inbox + ((size_t(parity) * world + r) * outs_local + o) * slot + k);
         dst[k] = add_result ? dst[k] + sum : sum;
     }
+    trace_mark(trace, hop, 4, 1);
 }
 
 // ---------------------------------------------------------------------------------------------

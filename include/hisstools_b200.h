@@ -181,6 +181,14 @@ int hb_conv_schedule(const hb_conv *c);
 /* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in
  * the overlapped one the tail's share, 2sB(P-1)(K+I) */
 uint64_t hb_conv_bytes_per_launch(const hb_conv *c);
+/* Kernel timeline (debug): while enabled, thread 0 of every CTA of the hop kernels stamps %globaltimer at entry
+ * and exit.  hb_conv_get_trace synchronises the device and copies the HB_TRACE_WORDS stamps out:
+ * out[(((hop % 16) * 5 + kind) * 2 + exit) * 256 + cta], kind 0 forward FFT, 1 head, 2 tail / whole
+ * multiply-accumulate, 3 inverse FFT, 4 owner-side sum of the multi-GPU exchange; *hop = hops processed so far
+ * (tools/trace_timeline.py prints it). */
+#define HB_TRACE_WORDS (16 * 5 * 2 * 256)
+int hb_conv_set_trace(hb_conv *c, int enable);
+int hb_conv_get_trace(hb_conv *c, uint64_t *out, uint64_t *hop);
 /* per-kernel device timing: while enabled, every hop records CUDA events around its kernels on the streams they
  * are launched on.  hb_conv_get_profile waits for the recorded hops and returns in ms[0..4] the summed milliseconds
  * of: forward FFTs; the whole (serial) or head (overlapped) multiply-accumulate; the wait for the tail; inverse
