@@ -12,7 +12,7 @@ import checkers as ck
 
 pytestmark = pytest.mark.gpu
 
-N_IN, N_OUT, L, B, BLOCKS = 4, 4, 3000, 256, 20
+N_IN, N_OUT, L, B, BLOCKS = 8, 8, 3000, 256, 20
 
 
 def _inputs():
@@ -63,12 +63,12 @@ def _worker(rank, world, port, out_dir, exchange):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["nccl", "fused"])
-def test_two_gpu_sharded_matrix(tmp_path, exchange):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_multi_gpu_sharded_matrix(tmp_path, exchange, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
     irs, xs = _inputs()
     got = np.concatenate([np.load(tmp_path / ("%s_rank%d.npy" % (exchange, r))) for r in range(world)], axis=0)
