@@ -10,6 +10,7 @@
 // (SURVEY A.2).  After a call the tail of both rows becomes the head of the other (ping-pong) row set.
 #include "hb_common.cuh"
 #include "hb_conv_kernels.cuh"
+#include "hb_conv_big.cuh"
 
 #include <algorithm>
 #include <map>
@@ -103,6 +104,8 @@ struct hb_conv
     bool tail_valid = false;        // d_St[tail_par] holds the tail of the upcoming hop
     int tail_par = 0;
     DevBuf d_trace;                 // optional kernel timeline (hb_conv_set_trace)
+    BigScratch big;                 // four-step scratch for FFT sizes above the single-CTA limit (hb_conv_big.cuh)
+    DevBuf d_nyq;
 
     // deferred host-pointer path of hb_conv_process: the block finished by a hop is fetched to pinned host
     // memory while the caller is away; a later call only waits on an event that completed long ago
@@ -243,6 +246,7 @@ void free_device(hb_conv *c)
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = c->d_tw = nullptr;
     c->d_S.release();
     c->d_St[0].release(); c->d_St[1].release(); c->d_trace.release();
+    c->big.release(); c->d_nyq.release();
     if (c->s_tail) cudaStreamDestroy(c->s_tail);
     if (c->ev_fwd) cudaEventDestroy(c->ev_fwd);
     for (int k = 0; k < 2; k++) if (c->ev_tail[k]) cudaEventDestroy(c->ev_tail[k]);
@@ -385,9 +389,33 @@ int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     return HB_OK;
 }
 
+template <class T> bool is_big(const hb_conv *c) { return (int) c->g.log2n - 1 > SmemFftLimit<T>::max_log2m; }
+inline dim3 bigc_grid(uint32_t B, size_t batch) { return dim3((unsigned) std::min<size_t>((B + 255) / 256, 256), (unsigned) batch); }
+
+// forward transform of every input channel at sizes above the single-CTA limit (hb_conv_big.cuh)
+template <class T>
+int launch_fwd_big(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const int m = (int) g.log2n - 1;
+    const size_t rows = size_t(g.groups) * g.ins;
+    int rc;
+    if ((rc = c->big.ensure<T>(m, std::max(rows, size_t(g.groups) * g.outs)))) return rc;
+    Cx<T> *z1 = (Cx<T> *) c->big.z1.p, *z2 = (Cx<T> *) c->big.z2.p;
+    const Cx<T> *tw = (const Cx<T> *) c->d_tw;
+    k_bigc_pack<T><<<bigc_grid(g.B, rows), 256, 0, st>>>(g, prev, prev_ld, newest, new_ld, save, save_ld, z1);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_cfft<T>(z1, z2, z1, m, rows, tw, c->tw_log2, st))) return rc;
+    if ((rc = big_split<T>(z1, m, 0, rows, tw, c->tw_log2, st))) return rc;
+    k_bigc_to_fdl<T><<<bigc_grid(g.B, rows), 256, 0, st>>>(g, z1, (Cx<T> *) c->d_X, (T *) c->d_Xnyq);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
 template <class T>
 int launch_fwd(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
 {
+    if (is_big<T>(c)) return launch_fwd_big<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st);
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_fwd_ept<T, EPT>(c, prev, prev_ld, newest, new_ld, save, save_ld, st));
 }
 
@@ -414,9 +442,38 @@ int launch_inv_ept(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStre
     return HB_OK;
 }
 
+// inverse transform of every output channel at sizes above the single-CTA limit (hb_conv_big.cuh)
+template <class T>
+int launch_inv_big(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const int m = (int) g.log2n - 1;
+    const size_t rows = size_t(g.groups) * g.outs;
+    int rc;
+    if ((rc = c->big.ensure<T>(m, std::max(rows, size_t(g.groups) * g.ins))) || (rc = c->d_nyq.ensure(rows * sizeof(T)))) return rc;
+    Cx<T> *z1 = (Cx<T> *) c->big.z1.p, *z2 = (Cx<T> *) c->big.z2.p;
+    const Cx<T> *tw = (const Cx<T> *) c->d_tw;
+    k_bigc_nyq<T><<<(unsigned) rows, 256, 0, st>>>(g, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, (T *) c->d_nyq.p);
+    HB_LAUNCH_CHECK();
+    k_bigc_gather<T><<<bigc_grid(g.B, rows), 256, 0, st>>>(g, sets, (const T *) c->d_nyq.p, z1, io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_split<T>(z1, m, 1, rows, tw, c->tw_log2, st))) return rc;
+    k_big_exchange<T><<<(unsigned) std::min<size_t>((rows * g.B + 255) / 256, 2048), 256, 0, st>>>(z1, rows * g.B);
+    HB_LAUNCH_CHECK();
+    if ((rc = big_cfft<T>(z1, z2, z1, m, rows, tw, c->tw_log2, st))) return rc;
+    k_bigc_store<T><<<bigc_grid(g.B / 2, rows), 256, 0, st>>>(g, z1, io.yout, io.ld, io.off, io.add_result);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
 template <class T>
 int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer = PeerOut())
 {
+    if (is_big<T>(c))
+    {
+        if (peer.world) { set_error("the fused multi-GPU exchange is not implemented for FFT sizes above the single-CTA limit"); return HB_ERR_UNSUPPORTED; }
+        return launch_inv_big<T>(c, sets, io, st);
+    }
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer));
 }
 
@@ -434,9 +491,48 @@ int launch_ir_ept(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t
 }
 
 template <class T>
+int launch_ir_big(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const int m = (int) g.log2n - 1;
+    const Cx<T> *tw = (const Cx<T> *) c->d_tw;
+    // partitions in batches that keep the scratch modest (the engine's own scratch is sized for its channels)
+    const uint32_t batch_max = (uint32_t) std::max<size_t>(1, (size_t(64) << 20) / (size_t(g.B) * sizeof(Cx<T>)));
+    BigScratch scratch;
+    int rc = HB_OK;
+    if ((rc = scratch.ensure<T>(m, std::min(nwrite, batch_max)))) return rc;
+    Cx<T> *z1 = (Cx<T> *) scratch.z1.p, *z2 = (Cx<T> *) scratch.z2.p;
+    for (uint32_t p0 = 0; p0 < nwrite && rc == HB_OK; p0 += batch_max)
+    {
+        const uint32_t nb = std::min(batch_max, nwrite - p0);
+        Geom gp = g;                                     // kernels index partitions from blockIdx.y: shift the base instead
+        const size_t skip = size_t(p0) * g.B;
+        const T *src = d_ir + std::min(skip, taps);
+        const size_t left = taps > skip ? taps - skip : 0;
+        k_bigc_ir_pack<T><<<bigc_grid(g.B, nb), 256, 0, st>>>(gp, src, left, z1);
+        count_launch();
+        if ((rc = big_cfft<T>(z1, z2, z1, m, nb, tw, c->tw_log2, st))) break;
+        if ((rc = big_split<T>(z1, m, 0, nb, tw, c->tw_log2, st))) break;
+        // unit addresses advance by Q per partition: partition p0 + k of this batch = partition k of a layout shifted by p0 units
+        Cx<T> *Hs = (Cx<T> *) c->d_H + size_t(p0) * g.Q * VecOf<T>::CPV;
+        T *Hn = (T *) c->d_Hnyq + p0;
+        k_bigc_to_h<T><<<bigc_grid(g.B, nb), 256, 0, st>>>(gp, z1, grp, in, o, Hs, Hn);
+        count_launch();
+    }
+    cudaError_t e = cudaStreamSynchronize(st);            // the scratch is freed on return
+    scratch.release();
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error("impulse-response transform -> %s", cudaGetErrorString(e)); return HB_ERR_CUDA; }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("impulse-response kernels -> %s", cudaGetErrorString(e)); return HB_ERR_CUDA; }
+    return HB_OK;
+}
+
+template <class T>
 int launch_ir(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
 {
     if (!nwrite) return HB_OK;
+    if (is_big<T>(c)) return launch_ir_big<T>(c, d_ir, taps, grp, in, o, nwrite, st);
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_ir_ept<T, EPT>(c, d_ir, taps, grp, in, o, nwrite, st));
 }
 
@@ -452,8 +548,8 @@ int launch_rows(T *dst, size_t dld, const T *src, size_t sld, size_t n, size_t r
 
 bool fft_supported(const hb_conv *c, uintptr_t log2n)
 {
-    const int lim = c->dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m;
-    return (int) log2n - 1 <= lim;
+    (void) c;
+    return (int) log2n - 1 <= BIG_MAX_LOG2;           // single CTA up to SmemFftLimit, four-step above (hb_conv_big.cuh)
 }
 
 // setFFTSize semantics (PartitionedConvolve.cpp:131-154)
@@ -876,8 +972,7 @@ extern "C" int hb_conv_create(hb_conv **out, int dtype, uint32_t groups, uint32_
     c->max_fft_log2 = l2;
     if (!fft_supported(c, l2))
     {
-        set_error("FFT size 2^%d is beyond the shared-memory FFT of this build (max 2^%d for this dtype)", (int) l2,
-                  (dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m) + 1);
+        set_error("FFT size 2^%d is beyond what this build implements (2^%d)", (int) l2, BIG_MAX_LOG2 + 1);
         delete c;
         return HB_ERR_UNSUPPORTED;
     }

@@ -156,6 +156,36 @@ def test_pconv_fft_sizes(hb, fft):
     assert ck.rel_rms(got, ck.direct_convolve_delayed(ir, x, B)) <= TOL32
 
 
+@pytest.mark.parametrize("fft,dtype", [(65536, np.float32), (131072, np.float32), (1 << 20, np.float32), (32768, np.float64), (65536, np.float64)])
+def test_pconv_fft_sizes_above_one_cta(hb, fft, dtype):
+    """FFT sizes whose half-length transform does not fit one CTA's shared memory (four-step path, hb_conv_big.cuh), up to
+    the reference's largest (2^20, PartitionedConvolve.h:18-19): against the unmodified reference (float) / the C oracle
+    (double) and float64 direct convolution, streamed in ragged calls; both schedules."""
+    B = fft // 2
+    L = 2 * B + B // 3 + 7                                   # three partitions, the last one ragged
+    ir = ck.synth_ir(L, 6).astype(dtype)
+    x = ck.synth_audio(B * 5 + 1234, 6).astype(dtype)
+    tol = TOL32 if dtype == np.float32 else TOL64
+    truth = ck.direct_convolve_delayed_fft(ir, x, B)
+    outs = {}
+    for schedule in (True, False):
+        pc = hb.PartitionedConvolve(fft, L, 0, 0, dtype=dtype)
+        pc.engine.set_schedule(schedule)
+        pc.setResetOffset(0)
+        assert int(pc.set(ir)) == 0
+        got = stream(lambda a, b, n: pc.process(a, b, n), x, B // 2 + 77, dtype=dtype)
+        assert ck.rel_rms(got, truth) <= tol
+        outs[schedule] = got
+        del pc
+    assert ck.rel_rms(outs[True], outs[False]) <= tol / 10
+    if dtype == np.float32 and ck.ref() is not None and fft <= 131072:
+        want, _ = ck.ref_pconv_run(fft, ir, x, B)
+        assert ck.rel_rms(outs[True], want) <= TOL32
+    if dtype == np.float64 and fft <= 32768:
+        want, _ = ck.oracle_pconv_run(fft, ir, x, B, dtype=np.float64)
+        assert ck.rel_rms(outs[True], want) <= TOL64
+
+
 def test_pconv_semantics(hb):
     E = hb.ConvolveError
     pc = hb.PartitionedConvolve(512, 1000, 0, 0)         # max length rounds up to 1024 (cpp:77-82)
