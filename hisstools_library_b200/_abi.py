@@ -71,6 +71,9 @@ SIGNATURES = {
     "hb_spectral_max_fft_size": (UP, [V]),
     "hb_spectral_convolved_size": (UP, [V, UP, UP, C.c_int]),
     "hb_spectral_convolve": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
+    "hb_spectral_correlate": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
+    "hb_spectral_convolve_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
+    "hb_spectral_correlate_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
     "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "hb_conv_set_trace": (C.c_int, [V, C.c_int]),

@@ -325,6 +325,18 @@ static int launch_cfft(const T *re_in, const T *im_in, T *re_out, T *im_out, int
     return HB_OK;
 }
 
+// complex transform of `batch` split-plane arrays in device memory (forward, or the unscaled inverse when swap != 0:
+// a forward transform of the exchanged planes, Core:1341-1346) -- the entry other translation units use
+int cfft_planes(int dtype, const void *re_in, const void *im_in, void *re_out, void *im_out, int log2n, int swap, size_t batch, size_t stride,
+                const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs)
+{
+    if (dtype == HB_F64)
+        return launch_cfft<double>((const double *) re_in, (const double *) im_in, (double *) re_out, (double *) im_out, log2n, swap, batch, stride,
+                                   (const Cx<double> *) tw, tw_log2, st, bs);
+    return launch_cfft<float>((const float *) re_in, (const float *) im_in, (float *) re_out, (float *) im_out, log2n, swap, batch, stride,
+                              (const Cx<float> *) tw, tw_log2, st, bs);
+}
+
 template <class T, class TI>
 static int launch_rfft(const TI *x, size_t in_length, size_t x_stride, const T *re_in, const T *im_in, T *re_out, T *im_out,
                        size_t stride, int log2n, size_t batch, const Cx<T> *tw, int tw_log2, cudaStream_t st, BigScratch *bs = nullptr)

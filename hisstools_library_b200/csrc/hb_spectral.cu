@@ -1,10 +1,12 @@
-// hb_spectral.cu -- one-shot FFT convolution of two real buffers: the hb_spectral_* entry points of
+// hb_spectral.cu -- one-shot FFT convolution and correlation of two buffers: the hb_spectral_* entry points of
 // include/hisstools_b200.h.
 //
-// Replaces spectral_processor<T>::convolve(T*, in_ptr, in_ptr, EdgeMode) of the reference
-// (SpectralProcessor.hpp:169-172 -> binary_op :616-674, op_sizes :323-354, arrange_convolve :445-481)
-// and the per-bin product it uses (SpectralFunctions.hpp: ir_convolve_real :420-424, real_operation
-// :63-84, impl::convolve :274-281).  Two launches:
+// Replaces spectral_processor<T>::convolve / correlate of the reference, real inputs (SpectralProcessor.hpp:169-172,
+// 181-184 -> binary_op :616-674) and complex inputs (:164-167, 176-179 -> binary_op :559-614), with op_sizes :323-354,
+// arrange_convolve :445-481, arrange_correlate :483-538 and the per-bin products they use (SpectralFunctions.hpp:
+// real_operation :63-84, complex_operation :49-61, impl::correlate :265-272, impl::convolve :274-281).
+// The edge-mode arrangement is evaluated as a list of "terms" (Arrange below) built on the host from the reference's
+// copy / wrap / zero calls.  Real inputs, two launches:
 //   k_spec_fwd  2 CTAs: zero-padded (or, for the fold modes, mirror-extended) inputs -> real FFT -> packed spectra
 //   k_spec_inv  1 CTA : scaled per-bin product (DC and Nyquist as two real products) -> inverse real FFT
 //                       -> the edge-mode arrangement (copy / wrap-add / offset copy) straight into the output
@@ -17,9 +19,28 @@
 
 using namespace hb;
 
+namespace hb
+{
+int cfft_planes(int dtype, const void *re_in, const void *im_in, void *re_out, void *im_out, int log2n, int swap, size_t batch, size_t stride,
+                const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs);          // hb_fft.cu
+}
+
 namespace
 {
 enum { MODE_LINEAR = 0, MODE_WRAP = 1, MODE_WRAP_CENTRE = 2, MODE_FOLD = 3, MODE_FOLD_REPEAT = 4 };
+
+// out[i] = sum over terms t with lo <= i < hi of L(src + i - lo), L = the result of the inverse transform (0 at or past
+// the FFT size).  The reference's copy() calls never overlap and its zero() ranges are the gaps, so "assign" and "add"
+// coincide and a gap reads as 0.
+struct Arrange
+{
+    uint32_t n;
+    uint32_t lo[5], hi[5], src[5];
+    uint32_t end_rel[5];       // the source index counts back from the end of the transform (negative lags)
+    uint32_t result;           // samples written
+    uint32_t fft_ref;          // the reference's transform size: a read at or past it contributes 0
+    uint32_t shift;            // this library's transform size minus fft_ref (non-zero only below 4 points)
+};
 
 struct SpecGeom
 {
@@ -29,26 +50,52 @@ struct SpecGeom
     uint32_t fold_size;        // mirrored samples each side of the longer input (fold modes)
     int mode;
     int first_is_big;          // n1 >= n2
+    int op;                    // 0 convolve, 1 correlate
+    Arrange arr;
 };
 
-// sample j of the FFT input of operand `which` (0: first / extended operand, 1: second)
+template <class F>
+__device__ __forceinline__ auto arrange_eval(const Arrange &a, uint32_t i, F lin) -> decltype(lin(0u))
+{
+    decltype(lin(0u)) v = 0;
+    for (uint32_t t = 0; t < a.n; t++)
+        if (i >= a.lo[t] && i < a.hi[t])
+        {
+            const uint32_t j = a.src[t] + (i - a.lo[t]);
+            if (j < a.fft_ref) v += lin(a.end_rel[t] ? j + a.shift : j);
+        }
+    return v;
+}
+
+// sample j of the FFT input of input `which` (0: in1, 1: in2): zero-padded, and for the fold modes the longer input
+// mirror-extended by fold_size on both sides (SpectralProcessor.hpp:356-372, 624-641)
+template <class T>
+__device__ __forceinline__ T fetch_padded(const T *__restrict__ in, uint32_t n, uint32_t size, uint32_t fold_size, uint32_t off, uint32_t j)
+{
+    // plane of `n` samples padded with zeros to `size`, then extended: [mirror | plane | mirror | zeros]
+    uint32_t k;
+    if (j < fold_size) k = off + fold_size - 1 - j;
+    else if (j < fold_size + size) k = j - fold_size;
+    else if (j < size + 2 * fold_size) k = size - off - 1 - (j - fold_size - size);
+    else return T(0);
+    return k < n ? in[k] : T(0);
+}
+
 template <class T>
 __device__ __forceinline__ T spec_fetch(const SpecGeom &g, const T *__restrict__ in1, const T *__restrict__ in2, int which, uint32_t j)
 {
     const bool fold = g.mode == MODE_FOLD || g.mode == MODE_FOLD_REPEAT;
-    if (!fold)
-    {
-        if (which == 0) return j < g.n1 ? in1[j] : T(0);
-        return j < g.n2 ? in2[j] : T(0);
-    }
-    // SpectralProcessor.hpp:624-641: the longer input is mirror-extended by fold_size on both sides
-    const T *big = g.first_is_big ? in1 : in2, *small = g.first_is_big ? in2 : in1;
-    if (which == 1) return j < g.mn ? small[j] : T(0);
-    const uint32_t off = g.mode == MODE_FOLD_REPEAT ? 0 : 1;
-    if (j < g.fold_size) return big[off + g.fold_size - 1 - j];
-    if (j < g.fold_size + g.mx) return big[j - g.fold_size];
-    if (j < g.mx + 2 * g.fold_size) return big[g.mx - off - 1 - (j - g.fold_size - g.mx)];
-    return T(0);
+    const bool is_big = (which == 0) == (g.first_is_big != 0);
+    const uint32_t n = which ? g.n2 : g.n1;
+    return fetch_padded<T>(which ? in2 : in1, n, n, (fold && is_big) ? g.fold_size : 0u, g.mode == MODE_FOLD_REPEAT ? 0u : 1u, j);
+}
+
+// scaled per-bin product of SpectralFunctions.hpp:265-281: a * b (convolve) or a * conj(b) (correlate)
+template <class T>
+__device__ __forceinline__ Cx<T> spec_op(int op, T scale, const Cx<T> a, const Cx<T> b)
+{
+    return op ? cx<T>(scale * (a.x * b.x + a.y * b.y), scale * (a.y * b.x - a.x * b.y))
+              : cx<T>(scale * (a.x * b.x - a.y * b.y), scale * (a.y * b.x + a.x * b.y));
 }
 
 template <class T, int EPT>
@@ -81,10 +128,8 @@ __global__ void __launch_bounds__(512) k_spec_inv(const SpecGeom g, const Cx<T> 
     for (uint32_t k = threadIdx.x; k < M; k += blockDim.x)
     {
         const Cx<T> a = A[k], b = B[k];
-        // SpectralFunctions.hpp:63-84: bin 0 carries DC and Nyquist, both real; :274-281 for the rest
-        Cx<T> r = k ? cx<T>(scale * (a.x * b.x - a.y * b.y), scale * (a.y * b.x + a.x * b.y))
-                    : cx<T>(scale * (a.x * b.x), scale * (a.y * b.y));
-        s[sidx<HB_PADSH>(k)] = r;
+        // SpectralFunctions.hpp:63-84: bin 0 carries DC and Nyquist, both real (for either operation); :265-281 for the rest
+        s[sidx<HB_PADSH>(k)] = k ? spec_op<T>(g.op, scale, a, b) : cx<T>(scale * (a.x * b.x), scale * (a.y * b.y));
     }
     __syncthreads();
     block_real_split<T, EPT, HB_PADSH>(s, M, (int) g.log2n, true, tw, tw_log2);
@@ -98,34 +143,7 @@ __global__ void __launch_bounds__(512) k_spec_inv(const SpecGeom g, const Cx<T> 
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, tw, tw_log2);
     // time sample i of the linear result: even samples sit in .y, odd ones in .x (planes exchanged)
     auto lin = [&](uint32_t i) -> T { const Cx<T> v = s[sidx<HB_PADSH>(i >> 1)]; return (i & 1) ? v.x : v.y; };
-    const uint32_t min_m1 = g.mn - 1;
-    const uint32_t result = g.mode == MODE_LINEAR ? g.n1 + g.n2 - 1 : g.mx;
-    for (uint32_t i = threadIdx.x; i < result; i += blockDim.x)
-    {
-        T v;
-        switch (g.mode)
-        {
-            case MODE_LINEAR:
-                v = lin(i);
-                break;
-            case MODE_WRAP:                                             // copy + wrap (SpectralProcessor.hpp:421-435,445-481)
-                v = lin(i);
-                if (i < min_m1) v += lin(g.mx + i);
-                break;
-            case MODE_WRAP_CENTRE:
-            {
-                const uint32_t wrapped = min_m1 >> 1;
-                v = lin(wrapped + i);
-                if (i < min_m1 - wrapped) v += lin(g.mx + wrapped + i);
-                if (i >= g.mx - wrapped) v += lin(i - (g.mx - wrapped));
-                break;
-            }
-            default:                                                    // Fold / FoldRepeat: offset copy
-                v = lin(min_m1 + i);
-                break;
-        }
-        out[i] = v;
-    }
+    for (uint32_t i = threadIdx.x; i < g.arr.result; i += blockDim.x) out[i] = arrange_eval(g.arr, i, lin);
 }
 
 // ---- sizes above the single-CTA limit: the same three stages over global memory (hb_fft_big.cuh) ----
@@ -146,8 +164,7 @@ __global__ void k_spec_big_mul(const SpecGeom g, Cx<T> *__restrict__ z)
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x)
     {
         const Cx<T> a = z[k], b = z[size_t(M) + k];
-        z[k] = k ? cx<T>(scale * (a.x * b.x - a.y * b.y), scale * (a.y * b.x + a.x * b.y))
-                 : cx<T>(scale * (a.x * b.x), scale * (a.y * b.y));
+        z[k] = k ? spec_op<T>(g.op, scale, a, b) : cx<T>(scale * (a.x * b.x), scale * (a.y * b.y));
     }
 }
 
@@ -156,34 +173,56 @@ template <class T>
 __global__ void k_spec_big_arrange(const SpecGeom g, const Cx<T> *__restrict__ z, T *__restrict__ out)
 {
     auto lin = [&](uint32_t i) -> T { const Cx<T> v = z[i >> 1]; return (i & 1) ? v.x : v.y; };
-    const uint32_t min_m1 = g.mn - 1;
-    const uint32_t result = g.mode == MODE_LINEAR ? g.n1 + g.n2 - 1 : g.mx;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < result; i += gridDim.x * blockDim.x)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.arr.result; i += gridDim.x * blockDim.x)
+        out[i] = arrange_eval(g.arr, i, lin);
+}
+
+// ---- complex inputs: split planes in global memory, the transforms through hb::cfft_planes (single CTA or four-step) ----
+// planes of operand `which` (blockIdx.y): [re | im], each padded to the FFT size; input planes may be shorter than the
+// operand (or absent), copy_fold_zero of SpectralProcessor.hpp:386-399
+template <class T>
+__global__ void k_cspec_pack(const SpecGeom g, const T *__restrict__ r1, uint32_t nr1, const T *__restrict__ i1, uint32_t ni1,
+                             const T *__restrict__ r2, uint32_t nr2, const T *__restrict__ i2, uint32_t ni2, T *__restrict__ planes)
+{
+    const uint32_t N = 1u << g.log2n;
+    const int which = blockIdx.y;
+    const bool fold = g.mode == MODE_FOLD || g.mode == MODE_FOLD_REPEAT;
+    const bool is_big = (which == 0) == (g.first_is_big != 0);
+    const uint32_t fs = (fold && is_big) ? g.fold_size : 0u, off = g.mode == MODE_FOLD_REPEAT ? 0u : 1u;
+    const uint32_t size = which ? g.n2 : g.n1;
+    const T *re = which ? r2 : r1, *im = which ? i2 : i1;
+    const uint32_t nre = which ? nr2 : nr1, nim = which ? ni2 : ni1;
+    T *pr = planes + size_t(which) * N, *pi = planes + size_t(2 + which) * N;      // layout: [re0 | re1 | im0 | im1]
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
     {
-        T v;
-        switch (g.mode)
-        {
-            case MODE_LINEAR:
-                v = lin(i);
-                break;
-            case MODE_WRAP:
-                v = lin(i);
-                if (i < min_m1) v += lin(g.mx + i);
-                break;
-            case MODE_WRAP_CENTRE:
-            {
-                const uint32_t wrapped = min_m1 >> 1;
-                v = lin(wrapped + i);
-                if (i < min_m1 - wrapped) v += lin(g.mx + wrapped + i);
-                if (i >= g.mx - wrapped) v += lin(i - (g.mx - wrapped));
-                break;
-            }
-            default:
-                v = lin(min_m1 + i);
-                break;
-        }
-        out[i] = v;
+        pr[j] = fetch_padded<T>(re, nre, size, fs, off, j);
+        pi[j] = fetch_padded<T>(im, nim, size, fs, off, j);
     }
+}
+
+// operand 0 <- scale * op(operand 0, operand 1) over all N bins (complex_operation, SpectralFunctions.hpp:49-61)
+template <class T>
+__global__ void k_cspec_mul(const SpecGeom g, T *__restrict__ planes)
+{
+    const uint32_t N = 1u << g.log2n;
+    const T scale = T(1) / T(size_t(1) << g.log2n);                               // SpectralProcessor.hpp:572
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x)
+    {
+        const Cx<T> a = cx<T>(planes[k], planes[size_t(2) * N + k]), b = cx<T>(planes[size_t(N) + k], planes[size_t(3) * N + k]);
+        const Cx<T> r = spec_op<T>(g.op, scale, a, b);
+        planes[k] = r.x;
+        planes[size_t(2) * N + k] = r.y;
+    }
+}
+
+template <class T>
+__global__ void k_cspec_arrange(const SpecGeom g, const T *__restrict__ planes, T *__restrict__ out)
+{
+    const uint32_t N = 1u << g.log2n;
+    const T *src = planes + size_t(blockIdx.y) * 2 * N;                            // plane 0 = re, plane 1 = im of operand 0
+    T *dst = out + size_t(blockIdx.y) * g.arr.result;
+    auto lin = [&](uint32_t i) -> T { return src[i]; };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.arr.result; i += gridDim.x * blockDim.x) dst[i] = arrange_eval(g.arr, i, lin);
 }
 
 uint32_t ceil_log2(uintptr_t value)
@@ -208,6 +247,7 @@ struct hb_spectral
     int tw_log2 = 1;
     cudaStream_t stream = nullptr;
     DevBuf d_in1, d_in2, d_spec, d_out;
+    DevBuf d_in3, d_in4, d_planes;      // complex inputs: imaginary planes and the [re0 | re1 | im0 | im1] work array
     BigScratch big;
     std::mutex lock;
 };
@@ -250,8 +290,66 @@ int set_max(hb_spectral *s, uintptr_t max_fft_size)
     return HB_OK;
 }
 
+// The reference's arrange_convolve (SpectralProcessor.hpp:445-481) / arrange_correlate (:483-538) as terms.  `copy(out,
+// spec, o, src, size)` is a term as is; `wrap(out, spec, o, third, size)` reads from `third - size` in the real
+// overloads (:437-443, an end) and from `third` in the Split overloads (:421-427, an offset): complex_index selects.
+Arrange build_arrange(uintptr_t n1, uintptr_t n2, uintptr_t fft, uintptr_t fft_actual, int mode, int op, bool complex_index)
+{
+    Arrange a;
+    memset(&a, 0, sizeof(a));
+    a.fft_ref = (uint32_t) fft;
+    a.shift = (uint32_t) (fft_actual - fft);
+    const uintptr_t mn = std::min(n1, n2), mx = std::max(n1, n2), linear = n1 + n2 - 1, min_m1 = mn - 1, size2_m1 = n2 - 1;
+    // from_end: `src` was derived from the transform size (the negative lags of a correlation sit at its end)
+    auto copy = [&](uintptr_t o, uintptr_t src, uintptr_t size, bool from_end)
+    {
+        if (!size) return;
+        a.lo[a.n] = (uint32_t) o; a.hi[a.n] = (uint32_t) (o + size); a.src[a.n] = (uint32_t) src; a.end_rel[a.n] = from_end ? 1u : 0u; a.n++;
+    };
+    auto wrap = [&](uintptr_t o, uintptr_t third, uintptr_t size, bool from_end) { copy(o, complex_index ? third : third - size, size, from_end); };
+    a.result = (uint32_t) (mode == MODE_LINEAR ? linear : mx);
+    if (op == 0)
+    {
+        switch (mode)
+        {
+            case MODE_LINEAR: copy(0, 0, linear, false); break;
+            case MODE_WRAP: copy(0, 0, mx, false); wrap(0, linear, min_m1, false); break;
+            case MODE_WRAP_CENTRE:
+            {
+                const uintptr_t wrapped = min_m1 >> 1;
+                copy(0, wrapped, mx, false);
+                wrap(0, linear, min_m1 - wrapped, false);
+                wrap(mx - wrapped, wrapped, wrapped, false);
+                break;
+            }
+            default: copy(0, min_m1, mx, false); break;
+        }
+        return a;
+    }
+    switch (mode)
+    {
+        case MODE_LINEAR: copy(0, 0, n1, false); copy(n1, fft - size2_m1, size2_m1, true); break;
+        case MODE_WRAP: copy(0, 0, n1, false); wrap(mx - size2_m1, fft, size2_m1, true); break;       // zero(n1, n2) = the gap
+        case MODE_WRAP_CENTRE:
+        {
+            const uintptr_t wrapped1 = min_m1 >> 1, wrapped2 = std::min(size2_m1, mx - wrapped1), wrapped3 = size2_m1 - wrapped2;
+            const uintptr_t offset = wrapped3 ? 0 : mx - (size2_m1 + wrapped1);
+            copy(0, wrapped1, n1 - wrapped1, false);
+            copy(mx - wrapped1, 0, wrapped1, false);
+            wrap(offset, fft, wrapped2, true);
+            wrap(mx - wrapped3, fft - wrapped2, wrapped3, true);
+            break;
+        }
+        default:
+            if (n1 >= n2) copy(0, 0, mx, false);
+            else { copy(0, 0, 1, false); copy(1, fft - (mx - 1), mx - 1, true); }
+            break;
+    }
+    return a;
+}
+
 template <class T>
-int convolve(hb_spectral *s, T *output, const T *in1, uintptr_t n1, const T *in2, uintptr_t n2, int mode, uintptr_t *written)
+int binary_real(hb_spectral *s, T *output, const T *in1, uintptr_t n1, const T *in2, uintptr_t n2, int mode, int op, uintptr_t *written)
 {
     Sizes z;
     if (written) *written = 0;
@@ -273,6 +371,8 @@ int convolve(hb_spectral *s, T *output, const T *in1, uintptr_t n1, const T *in2
     SpecGeom g;
     g.log2n = log2n; g.n1 = (uint32_t) n1; g.n2 = (uint32_t) n2; g.mn = (uint32_t) z.mn; g.mx = (uint32_t) z.mx;
     g.fold_size = (uint32_t) z.fold_size; g.mode = mode; g.first_is_big = n1 >= n2;
+    g.op = op;
+    g.arr = build_arrange(n1, n2, uintptr_t(1) << z.log2n, uintptr_t(1) << log2n, mode, op, false);
     const size_t smem = size_t(padded_elems<HB_PADSH>((uint32_t) M)) * sizeof(Cx<T>);
     const Cx<T> *tw = (const Cx<T> *) s->tw;
     if ((int) log2m > SmemFftLimit<T>::max_log2m)
@@ -305,6 +405,88 @@ int convolve(hb_spectral *s, T *output, const T *in1, uintptr_t n1, const T *in2
     if (written) *written = z.result;
     return HB_OK;
 }
+// complex inputs (SpectralProcessor.hpp:559-614): every plane has its own length, a length of 0 = absent
+template <class T>
+int binary_complex(hb_spectral *s, T *r_out, T *i_out, const T *r1, uintptr_t nr1, const T *i1, uintptr_t ni1,
+                   const T *r2, uintptr_t nr2, const T *i2, uintptr_t ni2, int mode, int op, uintptr_t *written)
+{
+    const uintptr_t n1 = std::max(nr1, ni1), n2 = std::max(nr2, ni2);
+    Sizes z;
+    if (written) *written = 0;
+    if (!plan_sizes(n1, n2, mode, s->max_log2, z)) return HB_OK;
+    if (n1 == 1 && n2 == 1)                                                     // :585-590 (the plain product for both operations)
+    {
+        const T a = nr1 ? r1[0] : T(0), b = ni1 ? i1[0] : T(0), c = nr2 ? r2[0] : T(0), d = ni2 ? i2[0] : T(0);
+        r_out[0] = a * c - b * d;
+        i_out[0] = a * d + b * c;
+        if (written) *written = 1;
+        return HB_OK;
+    }
+    const uint32_t log2n = z.log2n < 1 ? 1 : z.log2n;
+    const size_t N = size_t(1) << log2n;
+    int rc;
+    if ((rc = s->d_in1.ensure(std::max<size_t>(nr1, 1) * sizeof(T))) || (rc = s->d_in3.ensure(std::max<size_t>(ni1, 1) * sizeof(T))) ||
+        (rc = s->d_in2.ensure(std::max<size_t>(nr2, 1) * sizeof(T))) || (rc = s->d_in4.ensure(std::max<size_t>(ni2, 1) * sizeof(T))) ||
+        (rc = s->d_planes.ensure(4 * N * sizeof(T))) || (rc = s->d_out.ensure(2 * z.result * sizeof(T)))) return rc;
+    if (nr1) HB_CUDA(cudaMemcpyAsync(s->d_in1.p, r1, nr1 * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    if (ni1) HB_CUDA(cudaMemcpyAsync(s->d_in3.p, i1, ni1 * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    if (nr2) HB_CUDA(cudaMemcpyAsync(s->d_in2.p, r2, nr2 * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    if (ni2) HB_CUDA(cudaMemcpyAsync(s->d_in4.p, i2, ni2 * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    SpecGeom g;
+    g.log2n = log2n; g.n1 = (uint32_t) n1; g.n2 = (uint32_t) n2; g.mn = (uint32_t) z.mn; g.mx = (uint32_t) z.mx;
+    g.fold_size = (uint32_t) z.fold_size; g.mode = mode; g.first_is_big = n1 >= n2;
+    g.op = op;
+    g.arr = build_arrange(n1, n2, uintptr_t(1) << z.log2n, uintptr_t(1) << log2n, mode, op, true);
+    T *planes = (T *) s->d_planes.p;
+    const unsigned blocks = (unsigned) std::min<size_t>((N + 255) / 256, 1024);
+    k_cspec_pack<T><<<dim3(blocks, 2), 256, 0, s->stream>>>(g, (const T *) s->d_in1.p, (uint32_t) nr1, (const T *) s->d_in3.p, (uint32_t) ni1,
+                                                            (const T *) s->d_in2.p, (uint32_t) nr2, (const T *) s->d_in4.p, (uint32_t) ni2, planes);
+    HB_LAUNCH_CHECK();
+    // both operands forward in one batched launch (planes N apart), product into operand 0, unscaled inverse of operand 0
+    if ((rc = cfft_planes(s->dtype, planes, planes + 2 * N, planes, planes + 2 * N, (int) log2n, 0, 2, N, s->tw, s->tw_log2, s->stream, &s->big))) return rc;
+    k_cspec_mul<T><<<blocks, 256, 0, s->stream>>>(g, planes);
+    HB_LAUNCH_CHECK();
+    if ((rc = cfft_planes(s->dtype, planes, planes + 2 * N, planes, planes + 2 * N, (int) log2n, 1, 1, N, s->tw, s->tw_log2, s->stream, &s->big))) return rc;
+    k_cspec_arrange<T><<<dim3((unsigned) std::min<size_t>((z.result + 255) / 256, 1024), 2), 256, 0, s->stream>>>(g, planes, (T *) s->d_out.p);
+    HB_LAUNCH_CHECK();
+    HB_CUDA(cudaMemcpyAsync(r_out, s->d_out.p, z.result * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaMemcpyAsync(i_out, (const T *) s->d_out.p + z.result, z.result * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaStreamSynchronize(s->stream));
+    if (written) *written = z.result;
+    return HB_OK;
+}
+
+int real_entry(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2, int mode, int op, uintptr_t *written, const char *who)
+{
+    if (!s || mode < MODE_LINEAR || mode > MODE_FOLD_REPEAT || ((!output || !in1 || !in2) && n1 && n2))
+    {
+        set_error("%s: bad argument", who);
+        return HB_ERR_BAD_ARG;
+    }
+    std::lock_guard<std::mutex> g(s->lock);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return s->dtype == HB_F64 ? binary_real<double>(s, (double *) output, (const double *) in1, n1, (const double *) in2, n2, mode, op, written)
+                              : binary_real<float>(s, (float *) output, (const float *) in1, n1, (const float *) in2, n2, mode, op, written);
+}
+
+int complex_entry(hb_spectral *s, void *r_out, void *i_out, const void *r1, uintptr_t nr1, const void *i1, uintptr_t ni1,
+                  const void *r2, uintptr_t nr2, const void *i2, uintptr_t ni2, int mode, int op, uintptr_t *written, const char *who)
+{
+    const bool some = (nr1 || ni1) && (nr2 || ni2);
+    if (!s || mode < MODE_LINEAR || mode > MODE_FOLD_REPEAT || (some && (!r_out || !i_out)) || (nr1 && !r1) || (ni1 && !i1) || (nr2 && !r2) || (ni2 && !i2))
+    {
+        set_error("%s: bad argument", who);
+        return HB_ERR_BAD_ARG;
+    }
+    std::lock_guard<std::mutex> g(s->lock);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return s->dtype == HB_F64 ? binary_complex<double>(s, (double *) r_out, (double *) i_out, (const double *) r1, nr1, (const double *) i1, ni1,
+                                                       (const double *) r2, nr2, (const double *) i2, ni2, mode, op, written)
+                              : binary_complex<float>(s, (float *) r_out, (float *) i_out, (const float *) r1, nr1, (const float *) i1, ni1,
+                                                      (const float *) r2, nr2, (const float *) i2, ni2, mode, op, written);
+}
 } // namespace
 
 extern "C" int hb_spectral_create(hb_spectral **out, int dtype, uintptr_t max_fft_size, int device)
@@ -328,6 +510,7 @@ extern "C" void hb_spectral_destroy(hb_spectral *s)
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     s->d_in1.release(); s->d_in2.release(); s->d_spec.release(); s->d_out.release();
+    s->d_in3.release(); s->d_in4.release(); s->d_planes.release();
     s->big.release();
     cudaFree(s->tw);
     cudaStreamDestroy(s->stream);
@@ -354,14 +537,22 @@ extern "C" uintptr_t hb_spectral_convolved_size(const hb_spectral *s, uintptr_t 
 
 extern "C" int hb_spectral_convolve(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2, int mode, uintptr_t *written)
 {
-    if (!s || mode < MODE_LINEAR || mode > MODE_FOLD_REPEAT || ((!output || !in1 || !in2) && n1 && n2))
-    {
-        set_error("hb_spectral_convolve: bad argument");
-        return HB_ERR_BAD_ARG;
-    }
-    std::lock_guard<std::mutex> g(s->lock);
-    int rc = use_device(s->device);
-    if (rc) return rc;
-    return s->dtype == HB_F64 ? convolve<double>(s, (double *) output, (const double *) in1, n1, (const double *) in2, n2, mode, written)
-                              : convolve<float>(s, (float *) output, (const float *) in1, n1, (const float *) in2, n2, mode, written);
+    return real_entry(s, output, in1, n1, in2, n2, mode, 0, written, "hb_spectral_convolve");
+}
+
+extern "C" int hb_spectral_correlate(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2, int mode, uintptr_t *written)
+{
+    return real_entry(s, output, in1, n1, in2, n2, mode, 1, written, "hb_spectral_correlate");
+}
+
+extern "C" int hb_spectral_convolve_complex(hb_spectral *s, void *r_out, void *i_out, const void *r_in1, uintptr_t nr1, const void *i_in1, uintptr_t ni1,
+                                            const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written)
+{
+    return complex_entry(s, r_out, i_out, r_in1, nr1, i_in1, ni1, r_in2, nr2, i_in2, ni2, mode, 0, written, "hb_spectral_convolve_complex");
+}
+
+extern "C" int hb_spectral_correlate_complex(hb_spectral *s, void *r_out, void *i_out, const void *r_in1, uintptr_t nr1, const void *i_in1, uintptr_t ni1,
+                                             const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written)
+{
+    return complex_entry(s, r_out, i_out, r_in1, nr1, i_in1, ni1, r_in2, nr2, i_in2, ni2, mode, 1, written, "hb_spectral_correlate_complex");
 }

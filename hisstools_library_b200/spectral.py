@@ -1,10 +1,11 @@
-"""spectral_processor -- one-shot FFT convolution of two real buffers on the B200.
+"""spectral_processor -- one-shot FFT convolution and correlation on the B200.
 
-Mirror of the convolution part of the reference's spectral_processor<T> (SpectralProcessor.hpp:11-683):
-same class name, `EdgeMode` values, `convolve(output, in1, in2, mode)`, `convolved_size`,
-`set_max_fft_size` / `max_fft_size`.  correlate / change_phase are outside the convolution path
-(SURVEY 8f-4).  The transforms, the per-bin product and the edge-mode arrangement run as CUDA kernels
-behind hb_spectral_* of include/hisstools_b200.h.
+Mirror of the reference's spectral_processor<T> (SpectralProcessor.hpp:11-683): same class name, `EdgeMode`
+values, `convolve` / `correlate` for real inputs (output, in1, in2, mode) and for complex inputs
+(r_out, i_out, r_in1, i_in1, r_in2, i_in2, mode), `convolved_size` / `correlated_size`,
+`set_max_fft_size` / `max_fft_size`.  change_phase is not provided.  The transforms, the
+per-bin product and the edge-mode arrangement run as CUDA kernels behind hb_spectral_* of
+include/hisstools_b200.h.
 """
 import ctypes as C
 import enum
@@ -54,15 +55,43 @@ class spectral_processor:
     def convolved_size(self, size1, size2, mode):
         return int(_abi.lib().hb_spectral_convolved_size(self._h, int(size1), int(size2), int(mode)))
 
-    def convolve(self, output, in1, in2, mode=EdgeMode.Linear):
-        """output[:convolved_size] = in1 * in2 under `mode`; returns the number of samples written
-        (0: nothing done -- empty input or FFT above the maximum, as the reference)."""
+    correlated_size = convolved_size        # SpectralProcessor.hpp:215-218
+
+    def _check_out(self, out, need):
+        if out.dtype != self.dtype or not out.flags["C_CONTIGUOUS"] or out.size < need:
+            raise ValueError("output must be a contiguous %s array of at least %d samples" % (self.dtype, need))
+
+    def _real(self, fn, output, in1, in2, mode):
         in1 = np.ascontiguousarray(in1, self.dtype)
         in2 = np.ascontiguousarray(in2, self.dtype)
-        need = self.convolved_size(in1.size, in2.size, mode)
-        if output.dtype != self.dtype or not output.flags["C_CONTIGUOUS"] or output.size < need:
-            raise ValueError("output must be a contiguous %s array of at least %d samples" % (self.dtype, need))
+        self._check_out(output, self.convolved_size(in1.size, in2.size, mode))
         written = C.c_size_t(0)
-        _abi.check(_abi.lib().hb_spectral_convolve(self._h, output.ctypes.data_as(C.c_void_p), in1.ctypes.data_as(C.c_void_p), in1.size,
-                                                   in2.ctypes.data_as(C.c_void_p), in2.size, int(mode), C.byref(written)))
+        _abi.check(fn(self._h, output.ctypes.data_as(C.c_void_p), in1.ctypes.data_as(C.c_void_p), in1.size,
+                      in2.ctypes.data_as(C.c_void_p), in2.size, int(mode), C.byref(written)))
         return int(written.value)
+
+    def _complex(self, fn, r_out, i_out, planes, mode):
+        planes = [np.zeros(0, self.dtype) if p is None else np.ascontiguousarray(p, self.dtype) for p in planes]
+        need = self.convolved_size(max(planes[0].size, planes[1].size), max(planes[2].size, planes[3].size), mode)
+        self._check_out(r_out, need)
+        self._check_out(i_out, need)
+        written = C.c_size_t(0)
+        args = []
+        for p in planes:
+            args += [p.ctypes.data_as(C.c_void_p) if p.size else None, p.size]
+        _abi.check(fn(self._h, r_out.ctypes.data_as(C.c_void_p), i_out.ctypes.data_as(C.c_void_p), *args, int(mode), C.byref(written)))
+        return int(written.value)
+
+    def convolve(self, *args):
+        """convolve(output, in1, in2, mode) for real inputs or convolve(r_out, i_out, r_in1, i_in1, r_in2, i_in2, mode) for
+        complex ones (a missing plane: None), SpectralProcessor.hpp:164-172.  Returns the number of samples written
+        (0: nothing done -- empty input or FFT above the maximum, as the reference)."""
+        if len(args) in (3, 4):
+            return self._real(_abi.lib().hb_spectral_convolve, args[0], args[1], args[2], args[3] if len(args) == 4 else EdgeMode.Linear)
+        return self._complex(_abi.lib().hb_spectral_convolve_complex, args[0], args[1], args[2:6], args[6])
+
+    def correlate(self, *args):
+        """correlate(output, in1, in2, mode) / correlate(r_out, i_out, r_in1, i_in1, r_in2, i_in2, mode), SpectralProcessor.hpp:176-184."""
+        if len(args) in (3, 4):
+            return self._real(_abi.lib().hb_spectral_correlate, args[0], args[1], args[2], args[3] if len(args) == 4 else EdgeMode.Linear)
+        return self._complex(_abi.lib().hb_spectral_correlate_complex, args[0], args[1], args[2:6], args[6])

@@ -1,9 +1,9 @@
-// SpectralProcessor.hpp -- B200 drop-in for the convolution part of the reference's
-// spectral_processor<T> (SpectralProcessor.hpp:11-683): convolve(T*, in_ptr, in_ptr, EdgeMode),
-// convolved_size, set_max_fft_size / max_fft_size.  The transforms, the per-bin product
-// (SpectralFunctions.hpp:63-84,274-281) and the edge-mode arrangement (:445-481) run on the GPU through
-// hb_spectral_* of hisstools_b200.h.  correlate / change_phase / the complex-input overloads are not
-// part of the convolution path and are not provided.
+// SpectralProcessor.hpp -- B200 drop-in for the convolution / correlation part of the reference's
+// spectral_processor<T> (SpectralProcessor.hpp:11-683): convolve and correlate for real inputs (T*, in_ptr, in_ptr,
+// EdgeMode) and complex inputs (T*, T*, in_ptr x 4, EdgeMode), convolved_size / correlated_size, set_max_fft_size /
+// max_fft_size.  The transforms, the per-bin products (SpectralFunctions.hpp:49-84, 265-281) and the edge-mode
+// arrangements (:445-538) run on the GPU through hb_spectral_* of hisstools_b200.h.  change_phase and the raw
+// fft / rfft members are not provided.
 #ifndef HISSTOOLS_B200_SPECTRALPROCESSOR_HPP
 #define HISSTOOLS_B200_SPECTRALPROCESSOR_HPP
 
@@ -52,10 +52,29 @@ public:
         hisstools_b200_detail::check(hb_spectral_convolve(m_handle, output, in1.m_ptr, in1.m_size, in2.m_ptr, in2.m_size, static_cast<int>(mode), nullptr));
     }
 
+    void convolve(T *r_out, T *i_out, in_ptr r_in1, in_ptr i_in1, in_ptr r_in2, in_ptr i_in2, EdgeMode mode)
+    {
+        hisstools_b200_detail::check(hb_spectral_convolve_complex(m_handle, r_out, i_out, r_in1.m_ptr, r_in1.m_size, i_in1.m_ptr, i_in1.m_size,
+                                                                  r_in2.m_ptr, r_in2.m_size, i_in2.m_ptr, i_in2.m_size, static_cast<int>(mode), nullptr));
+    }
+
+    void correlate(T *output, in_ptr in1, in_ptr in2, EdgeMode mode)
+    {
+        hisstools_b200_detail::check(hb_spectral_correlate(m_handle, output, in1.m_ptr, in1.m_size, in2.m_ptr, in2.m_size, static_cast<int>(mode), nullptr));
+    }
+
+    void correlate(T *r_out, T *i_out, in_ptr r_in1, in_ptr i_in1, in_ptr r_in2, in_ptr i_in2, EdgeMode mode)
+    {
+        hisstools_b200_detail::check(hb_spectral_correlate_complex(m_handle, r_out, i_out, r_in1.m_ptr, r_in1.m_size, i_in1.m_ptr, i_in1.m_size,
+                                                                   r_in2.m_ptr, r_in2.m_size, i_in2.m_ptr, i_in2.m_size, static_cast<int>(mode), nullptr));
+    }
+
     uintptr_t convolved_size(uintptr_t size1, uintptr_t size2, EdgeMode mode) const
     {
         return hb_spectral_convolved_size(m_handle, size1, size2, static_cast<int>(mode));
     }
+
+    uintptr_t correlated_size(uintptr_t size1, uintptr_t size2, EdgeMode mode) const { return convolved_size(size1, size2, mode); }
 
 private:
 

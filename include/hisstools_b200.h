@@ -237,9 +237,10 @@ hb_conv *hb_matrix_part(hb_matrix *m, uint32_t index);
 uint32_t hb_matrix_head_taps(const hb_matrix *m);
 
 /* ---------------------------------------------------------------------------------------------
- * One-shot FFT convolution of two real buffers -- replaces spectral_processor<T>::convolve(T *output,
+ * One-shot FFT convolution / correlation of two buffers -- replaces spectral_processor<T>::convolve(T *output,
  * in_ptr in1, in_ptr in2, EdgeMode mode) (SpectralProcessor.hpp:169-172, 616-674) with its per-bin
- * product ir_convolve_real (SpectralFunctions.hpp:420-424, 63-84, 274-281).
+ * product ir_convolve_real (SpectralFunctions.hpp:420-424, 63-84, 274-281), and its neighbours correlate and the
+ * complex-input overloads (below).
  * mode: 0 Linear (n1+n2-1 samples), 1 Wrap, 2 WrapCentre, 3 Fold, 4 FoldRepeat (max(n1,n2) samples;
  * SpectralProcessor.hpp:22, 445-481).  Host pointers of the handle's dtype.
  * ------------------------------------------------------------------------------------------- */
@@ -257,6 +258,20 @@ uintptr_t hb_spectral_convolved_size(const hb_spectral *s, uintptr_t n1, uintptr
  * maximum -- the reference silently returns, SpectralProcessor.hpp:651-652) */
 int hb_spectral_convolve(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2,
                          int mode, uintptr_t *written);
+/* correlate(T *output, in_ptr in1, in_ptr in2, EdgeMode): SpectralProcessor.hpp:181-184, 483-538 (arrange_correlate),
+ * SpectralFunctions.hpp:265-272, 432-436.  Same sizes as convolve (correlated_size = convolved_size, :215-218). */
+int hb_spectral_correlate(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2,
+                          int mode, uintptr_t *written);
+/* complex inputs -- convolve / correlate(T *r_out, T *i_out, in_ptr r_in1, in_ptr i_in1, in_ptr r_in2, in_ptr i_in2,
+ * EdgeMode): SpectralProcessor.hpp:164-167, 176-179, 559-614.  Every plane has its own length (0 = absent plane); the
+ * operand length is the longer of its planes.  The reference's Split overload of wrap() takes an offset where its
+ * callers pass an end (:421-427 against :437-443), so its Wrap / WrapCentre modes add samples read at or past the end
+ * of the transform (unrelated temporary memory); reads past the transform contribute 0 here, everything else follows
+ * the reference index for index. */
+int hb_spectral_convolve_complex(hb_spectral *s, void *r_out, void *i_out, const void *r_in1, uintptr_t nr1, const void *i_in1, uintptr_t ni1,
+                                 const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written);
+int hb_spectral_correlate_complex(hb_spectral *s, void *r_out, void *i_out, const void *r_in1, uintptr_t nr1, const void *i_in1, uintptr_t ni1,
+                                  const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,8 @@ def oracle():
             sig("orc_mono_reset", None, V)
             sig("orc_mono_process", None, V, P, P, SZ, C.c_int)
             sig("orc_spectral_convolve", SZ, P, P, SZ, P, SZ, C.c_int, SZ)
+            sig("orc_spectral_binary", SZ, P, P, SZ, P, SZ, C.c_int, C.c_int, SZ)
+            sig("orc_spectral_binary_complex", SZ, P, P, P, SZ, P, SZ, P, SZ, P, SZ, C.c_int, C.c_int, SZ)
         _oracle = lib
     return _oracle
 
@@ -188,6 +190,13 @@ def ref_spectral():
         lib.ref_spectral_convolve_f32.argtypes = [c_f32p, c_f32p, SZ, c_f32p, SZ, C.c_int, SZ]
         lib.ref_spectral_convolve_f64.restype = SZ
         lib.ref_spectral_convolve_f64.argtypes = [c_f64p, c_f64p, SZ, c_f64p, SZ, C.c_int, SZ]
+        for suf, P in (("_f32", c_f32p), ("_f64", c_f64p)):
+            fn = getattr(lib, "ref_spectral_binary" + suf)
+            fn.restype = SZ
+            fn.argtypes = [P, P, SZ, P, SZ, C.c_int, C.c_int, SZ]
+            fn = getattr(lib, "ref_spectral_binary_complex" + suf)
+            fn.restype = SZ
+            fn.argtypes = [P, P, P, SZ, P, SZ, P, SZ, P, SZ, C.c_int, C.c_int, SZ]
         _ref_spec = lib
     return _ref_spec
 

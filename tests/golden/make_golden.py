@@ -142,6 +142,26 @@ def main():
                 size = getattr(rs, "ref_spectral_convolve" + suf)(ck.fptr(y), ck.fptr(a), n1, ck.fptr(b), n2, mode, 32768)
                 g["spec%s_%d_%d_m%d" % (suf, n1, n2, mode)] = y[:size]
 
+    # ---- spectral_processor::correlate (real) and the complex-input convolve / correlate --------------
+    # complex Wrap / WrapCentre read past the transform in the reference: kept out of the fixtures
+    for dtype, suf in ((np.float32, "_f32"), (np.float64, "_f64")):
+        for n1, n2 in ((1000, 300), (300, 1000), (64, 64), (7, 2), (1, 9)):
+            a, b = g["spec%s_%d_%d_a" % (suf, n1, n2)], g["spec%s_%d_%d_b" % (suf, n1, n2)]
+            for mode in range(5):
+                y = np.zeros(n1 + n2 + 8, dtype)
+                size = getattr(rs, "ref_spectral_binary" + suf)(ck.fptr(y), ck.fptr(a), n1, ck.fptr(b), n2, mode, 1, 32768)
+                g["corr%s_%d_%d_m%d" % (suf, n1, n2, mode)] = y[:size]
+            ai = rng.uniform(-1, 1, max(n1 // 2, 1)).astype(dtype)          # shorter imaginary plane
+            bi = rng.uniform(-1, 1, n2).astype(dtype)
+            g["cspec%s_%d_%d_ai" % (suf, n1, n2)] = ai
+            g["cspec%s_%d_%d_bi" % (suf, n1, n2)] = bi
+            for op in (0, 1):
+                for mode in (0, 3, 4):
+                    yr, yi = np.zeros(n1 + n2 + 8, dtype), np.zeros(n1 + n2 + 8, dtype)
+                    size = getattr(rs, "ref_spectral_binary_complex" + suf)(ck.fptr(yr), ck.fptr(yi), ck.fptr(a), n1, ck.fptr(ai), len(ai),
+                                                                            ck.fptr(b), n2, ck.fptr(bi), n2, mode, op, 32768)
+                    g["cspec%s_%d_%d_op%d_m%d" % (suf, n1, n2, op, mode)] = np.stack([yr[:size], yi[:size]])
+
     path = os.path.join(HERE, "golden.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes,", len(g), "arrays")

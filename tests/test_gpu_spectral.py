@@ -69,6 +69,63 @@ def test_against_oracle_and_direct(hb, suf):
         assert ck.rel_rms(wrap, circ) <= TOL[suf]
 
 
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("n1,n2", [(1000, 300), (300, 1000), (64, 64), (7, 2), (1, 9)])
+def test_golden_correlate_and_complex(hb, suf, n1, n2):
+    """correlate (real, five edge modes) and complex-input convolve / correlate (Linear, Fold, FoldRepeat) against the
+    fixtures made by the unmodified reference."""
+    sp = hb.spectral_processor(MAXFFT[suf], DT[suf])
+    a, b = G["spec_%s_%d_%d_a" % (suf, n1, n2)], G["spec_%s_%d_%d_b" % (suf, n1, n2)]
+    for mode in range(5):
+        want = G["corr_%s_%d_%d_m%d" % (suf, n1, n2, mode)]
+        assert sp.correlated_size(n1, n2, mode) == len(want)
+        out = np.zeros(len(want) + 3, DT[suf])
+        assert sp.correlate(out, a, b, mode) == len(want)
+        assert ck.rel_rms(out[:len(want)], want) <= TOL[suf], (suf, n1, n2, mode)
+        assert np.all(out[len(want):] == 0)
+    ai, bi = G["cspec_%s_%d_%d_ai" % (suf, n1, n2)], G["cspec_%s_%d_%d_bi" % (suf, n1, n2)]
+    for op, fn in ((0, sp.convolve), (1, sp.correlate)):
+        for mode in (0, 3, 4):
+            want = G["cspec_%s_%d_%d_op%d_m%d" % (suf, n1, n2, op, mode)]
+            size = want.shape[1]
+            r_out, i_out = np.zeros(size + 2, DT[suf]), np.zeros(size + 2, DT[suf])
+            assert fn(r_out, i_out, a, ai, b, bi, mode) == size
+            assert ck.rel_rms(np.concatenate([r_out[:size], i_out[:size]]), want.ravel()) <= TOL[suf], (suf, n1, n2, op, mode)
+            assert np.all(r_out[size:] == 0) and np.all(i_out[size:] == 0)
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_correlate_and_complex_against_oracle(hb, suf):
+    """all five edge modes, real correlate and both complex operations, against the plain-C oracle (which is pinned to the
+    reference), including sizes on the four-step path, absent planes and the single-sample special cases."""
+    dt = DT[suf]
+    lib = ck.oracle()
+    fr, fc = getattr(lib, "orc_spectral_binary_" + suf), getattr(lib, "orc_spectral_binary_complex_" + suf)
+    sp = hb.spectral_processor(MAXFFT[suf], dt)
+    rng = np.random.default_rng(77)
+    for n1, n2 in [(1, 1), (1, 2), (2, 1), (3, 5), (16, 16), (129, 64), (64, 129), (4000, 4000), (12000, 3000), (3000, 12000), (20000, 12000), (40000, 20000)]:
+        a = rng.uniform(-1, 1, n1).astype(dt)
+        b = (rng.standard_normal(n2) * np.exp(-3.0 * np.arange(n2) / n2)).astype(dt)
+        for mode in range(5):
+            want = np.zeros(n1 + n2, dt)
+            size = fr(ck.fptr(want), ck.fptr(a), n1, ck.fptr(b), n2, mode, 1, MAXFFT[suf])
+            got = np.zeros(n1 + n2, dt)
+            assert sp.correlate(got, a, b, mode) == size, (n1, n2, mode)
+            if size:
+                assert ck.rel_rms(got[:size], want[:size]) <= TOL[suf], (suf, n1, n2, mode)
+        for planes in ((n1, n1, n2, n2), (n1, n1 // 2, n2, 0), (0, n1, n2, n2 // 3)):
+            ps = [rng.uniform(-1, 1, k).astype(dt) for k in planes]
+            for op, fn in ((0, sp.convolve), (1, sp.correlate)):
+                for mode in range(5):
+                    wr, wi = np.zeros(n1 + n2, dt), np.zeros(n1 + n2, dt)
+                    size = fc(ck.fptr(wr), ck.fptr(wi), ck.fptr(ps[0]), planes[0], ck.fptr(ps[1]), planes[1], ck.fptr(ps[2]), planes[2],
+                              ck.fptr(ps[3]), planes[3], mode, op, MAXFFT[suf])
+                    gr, gi = np.zeros(n1 + n2, dt), np.zeros(n1 + n2, dt)
+                    assert fn(gr, gi, ps[0] if planes[0] else None, ps[1] if planes[1] else None, ps[2], ps[3] if planes[3] else None, mode) == size
+                    if size:
+                        assert ck.rel_rms(np.concatenate([gr[:size], gi[:size]]), np.concatenate([wr[:size], wi[:size]])) <= TOL[suf], (suf, planes, op, mode)
+
+
 def test_limits_and_noops(hb):
     sp = hb.spectral_processor(1024)
     assert sp.max_fft_size() == 1024

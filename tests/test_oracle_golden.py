@@ -125,3 +125,29 @@ def test_spectral_convolve(suf, n1, n2, mode):
     size = getattr(lib, "orc_spectral_convolve" + suf)(ck.fptr(y), ck.fptr(a), n1, ck.fptr(b), n2, mode, 32768)
     assert size == len(want)
     assert ck.rel_rms(y[:size], want) < TOL[suf]
+
+
+@pytest.mark.parametrize("suf", ["_f32", "_f64"])
+@pytest.mark.parametrize("n1,n2", [(1000, 300), (300, 1000), (64, 64), (7, 2), (1, 9)])
+def test_spectral_correlate_and_complex(suf, n1, n2):
+    """oracle restatement of correlate (real, five edge modes) and of the complex-input convolve / correlate
+    (Linear, Fold, FoldRepeat) against fixtures made by the unmodified reference."""
+    lib = ck.oracle()
+    a = np.ascontiguousarray(G["spec%s_%d_%d_a" % (suf, n1, n2)])
+    b = np.ascontiguousarray(G["spec%s_%d_%d_b" % (suf, n1, n2)])
+    for mode in range(5):
+        want = G["corr%s_%d_%d_m%d" % (suf, n1, n2, mode)]
+        y = np.zeros(n1 + n2 + 8, a.dtype)
+        size = getattr(lib, "orc_spectral_binary" + suf)(ck.fptr(y), ck.fptr(a), n1, ck.fptr(b), n2, mode, 1, 32768)
+        assert size == len(want)
+        assert ck.rel_rms(y[:size], want) < TOL[suf], (mode,)
+    ai = np.ascontiguousarray(G["cspec%s_%d_%d_ai" % (suf, n1, n2)])
+    bi = np.ascontiguousarray(G["cspec%s_%d_%d_bi" % (suf, n1, n2)])
+    for op in (0, 1):
+        for mode in (0, 3, 4):
+            want = G["cspec%s_%d_%d_op%d_m%d" % (suf, n1, n2, op, mode)]
+            yr, yi = np.zeros(n1 + n2 + 8, a.dtype), np.zeros(n1 + n2 + 8, a.dtype)
+            size = getattr(lib, "orc_spectral_binary_complex" + suf)(ck.fptr(yr), ck.fptr(yi), ck.fptr(a), n1, ck.fptr(ai), len(ai),
+                                                                     ck.fptr(b), n2, ck.fptr(bi), n2, mode, op, 32768)
+            assert size == want.shape[1]
+            assert ck.rel_rms(np.concatenate([yr[:size], yi[:size]]), want.ravel()) < TOL[suf], (op, mode)

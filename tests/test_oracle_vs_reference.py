@@ -319,6 +319,53 @@ def test_spectral_convolve(dtype, mode, n1, n2):
         assert ck.rel_rms(outs[1][1][: n1 + n2 - 1], truth) < (2e-6 if dtype == np.float32 else 1e-13)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 9), (9, 1), (1000, 300), (300, 1000), (64, 64), (7, 2), (2, 7), (513, 512), (2000, 1999)])
+def test_spectral_correlate_and_complex(dtype, n1, n2):
+    """correlate (real, all edge modes) and the complex-input operations (all edge modes where the reference's
+    reads stay inside its transform; Linear / Fold / FoldRepeat always do) -- oracle against the compiled reference,
+    and Linear against direct float64 correlation / convolution."""
+    rs, lib = ck.ref_spectral(), ck.oracle()
+    if rs is None:
+        pytest.skip("compiled reference not available")
+    suf = ck.SUF[np.dtype(dtype)]
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    rng = np.random.default_rng(n1 * 37 + n2)
+    a = rng.uniform(-1, 1, n1).astype(dtype)
+    b = rng.uniform(-1, 1, n2).astype(dtype)
+    for mode in range(5):
+        outs = []
+        for fn in (getattr(rs, "ref_spectral_binary" + suf), getattr(lib, "orc_spectral_binary" + suf)):
+            y = np.zeros(n1 + n2 + 8, dtype)
+            outs.append((fn(ck.fptr(y), ck.fptr(a), n1, ck.fptr(b), n2, mode, 1, 32768), y))
+        assert outs[0][0] == outs[1][0] > 0
+        assert ck.rel_rms(outs[1][1], outs[0][1]) < tol, (mode,)
+        if mode == 0 and n1 + n2 > 2:
+            # Linear correlation: lags 0..n1-1 then the negative lags -(n2-1)..-1 (arrange_correlate :490-495)
+            full = np.correlate(a.astype(np.float64), b.astype(np.float64), "full")         # lags -(n2-1) .. n1-1
+            truth = np.concatenate([full[n2 - 1:], full[:n2 - 1]])
+            assert ck.rel_rms(outs[1][1][: n1 + n2 - 1], truth) < tol
+    ai = rng.uniform(-1, 1, max(n1 // 2, 0)).astype(dtype)
+    bi = rng.uniform(-1, 1, n2).astype(dtype)
+    for op in (0, 1):
+        for mode in (0, 3, 4):
+            outs = []
+            for fn in (getattr(rs, "ref_spectral_binary_complex" + suf), getattr(lib, "orc_spectral_binary_complex" + suf)):
+                yr, yi = np.zeros(n1 + n2 + 8, dtype), np.zeros(n1 + n2 + 8, dtype)
+                size = fn(ck.fptr(yr), ck.fptr(yi), ck.fptr(a), n1, ck.fptr(ai), len(ai), ck.fptr(b), n2, ck.fptr(bi), n2, mode, op, 32768)
+                outs.append((size, np.concatenate([yr, yi])))
+            assert outs[0][0] == outs[1][0] > 0
+            assert ck.rel_rms(outs[1][1], outs[0][1]) < tol, (op, mode)
+    if n1 + n2 > 2:
+        za = a.astype(np.complex128)
+        za[:len(ai)] += 1j * ai
+        zb = b.astype(np.float64) + 1j * bi
+        yr, yi = np.zeros(n1 + n2 + 8, dtype), np.zeros(n1 + n2 + 8, dtype)
+        getattr(lib, "orc_spectral_binary_complex" + suf)(ck.fptr(yr), ck.fptr(yi), ck.fptr(a), n1, ck.fptr(ai), len(ai), ck.fptr(b), n2, ck.fptr(bi), n2, 0, 0, 32768)
+        truth = np.convolve(za, zb)
+        assert ck.rel_rms(np.concatenate([yr[: n1 + n2 - 1], yi[: n1 + n2 - 1]]), np.concatenate([truth.real, truth.imag])) < tol
+
+
 def test_spectral_convolve_fft_too_large_is_noop():
     rs, lib = ck.ref_spectral(), ck.oracle()
     a = np.ones(600, np.float64)
