@@ -74,6 +74,11 @@ SIGNATURES = {
     "hb_spectral_correlate": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_spectral_convolve_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_spectral_correlate_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
+    "hb_audio_probe": (C.c_int, [C.c_char_p, V]),
+    "hb_audio_read": (C.c_int, [C.c_char_p, U32, U32, C.c_int32, V, C.c_int, C.c_int]),
+    "hb_audio_decode_dev": (C.c_int, [V, V, C.c_uint64, C.c_int32, V, C.c_uint64, C.c_int, C.c_int, V]),
+    "hb_conv_set_ir_file": (C.c_int, [V, U32, U32, U32, C.c_char_p, U32, C.c_int]),
+    "hb_conv_dtype": (C.c_int, [V]),
     "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
     "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "hb_conv_set_trace": (C.c_int, [V, C.c_int]),

@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libhisstools_b200.so"
-SOURCES = ["hb_fft.cu", "hb_conv.cu", "hb_matrix.cu", "hb_spectral.cu"]
-HEADERS = ["hb_common.cuh", "hb_fft_core.cuh", "hb_fft_block.cuh", "hb_conv_kernels.cuh",
+SOURCES = ["hb_fft.cu", "hb_conv.cu", "hb_matrix.cu", "hb_spectral.cu", "hb_audio.cu"]
+HEADERS = ["hb_common.cuh", "hb_fft_core.cuh", "hb_fft_block.cuh", "hb_fft_big.cuh", "hb_conv_kernels.cuh", "hb_conv_big.cuh",
            os.path.join("..", "..", "include", "hisstools_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886"]

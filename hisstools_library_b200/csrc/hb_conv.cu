@@ -1148,6 +1148,7 @@ extern "C" int hb_conv_reset(hb_conv *c)
     return ERR_NONE;
 }
 
+extern "C" int hb_conv_dtype(const hb_conv *c) { return c ? c->dtype : HB_F32; }
 extern "C" uintptr_t hb_conv_partitions(const hb_conv *c) { return c ? c->P : 0; }
 extern "C" uintptr_t hb_conv_max_length(const hb_conv *c) { return c ? c->max_length : 0; }
 extern "C" uintptr_t hb_conv_fft_size(const hb_conv *c) { return c ? (uintptr_t(1) << c->fft_log2) : 0; }

@@ -273,6 +273,42 @@ int hb_spectral_convolve_complex(hb_spectral *s, void *r_out, void *i_out, const
 int hb_spectral_correlate_complex(hb_spectral *s, void *r_out, void *i_out, const void *r_in1, uintptr_t nr1, const void *i_in1, uintptr_t ni1,
                                   const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written);
 
+/* ---------------------------------------------------------------------------------------------
+ * Impulse responses from WAV / AIFF / AIFC files -- replaces the reading half of the reference's AudioFile component
+ * (AudioFile/IAudioFile.h:30-54: open, the BaseAudioFile getters, seek, readInterleaved, readChannel), the step before
+ * Convolver::set in real use.  Headers are parsed on the host; PCM decoding (8 / 16 / 24 / 32-bit integers of either
+ * byte order, 32 / 64-bit floats; de-interleaving) runs on the GPU.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hb_audio_info
+{
+    int32_t file_type;          /* BaseAudioFile::FileType: 0 none, 1 AIFF, 2 AIFC, 3 WAVE (BaseAudioFile.h:19-25) */
+    int32_t pcm_format;         /* BaseAudioFile::PCMFormat: 0 int8, 1 int16, 2 int24, 3 int32, 4 float32, 5 float64 (:27-35) */
+    int32_t header_big_endian;  /* getHeaderEndianness() == kAudioFileBigEndian */
+    int32_t audio_big_endian;   /* getAudioEndianness() == kAudioFileBigEndian */
+    uint32_t channels;          /* getChannels() */
+    uint32_t frames;            /* getFrames() */
+    double sampling_rate;       /* getSamplingRate() */
+    uint64_t pcm_offset;        /* byte offset of the first frame (getPCMOffset()) */
+    int32_t error_flags;        /* BaseAudioFile::Error bits (:49-62); 0 = readable */
+    int32_t reserved;
+} hb_audio_info;
+
+/* IAudioFile::open + parseHeader (IAudioFile.cpp:36-53, 375-609).  Returns HB_OK whenever the probe itself ran; what the
+ * reference would report through getErrorFlags() is in info->error_flags (e.g. 4 = could not open). */
+int hb_audio_probe(const char *path, hb_audio_info *info);
+/* seek(first_frame) then readChannel(out, frames, channel) (channel >= 0) or readInterleaved(out, frames) (channel < 0):
+ * IAudioFile.cpp:74-115, 613-689.  out: host array of out_dtype (HB_F32 / HB_F64), frames (x channels) elements. */
+int hb_audio_read(const char *path, uint32_t first_frame, uint32_t frames, int32_t channel, void *out, int out_dtype, int device);
+/* the decode step alone on device memory: d_raw holds `frames` raw interleaved frames as stored in the file; channel >= 0
+ * writes that channel to d_out[0 .. frames), channel < 0 writes every channel c to row d_out + c * ld (planar). */
+int hb_audio_decode_dev(const hb_audio_info *info, const void *d_raw, uint64_t frames, int32_t channel, void *d_out, uint64_t ld,
+                        int out_dtype, int device, void *stream);
+/* file -> spectra without a host float array: channel `channel` of the file becomes the impulse response of pair
+ * (group, in, out) of a uniform engine (hb_conv_set_ir_dev on the decoded device row). */
+int hb_conv_set_ir_file(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const char *path, uint32_t channel, int device);
+/* element type of an engine (HB_F32 / HB_F64) */
+int hb_conv_dtype(const hb_conv *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -201,6 +201,34 @@ def ref_spectral():
     return _ref_spec
 
 
+class RefAudioInfo(C.Structure):
+    """ref_audio_info of oracle/ref_audio_shim.cpp"""
+    _fields_ = [("file_type", C.c_int32), ("pcm_format", C.c_int32), ("header_big_endian", C.c_int32), ("audio_big_endian", C.c_int32),
+                ("channels", C.c_uint32), ("frames", C.c_uint32), ("sampling_rate", C.c_double), ("error_flags", C.c_int32), ("is_open", C.c_int32)]
+
+
+_ref_audio = None
+
+
+def ref_audio():
+    """The reference's audio-file reader / writer (oracle/_ref/libhisstools_ref_audio.so), or None."""
+    global _ref_audio
+    if _ref_audio is None:
+        lib = _load(os.path.join(ORACLE_DIR, "_ref", "libhisstools_ref_audio.so"))
+        if lib is None:
+            return None
+        lib.ref_audio_write.restype = C.c_int
+        lib.ref_audio_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_f64p, C.c_uint32]
+        lib.ref_audio_probe.restype = None
+        lib.ref_audio_probe.argtypes = [C.c_char_p, C.POINTER(RefAudioInfo)]
+        lib.ref_audio_read_f32.restype = C.c_int
+        lib.ref_audio_read_f32.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, c_f32p]
+        lib.ref_audio_read_f64.restype = C.c_int
+        lib.ref_audio_read_f64.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, c_f64p]
+        _ref_audio = lib
+    return _ref_audio
+
+
 def planar_ptrs(arr2d):
     """2-D C-contiguous float array -> (ctypes array of row pointers)."""
     assert arr2d.flags["C_CONTIGUOUS"]
