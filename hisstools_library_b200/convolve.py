@@ -150,12 +150,13 @@ class _Engine:
         return np.frombuffer(buf, dtype=np.uint64).reshape(16, 5, 2, 256).copy(), int(hop.value)
 
     def set_schedule(self, overlapped=True):
-        """True: overlapped (tail of the next hop computed ahead on a second stream), False: serial, None: automatic."""
+        """True: overlapped (tail of the next hop computed ahead on a second stream), False: serial, None: automatic
+        (the fused single-launch hop where it applies, else overlapped / serial by size)."""
         return _abi.check(_abi.lib().hb_conv_set_schedule(self._h, 2 if overlapped is None else (1 if overlapped else 0)))
 
     @property
     def schedule(self):
-        return "overlapped" if _abi.lib().hb_conv_schedule(self._h) else "serial"
+        return ("serial", "overlapped", "fused")[_abi.lib().hb_conv_schedule(self._h)]
 
     @property
     def bytes_per_launch(self):

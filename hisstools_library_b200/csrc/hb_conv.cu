@@ -11,6 +11,7 @@
 #include "hb_common.cuh"
 #include "hb_conv_kernels.cuh"
 #include "hb_conv_big.cuh"
+#include "hb_conv_fused.cuh"
 
 #include <algorithm>
 #include <map>
@@ -95,8 +96,10 @@ struct hb_conv
     // the forward FFTs of hop t are done, beside the inverse FFTs of hop t and the forward FFTs of hop t+1; the
     // critical path of a hop is then forward FFT -> partition 0 ("head") -> inverse FFT.  This is the load
     // spreading of PartitionedConvolve.cpp:330-347 (partitions done ahead, between hops) in stream form.
-    int schedule = 2;               // requested: 0 serial, 1 overlapped, 2 overlapped where the tail is worth a stream of its own
-    bool split = false;             // in effect for the current geometry (needs P >= 2)
+    int schedule = 2;               // requested: 0 serial, 1 overlapped, 2 automatic, 3 fused (one cluster launch per hop) where eligible
+    bool split = false;             // overlapped schedule in effect for the current geometry (needs P >= 2)
+    bool fused = false;             // fused single-launch hop in effect (hb_conv_fused.cuh)
+    uint32_t fused_cs = 1;          // its cluster size
     Range r_full{}, r_head{}, r_tail{};
     DevBuf d_St[2];                 // tail partial segments, double-buffered over hops
     cudaStream_t s_tail = nullptr;
@@ -198,7 +201,20 @@ void plan_geometry(hb_conv *c)
     // automatic choice: below a few MiB of tail spectra a hop is bound by launch latency, and the extra launch and
     // the two stream hand-overs of the overlapped schedule cost more than they hide (measured: DESIGN.md 4)
     const uint64_t tail_bytes = uint64_t(c->pairs() + uint64_t(g.groups) * g.ins) * (g.P ? g.P - 1 : 0) * g.B * 2 * c->esize();
-    c->split = g.P >= 2 && (c->schedule == 1 || (c->schedule == 2 && tail_bytes >= (uint64_t(4) << 20)));
+    // fused single-launch hop (hb_conv_fused.cuh): single-output engines whose partition spectrum is one bin tile and
+    // whose per-output share of the delay line is small enough for one cluster (<= 8 CTAs x 256 KiB of L2-resident reads)
+    c->fused = false;
+    c->fused_cs = 1;
+    if ((c->schedule == 2 || c->schedule == 3) && g.outs == 1 && g.n_bt == 1 && g.P >= 1 && log2m <= 12 && log2m >= 3)
+    {
+        const uint64_t per_output = tail_bytes / std::max<uint32_t>(g.groups, 1);
+        uint32_t cs = 1;
+        while (cs < 8 && per_output / cs > (uint64_t(96) << 10)) cs <<= 1;
+        // measured (profiles/r1_small_hops.txt): config 1 15 us against 21, config 2 21 us against 27; an 8 -> 1 engine with
+        // 2 MiB per rank is slower fused (42 us) than overlapped (36 us)
+        if (per_output / cs <= (uint64_t(256) << 10)) { c->fused = true; c->fused_cs = cs; }
+    }
+    c->split = !c->fused && g.P >= 2 && (c->schedule == 1 || ((c->schedule == 2 || c->schedule == 3) && tail_bytes >= (uint64_t(4) << 20)));
     // TMA ring depth: about 96 KB in flight per SM, 3 to 6 stages.  Measured on B200 at config 4 (32.5 KB stages,
     // profiles/r1_ring_depth.txt): 3 stages stream 7.2 TB/s, 2 stages 6.6, 5-6 stages 6.5 -- twice Little's law for
     // the chip (7.3 TB/s x ~1 us / 148 SMs = 49 KB) is enough, and a deeper ring only lowers the DRAM efficiency.
@@ -477,6 +493,48 @@ int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer));
 }
 
+// the whole hop in one cluster launch (hb_conv_fused.cuh); eligibility is decided in plan_geometry
+template <class T>
+int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, const InvIO<T> &io, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    constexpr int EPT = 8;
+    const uint32_t B = g.B, cs = c->fused_cs;
+    const size_t smem = (size_t(padded_elems<HB_PADSH>(B)) + 2 * size_t(B)) * sizeof(Cx<T>);
+    auto kernel = k_hop_fused<T, EPT>;
+    int rc = allow_smem(kernel, smem);
+    if (rc) return rc;
+    if (cs > 8)
+    {
+        static std::mutex m;
+        static std::map<std::pair<const void *, int>, bool> done;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(m);
+        bool &ok = done[std::make_pair((const void *) kernel, dev)];
+        if (!ok) { HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); ok = true; }
+    }
+    FusedArgs fa;
+    fa.cs = cs;
+    fa.tail_items = g.ins * (g.P - 1);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(g.groups * cs);
+    cfg.blockDim = dim3(std::max<uint32_t>(std::min<uint32_t>(B / EPT, 512u), 128u));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kernel, g, fa, prev, prev_ld, newest, new_ld, save, save_ld, (const Cx<T> *) c->d_H, (Cx<T> *) c->d_X,
+                               (const T *) c->d_Hnyq, (T *) c->d_Xnyq, io.yout, io.ld, io.off, io.add_result,
+                               io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry, (const Cx<T> *) c->d_tw, c->tw_log2));
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
 template <class T, int EPT>
 int launch_ir_ept(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
 {
@@ -729,6 +787,12 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     c->g.hop++;
     c->g.trace = (unsigned long long *) c->d_trace.p;
     if (pe) HB_CUDA(cudaEventRecord(pe[0], st));
+    if (c->fused && !peer.world)
+    {
+        if ((r = launch_fused<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, io, st))) return r;
+        if (pe) for (int k = 1; k <= 4; k++) HB_CUDA(cudaEventRecord(pe[k], st));
+        return HB_OK;
+    }
     if ((r = launch_fwd<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st))) return r;
     if (pe) HB_CUDA(cudaEventRecord(pe[1], st));
     SegSets sets;
@@ -1389,7 +1453,7 @@ extern "C" int hb_conv_set_schedule(hb_conv *c, int overlapped)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
-    if (overlapped < 0 || overlapped > 2) { set_error("schedule must be 0 (serial), 1 (overlapped) or 2 (automatic)"); return HB_ERR_BAD_ARG; }
+    if (overlapped < 0 || overlapped > 3) { set_error("schedule must be 0 (serial), 1 (overlapped), 2 (automatic) or 3 (fused where eligible)"); return HB_ERR_BAD_ARG; }
     c->schedule = overlapped;
     c->need_reset = true;           // the partial-segment sets depend on the schedule
     return HB_OK;
@@ -1455,7 +1519,7 @@ extern "C" int hb_conv_get_profile(hb_conv *c, double *ms, uint64_t *hops)
     return HB_OK;
 }
 
-extern "C" int hb_conv_schedule(const hb_conv *c) { return c && c->split ? 1 : 0; }
+extern "C" int hb_conv_schedule(const hb_conv *c) { return !c ? 0 : (c->fused ? 2 : (c->split ? 1 : 0)); }
 
 extern "C" uint64_t hb_conv_bytes_per_launch(const hb_conv *c)
 {

@@ -1,0 +1,223 @@
+// hb_conv_fused.cuh -- one launch per hop for small single-output engines (PartitionedConvolve, MonoConvolve parts,
+// NToMonoConvolve: groups x ins x 1 output, spectrum of one partition <= 32 KiB so that bin tiles do not split).
+//
+// Such hops are bound by launch latency, not by HBM: the three-kernel hop (k_fwd -> k_cmac -> k_inv) spends ~7 us per
+// launch on a few hundred KiB of L2-resident data.  Here one thread-block CLUSTER per (group, output) does the whole
+// hop (PartitionedConvolve.cpp:352-377):
+//   every rank  forward FFT of the inputs it owns (rank = input mod cluster size) into the newest FDL slot, partition 0
+//               against that fresh spectrum, then its share of the (input, partition >= 1) products against spectra that
+//               are already in the delay line -- all accumulated in registers, one complex bin set per thread;
+//   cluster barrier; rank 0 adds the other ranks' partial spectra and Nyquist sums straight out of their shared memory
+//               (distributed shared memory), then inverse split, inverse FFT, scale 1/(4N), first B samples out.
+// Layouts are the engine's own (hb_conv_kernels.cuh) with OT = 1 and one bin tile, so IR loading and the other
+// schedules are unchanged.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "hb_conv_kernels.cuh"
+
+namespace hb
+{
+namespace cg = cooperative_groups;
+
+struct FusedArgs
+{
+    uint32_t cs;               // cluster size
+    uint32_t tail_items;       // ins * (P - 1)
+};
+
+template <class T, int EPT>
+__global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs fa,
+                                                   const T *__restrict__ prev, size_t prev_ld, const T *__restrict__ newest, size_t new_ld,
+                                                   T *__restrict__ save, size_t save_ld,
+                                                   const Cx<T> *__restrict__ H, Cx<T> *__restrict__ X, const T *__restrict__ Hnyq, T *__restrict__ Xnyq,
+                                                   T *__restrict__ yout, size_t ld, size_t off, int add_result,
+                                                   const T *__restrict__ carry_src, size_t carry_src_ld, T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
+                                                   const Cx<T> *__restrict__ tw, int tw_log2)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank(), cs = fa.cs;
+    const uint32_t grp = blockIdx.x / cs;                       // one cluster per (group, the single output)
+    const uint32_t B = g.B, P = g.P;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);             // FFT work array (padded)
+    Cx<T> *stw = s + padded_elems<HB_PADSH>(B);                 // twiddles of this size
+    Cx<T> *xch = stw + B;                                       // this rank's partial spectrum, read by rank 0
+    __shared__ T red[40];
+    __shared__ T nyq_part;
+    trace_mark(g, 0, 0);
+
+    // twiddles of this transform size into shared memory (published by the first barrier below)
+    {
+        Cx<T> twr[EPT];
+        twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
+    }
+    const Cx<T> *twl = stw;
+    const int twl_log2 = (int) g.log2n;
+
+    if (rank == 0 && carry_dst)
+    {
+        // hand the block computed by the previous hop to the caller (the output-ring read of PartitionedConvolve.cpp:307)
+        const T *cs_ = carry_src + size_t(grp) * carry_src_ld;
+        T *cd = carry_dst + size_t(grp) * carry_dst_ld;
+        for (uint32_t k = tid; k < B; k += nthr) cd[k] = add_carry ? cd[k] + cs_[k] : cs_[k];
+    }
+
+    Cx<T> acc[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) acc[e] = cx<T>(T(0), T(0));
+    T nyq = T(0);
+
+    // ---- inputs this rank transforms: forward FFT, newest FDL slot, partition 0 ----
+    for (uint32_t in = rank; in < g.ins; in += cs)
+    {
+        const uint32_t ch = grp * g.ins + in;
+        const T *pn = newest + size_t(ch) * new_ld, *pp = prev + size_t(ch) * prev_ld;
+        T *ps = save ? save + size_t(ch) * save_ld : nullptr;
+        __syncthreads();                                        // s is free (previous input's spectrum consumed)
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+        {
+            const uint32_t k = tid + e * nthr, j = 2 * k;
+            if (k < B)
+            {
+                T a, b;
+                if (j < B)
+                {
+                    a = pn[j]; b = pn[j + 1];
+                    if (ps) { ps[j] = a; ps[j + 1] = b; }
+                }
+                else { a = pp[j - B]; b = pp[j - B + 1]; }
+                s[sidx<HB_PADSH>(k)] = cx<T>(a, b);
+            }
+        }
+        __syncthreads();
+        block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
+        block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, twl, twl_log2);
+        __syncthreads();
+        Cx<T> *xrow = X + (size_t(ch) * P + g.slot) * B;
+        const Cx<T> *h0 = H + (size_t(ch) * g.Pcap) * B;       // unit (tile = grp, in, p = 0): OT = 1, one bin tile
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B)
+            {
+                Cx<T> z = s[sidx<HB_PADSH>(k)];
+                if (k == 0)
+                {
+                    const T xn = z.y;
+                    Xnyq[size_t(ch) * P + g.slot] = xn;
+                    nyq += xn * Hnyq[size_t(ch) * g.Pcap];      // outs = 1: Hnyq[(grp * 1 + 0) * ins + in][p]
+                    z.y = T(0);
+                }
+                xrow[k] = z;
+                const Cx<T> h = h0[k];
+                acc[e].x = fma(z.x, h.x, acc[e].x); acc[e].x = fma(-z.y, h.y, acc[e].x);
+                acc[e].y = fma(z.x, h.y, acc[e].y); acc[e].y = fma(z.y, h.x, acc[e].y);
+            }
+        }
+    }
+
+    // ---- this rank's share of the (input, partition >= 1) products: spectra already in the delay line ----
+    {
+        const uint32_t q0 = (uint32_t) ((uint64_t(rank) * fa.tail_items) / cs), q1 = (uint32_t) ((uint64_t(rank + 1) * fa.tail_items) / cs);
+        const uint32_t pm1 = P - 1;
+        for (uint32_t q = q0; q < q1; q++)
+        {
+            const uint32_t in = q / pm1, p = 1 + (q - in * pm1);
+            const uint32_t ch = grp * g.ins + in;
+            uint32_t sl = g.slot + p;
+            if (sl >= P) sl -= P;
+            const Cx<T> *hp = H + (size_t(ch) * g.Pcap + p) * B;
+            const Cx<T> *xp = X + (size_t(ch) * P + sl) * B;
+            Cx<T> hv[EPT], xv[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B) { hv[e] = hp[k]; xv[e] = xp[k]; }
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B)
+                {
+                    acc[e].x = fma(xv[e].x, hv[e].x, acc[e].x); acc[e].x = fma(-xv[e].y, hv[e].y, acc[e].x);
+                    acc[e].y = fma(xv[e].x, hv[e].y, acc[e].y); acc[e].y = fma(xv[e].y, hv[e].x, acc[e].y);
+                }
+            }
+            if (tid == 0) nyq += Xnyq[size_t(ch) * P + sl] * Hnyq[size_t(ch) * g.Pcap + p];
+        }
+    }
+
+    // ---- publish the partial spectrum and Nyquist sum; rank 0 reduces over the cluster ----
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
+    {
+        const uint32_t k = tid + e * nthr;
+        if (k < B) xch[k] = acc[e];
+    }
+    const T nyq_sum = block_sum<T>(nyq, red);
+    if (tid == 0) nyq_part = nyq_sum;
+    cluster.sync();
+    if (rank == 0)
+    {
+        T nyq_total = nyq_sum;
+        for (uint32_t r = 1; r < cs; r++)
+        {
+            const Cx<T> *rx = cluster.map_shared_rank(xch, r);
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B) { const Cx<T> v = rx[k]; acc[e].x += v.x; acc[e].y += v.y; }
+            }
+            nyq_total += *cluster.map_shared_rank(&nyq_part, r);
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B) s[sidx<HB_PADSH>(k)] = k ? acc[e] : cx<T>(acc[e].x, nyq_total);
+        }
+    }
+    cluster.sync();                                             // remote shared memory may go away from here on
+    if (rank != 0) { trace_mark(g, 0, 1); return; }
+
+    // ---- inverse real FFT, scale, first B samples (k_inv's tail) ----
+    block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, true, twl, twl_log2);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; e++)
+    {
+        const uint32_t k = tid + e * nthr;
+        if (k < B)
+        {
+            const Cx<T> z = s[sidx<HB_PADSH>(k)];
+            s[sidx<HB_PADSH>(k)] = cx<T>(z.y, z.x);
+        }
+    }
+    __syncthreads();
+    block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
+    const T scale = T(1) / T(size_t(4) << g.log2n);
+    T *dst = yout + size_t(grp) * ld + off;
+#pragma unroll
+    for (int e = 0; e < EPT / 2; e++)
+    {
+        const uint32_t k = tid + e * nthr;
+        if (k < B / 2)
+        {
+            const Cx<T> z = s[sidx<HB_PADSH>(k)];
+            if (add_result) { dst[2 * k] += z.y * scale; dst[2 * k + 1] += z.x * scale; }
+            else { dst[2 * k] = z.y * scale; dst[2 * k + 1] = z.x * scale; }
+        }
+    }
+    trace_mark(g, 0, 1);
+}
+
+} // namespace hb

@@ -172,11 +172,14 @@ uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
  * done, beside the inverse FFTs of this hop and the forward FFTs of the next; a hop's critical path is forward
  * FFT -> partition 0 ("head") -> inverse FFT.  It is the stream form of the reference's spreading of partitions
  * over the samples of a hop (PartitionedConvolve.cpp:330-347).  overlapped = 0: forward FFTs, one multiply-accumulate
- * over all partitions, inverse FFTs, in a row.  overlapped = 2 (default): overlapped when the tail streams at least
- * 4 MiB of spectra per hop, serial below that (launch-latency-bound hops gain nothing from a second stream).
- * Results differ by summation order only.  Takes effect with a reset. */
+ * over all partitions, inverse FFTs, in a row.  overlapped = 2 (default, automatic): the fused hop where it applies,
+ * else overlapped when the tail streams at least 4 MiB of spectra per hop, else serial (launch-latency-bound hops gain
+ * nothing from a second stream).  overlapped = 3: as 2.  The FUSED hop is one thread-block-cluster launch per hop for
+ * single-output engines with small spectra (PartitionedConvolve, MonoConvolve parts, NToMonoConvolve): the ranks of a
+ * cluster transform the inputs, split the (input, partition) products and reduce through distributed shared memory
+ * (hb_conv_fused.cuh).  overlapped = 0 / 1 never fuse.  Results differ by summation order only.  Takes effect with a reset. */
 int hb_conv_set_schedule(hb_conv *c, int overlapped);
-/* schedule in effect after the last reset (1 overlapped, 0 serial: also whenever only one partition is loaded) */
+/* schedule in effect after the last reset: 0 serial (also whenever only one partition is loaded), 1 overlapped, 2 fused */
 int hb_conv_schedule(const hb_conv *c);
 /* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in
  * the overlapped one the tail's share, 2sB(P-1)(K+I) */

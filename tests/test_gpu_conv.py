@@ -38,7 +38,7 @@ def stream(obj_process, x, block, dtype=np.float32, sizes=None):
 
 # ---- PartitionedConvolve ------------------------------------------------------------------------
 
-@pytest.mark.parametrize("schedule", ["overlapped", "serial"])
+@pytest.mark.parametrize("schedule", ["overlapped", "serial", "auto"])
 @pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("name", ["c1", "ragged", "phase", "slice", "trunc", "min"])
 def test_pconv_golden(hb, name, variant, schedule):
@@ -46,11 +46,13 @@ def test_pconv_golden(hb, name, variant, schedule):
     ir, x, want = G["pconv_%s_ir" % name], G["pconv_%s_x" % name], G["pconv_%s_y" % name]
     pc = hb.PartitionedConvolve(fft, len(ir) if max_len < 0 else max_len, offset, length)
     pc.engine.set_tuning(0, variant)
-    pc.engine.set_schedule(schedule == "overlapped")
+    pc.engine.set_schedule(None if schedule == "auto" else schedule == "overlapped")
     pc.setResetOffset(reset_offset)
     assert int(pc.set(ir, len(ir))) == err
     got = stream(lambda a, b, n: pc.process(a, b, n), x, block)
     assert ck.rel_rms(got, want) <= TOL32
+    if schedule == "auto":
+        assert pc.engine.schedule == "fused"             # a single small channel: one cluster launch per hop
 
 
 @pytest.mark.parametrize("variant", [1, 0])
@@ -118,6 +120,52 @@ def test_schedules_agree_and_survive_mid_stream_changes(hb, dtype):
     for o in range(n_out):
         truth = sum(ck.direct_convolve_delayed(irs[o][i], xs[i][:first], B) for i in range(n_in))
         assert ck.rel_rms(outs["overlapped"][o][:first], truth) <= tol * (1 if dtype == np.float32 else 10)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("ins,groups,B,L", [(1, 1, 512, 4096), (1, 1, 1024, 65536), (8, 1, 2048, 30000), (3, 2, 256, 5000), (1, 3, 16, 100), (5, 1, 64, 64)])
+def test_fused_hop_against_serial_and_truth(hb, dtype, ins, groups, B, L):
+    """The fused single-launch hop (one thread-block cluster per output: hb_conv_fused.cuh) on single-output engines --
+    BASELINE configs 1 and 2, a config-3-like 8 -> 1 shape, several groups, tiny and one-partition sizes -- against the
+    serial three-kernel hop (summation order only) and float64 direct convolution, ragged calls included."""
+    from hisstools_library_b200.convolve import _Engine
+    if dtype == np.float64 and B > 2048:
+        pytest.skip("spectrum above one bin tile")
+    tol = TOL32 if dtype == np.float32 else TOL64
+    irs = [[ck.synth_ir(L, 700 + 10 * g + i).astype(dtype) for i in range(ins)] for g in range(groups)]
+    n = B * 12 + 37
+    xs = np.stack([ck.synth_audio(n, 700 + r) for r in range(groups * ins)]).astype(dtype)
+    outs = {}
+    for mode in ("auto", "serial"):
+        e = _Engine(dtype, groups, ins, 1, 2 * B, L, 0, 0, 0)
+        e.set_schedule(None if mode == "auto" else False)
+        e.set_reset_offset(0)
+        for g in range(groups):
+            for i in range(ins):
+                e.set_ir(g, i, 0, irs[g][i], L)
+        y = np.zeros((groups, n), dtype)
+        pos, k = 0, 0
+        sizes = [B, B, B // 2 + 1, 3 * B, 5, B]
+        while pos < n:
+            m = min(sizes[k % len(sizes)], n - pos)
+            yo = [np.zeros(m, dtype) for _ in range(groups)]
+            e.process([np.ascontiguousarray(xs[r, pos:pos + m]) for r in range(groups * ins)], yo, m)
+            for g in range(groups):
+                y[g, pos:pos + m] = yo[g]
+            pos += m
+            k += 1
+        # eligible for the fused hop: at most 8 ranks x 256 KiB of spectra per output (plan_geometry)
+        eligible = ins * (-(-L // B) - 1) * B * 4 * np.dtype(dtype).itemsize <= 8 * 256 * 1024
+        if mode == "serial" or eligible:
+            assert e.schedule == ("fused" if mode == "auto" else "serial")
+        else:
+            assert e.schedule in ("overlapped", "serial")
+        outs[mode] = y
+        e.close()
+    for g in range(groups):
+        assert ck.rel_rms(outs["auto"][g], outs["serial"][g]) <= tol / 5
+        truth = sum(ck.direct_convolve_delayed_fft(irs[g][i], xs[g * ins + i], B) for i in range(ins))
+        assert ck.rel_rms(outs["auto"][g], truth) <= tol * (1 if dtype == np.float32 else 10)
 
 
 def test_pconv_call_sizes_do_not_matter(hb):

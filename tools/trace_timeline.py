@@ -10,7 +10,8 @@ sys.path.insert(0, ROOT)
 import torch
 from hisstools_library_b200.convolve import _Engine
 
-CFG = {"c4": (64, 64, 1, 262144, 4096, np.float32), "c4n8": (8, 64, 1, 262144, 4096, np.float32), "c3": (8, 1, 1, 131072, 2048, np.float32),
+CFG = {"c1": (1, 1, 1, 4096, 512, np.float32), "c2": (1, 1, 1, 65536, 1024, np.float32),
+       "c4": (64, 64, 1, 262144, 4096, np.float32), "c4n8": (8, 64, 1, 262144, 4096, np.float32), "c3": (8, 1, 1, 131072, 2048, np.float32),
        "c5": (1, 1, 16, 1048576, 8192, np.float64)}
 KIND = ["fwd", "head", "tail", "inv", "gath"]
 
@@ -25,7 +26,7 @@ def main():
     tdt = torch.float64 if dt == np.float64 else torch.float32
     eng = _Engine(dt, groups, ins, outs, 2 * B, taps, 0, 0, 0)
     eng.set_reset_offset(0)
-    eng.set_schedule(sched == "overlapped")
+    eng.set_schedule(None if sched == "auto" else sched == "overlapped")
     eng.set_tuning(0, variant)
     ir = torch.randn(taps, device=dev, dtype=tdt)
     for g in range(groups):
