@@ -24,6 +24,8 @@ namespace
 {
 constexpr uintptr_t MIN_FFT_LOG2 = 5;       // PartitionedConvolve.h:18
 constexpr uintptr_t MAX_FFT_LOG2 = 20;      // PartitionedConvolve.h:19
+constexpr uint32_t MH_MAX = 4;              // hops one multi-hop multiply-accumulate launch covers at most
+constexpr uint32_t MH_EXTRA = MH_MAX - 1;   // extra delay-line slots that needs
 
 // reference error codes (ConvolveErrors.h:4-19)
 enum
@@ -170,6 +172,7 @@ void plan_geometry(hb_conv *c)
     g.B = 1u << (g.log2n - 1);
     g.Pcap = (uint32_t) (c->max_length / g.B);
     g.P = c->P;
+    g.R = c->P ? c->P + MH_EXTRA : 0;             // the delay line keeps the look-ahead slots of a multi-hop launch
     g.OT = choose_ot(c->outs);
     g.n_ot = (c->outs + g.OT - 1) / g.OT;
     const uint32_t xq = g.B / cpv;
@@ -296,10 +299,11 @@ int alloc_capacity(hb_conv *c)
     cudaFree(c->d_H); cudaFree(c->d_X); cudaFree(c->d_Hnyq); cudaFree(c->d_Xnyq);
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = nullptr;
     const size_t hbytes = h_vectors(c) * 16;
-    const size_t xbytes = size_t(c->groups) * c->ins * c->max_length * 2 * c->esize();
+    const size_t maxB_ = (size_t(1) << c->max_fft_log2) >> 1;
+    const size_t xbytes = size_t(c->groups) * c->ins * (c->max_length + MH_EXTRA * maxB_) * 2 * c->esize();
     // Nyquist side arrays are sized for the smallest hop the object may be switched to
     const size_t minB = size_t(1) << (MIN_FFT_LOG2 - 1);
-    const size_t pmax = c->max_length / minB;
+    const size_t pmax = c->max_length / minB + MH_EXTRA;
     if (cudaMalloc(&c->d_H, std::max<size_t>(hbytes, 16)) != cudaSuccess ||
         cudaMalloc(&c->d_X, std::max<size_t>(xbytes, 16)) != cudaSuccess ||
         cudaMalloc(&c->d_Hnyq, std::max<size_t>(c->pairs() * pmax * c->esize(), 16)) != cudaSuccess ||
@@ -698,8 +702,8 @@ int do_reset(hb_conv *c, cudaStream_t st)
             if (!c->ev_tail[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[k], cudaEventDisableTiming));
     }
     // FDL silence: stale slots are masked in the reference by mValidPartitions (:285,373); zeros do the same
-    HB_CUDA(cudaMemsetAsync(c->d_X, 0, size_t(g.groups) * g.ins * g.P * g.B * 2 * sizeof(T), st));
-    HB_CUDA(cudaMemsetAsync(c->d_Xnyq, 0, size_t(g.groups) * g.ins * g.P * sizeof(T), st));
+    HB_CUDA(cudaMemsetAsync(c->d_X, 0, size_t(g.groups) * g.ins * g.R * g.B * 2 * sizeof(T), st));
+    HB_CUDA(cudaMemsetAsync(c->d_Xnyq, 0, size_t(g.groups) * g.ins * g.R * sizeof(T), st));
     c->rw = c->reset_offset < 0 ? 0 : uintptr_t(c->reset_offset) % g.B;
     c->g.slot = 0;
     // staging rows start as silence: previous hop, pending samples and previous result block
@@ -783,7 +787,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     cudaEvent_t *pe = nullptr;
     if (c->profiling && (r = profile_begin_hop(c, &pe))) return r;
     // newest spectrum goes one slot below the previous one (mInputPosition--, cpp:374)
-    c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+    c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
     c->g.hop++;
     c->g.trace = (unsigned long long *) c->d_trace.p;
     if (pe) HB_CUDA(cudaEventRecord(pe[0], st));
@@ -813,7 +817,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
         HB_CUDA(cudaEventRecord(c->ev_fwd, st));
         const int np = c->tail_par ^ 1;
         Range rt = c->r_tail;
-        rt.slot = c->g.slot ? c->g.slot - 1 : c->g.P - 1;
+        rt.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
         rt.kind = 2;
         HB_CUDA(cudaStreamWaitEvent(c->s_tail, c->ev_fwd, 0));
         if (pe) { HB_CUDA(cudaEventRecord(pe[5], c->s_tail)); c->ev_has_tail[c->ev_used - 1] = 1; }

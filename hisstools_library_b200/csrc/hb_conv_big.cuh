@@ -45,17 +45,17 @@ __global__ void k_bigc_to_fdl(const Geom g, const Cx<T> *__restrict__ z, Cx<T> *
     const uint32_t ch = blockIdx.y, B = g.B;
     const uint32_t TB = tile_bins<T>(g);
     const Cx<T> *zc = z + size_t(ch) * B;
-    Cx<T> *xrow = X + size_t(ch) * g.n_bt * g.P * TB;
+    Cx<T> *xrow = X + size_t(ch) * g.n_bt * g.R * TB;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < B; k += gridDim.x * blockDim.x)
     {
         Cx<T> v = zc[k];
         if (k == 0)
         {
-            Xnyq[size_t(ch) * g.P + g.slot] = v.y;
+            Xnyq[size_t(ch) * g.R + g.slot] = v.y;
             v.y = T(0);
         }
         const uint32_t bt = k / TB, j = k - bt * TB;
-        xrow[(size_t(bt) * g.P + g.slot) * TB + j] = v;
+        xrow[(size_t(bt) * g.R + g.slot) * TB + j] = v;
     }
 }
 
@@ -107,14 +107,14 @@ __global__ void __launch_bounds__(256) k_bigc_nyq(const Geom g, const T *__restr
     const uint32_t ch = blockIdx.x;
     const uint32_t grp = ch / g.outs, o = ch - grp * g.outs;
     const T *hn = Hnyq + (size_t(grp) * g.outs + o) * g.ins * g.Pcap;
-    const T *xn = Xnyq + size_t(grp) * g.ins * g.P;
+    const T *xn = Xnyq + size_t(grp) * g.ins * g.R;
     T part = T(0);
     for (uint32_t idx = threadIdx.x; idx < g.upt; idx += blockDim.x)
     {
         const uint32_t in = idx / g.P, p = idx - in * g.P;
         uint32_t sl = g.slot + p;
-        if (sl >= g.P) sl -= g.P;
-        part += xn[size_t(in) * g.P + sl] * hn[size_t(in) * g.Pcap + p];
+        if (sl >= g.R) sl -= g.R;
+        part += xn[size_t(in) * g.R + sl] * hn[size_t(in) * g.Pcap + p];
     }
     const T total = block_sum<T>(part, red);
     if (threadIdx.x == 0) nyq[ch] = total;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank(), cs = fa.cs;
     const uint32_t grp = blockIdx.x / cs;                       // one cluster per (group, the single output)
-    const uint32_t B = g.B, P = g.P;
+    const uint32_t B = g.B, P = g.P, R = g.R;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);             // FFT work array (padded)
     Cx<T> *stw = s + padded_elems<HB_PADSH>(B);                 // twiddles of this size
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
         block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
         block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, twl, twl_log2);
         __syncthreads();
-        Cx<T> *xrow = X + (size_t(ch) * P + g.slot) * B;
+        Cx<T> *xrow = X + (size_t(ch) * R + g.slot) * B;
         const Cx<T> *h0 = H + (size_t(ch) * g.Pcap) * B;       // unit (tile = grp, in, p = 0): OT = 1, one bin tile
 #pragma unroll
         for (int e = 0; e < EPT; e++)
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 if (k == 0)
                 {
                     const T xn = z.y;
-                    Xnyq[size_t(ch) * P + g.slot] = xn;
+                    Xnyq[size_t(ch) * R + g.slot] = xn;
                     nyq += xn * Hnyq[size_t(ch) * g.Pcap];      // outs = 1: Hnyq[(grp * 1 + 0) * ins + in][p]
                     z.y = T(0);
                 }
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
             const uint32_t in = q / pm1, p = 1 + (q - in * pm1);
             const uint32_t ch = grp * g.ins + in;
             uint32_t sl = g.slot + p;
-            if (sl >= P) sl -= P;
+            if (sl >= R) sl -= R;
             const Cx<T> *hp = H + (size_t(ch) * g.Pcap + p) * B;
-            const Cx<T> *xp = X + (size_t(ch) * P + sl) * B;
+            const Cx<T> *xp = X + (size_t(ch) * R + sl) * B;
             Cx<T> hv[EPT], xv[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; e++)
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                     acc[e].y = fma(xv[e].x, hv[e].y, acc[e].y); acc[e].y = fma(xv[e].y, hv[e].x, acc[e].y);
                 }
             }
-            if (tid == 0) nyq += Xnyq[size_t(ch) * P + sl] * Hnyq[size_t(ch) * g.Pcap + p];
+            if (tid == 0) nyq += Xnyq[size_t(ch) * R + sl] * Hnyq[size_t(ch) * g.Pcap + p];
         }
     }
 

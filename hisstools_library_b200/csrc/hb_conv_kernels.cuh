@@ -38,7 +38,8 @@ struct Geom
     uint32_t groups, ins, outs;
     uint32_t log2n;        // log2 of the FFT size N
     uint32_t B;            // hop = N/2 = complex bins per spectrum
-    uint32_t P;            // partitions in use = FDL ring length
+    uint32_t P;            // partitions in use
+    uint32_t R;            // FDL ring length (slots) >= P: P + the hops a multi-hop launch looks ahead
     uint32_t Pcap;         // partition stride of the IR layout (capacity at this FFT size)
     uint32_t OT, n_ot;     // output rows per tile, output tiles
     uint32_t TBV, n_bt;    // vectors along bins per tile, bin tiles
@@ -200,8 +201,8 @@ struct Cursor
         uint32_t bt = tile % g.n_bt;
         uint32_t grp = tile / (g.n_bt * g.n_ot);
         uint32_t s = r.slot + p;
-        if (s >= g.P) s -= g.P;
-        return (((uint64_t(grp) * g.ins + in) * g.n_bt + bt) * g.P + s) * g.TBV;
+        if (s >= g.R) s -= g.R;
+        return (((uint64_t(grp) * g.ins + in) * g.n_bt + bt) * g.R + s) * g.TBV;
     }
 };
 
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg, 
         const V *hp = H + cur.h_off(g) + lane_off;
         const V *xbase = X + cur.x_off(g, rg) + tx;      // slot (rg.slot + p) of this (group, in, bin-tile)
         uint32_t s = rg.slot + cur.p;
-        if (s >= g.P) s -= g.P;
+        if (s >= g.R) s -= g.R;
         const V *xp = xbase;
         const V *xwrap = xbase - uint64_t(s) * g.TBV;    // slot 0
 #pragma unroll 2
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg, 
                 for (int a = 0; a < XA; a++) cmac(acc[b * XA + a], xv[a], hv[b * XA + a]);
             hp += g.Q;
             xp += g.TBV;
-            if (++s == g.P) { s = 0; xp = xwrap; }
+            if (++s == g.R) { s = 0; xp = xwrap; }
         }
         u += run;
         const uint32_t tile_done = cur.tile;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
     block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, tw, tw_log2);
     __syncthreads();
     const uint32_t TB = tile_bins<T>(g);
-    Cx<T> *xrow = X + size_t(ch) * g.n_bt * g.P * TB;
+    Cx<T> *xrow = X + size_t(ch) * g.n_bt * g.R * TB;
 #pragma unroll
     for (int e = 0; e < EPT; e++)
     {
@@ -513,11 +514,11 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
             Cx<T> z = s[sidx<HB_PADSH>(k)];
             if (k == 0)
             {
-                Xnyq[size_t(ch) * g.P + g.slot] = z.y;
+                Xnyq[size_t(ch) * g.R + g.slot] = z.y;
                 z.y = T(0);
             }
             const uint32_t bt = k / TB, j = k - bt * TB;
-            xrow[(size_t(bt) * g.P + g.slot) * TB + j] = z;
+            xrow[(size_t(bt) * g.R + g.slot) * TB + j] = z;
         }
     }
     trace_mark(g, 0, 1);
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
     // Nyquist bin: a real dot product over (in, partition)
     T part = T(0);
     const T *hn = Hnyq + (size_t(grp) * g.outs + o) * g.ins * g.Pcap;
-    const T *xn = Xnyq + size_t(grp) * g.ins * g.P;
+    const T *xn = Xnyq + size_t(grp) * g.ins * g.R;
     for (uint32_t idx0 = tid; idx0 < g.upt; idx0 += 4 * nthr)
     {
         T xv[4], hv[4];
@@ -704,8 +705,8 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
             {
                 const uint32_t in = idx / g.P, p = idx - in * g.P;
                 uint32_t sl = g.slot + p;
-                if (sl >= g.P) sl -= g.P;
-                xv[q] = xn[size_t(in) * g.P + sl];
+                if (sl >= g.R) sl -= g.R;
+                xv[q] = xn[size_t(in) * g.R + sl];
                 hv[q] = hn[size_t(in) * g.Pcap + p];
             }
         }
