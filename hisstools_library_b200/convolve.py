@@ -140,6 +140,9 @@ class _Engine:
         _abi.check(_abi.lib().hb_conv_get_profile(self._h, ms, C.byref(h)))
         return dict(zip(("forward", "cmac", "wait", "inverse", "tail"), [float(v) for v in ms])), int(h.value)
 
+    def set_multi_hop(self, enable=True):
+        return _abi.check(_abi.lib().hb_conv_set_multi_hop(self._h, 1 if enable else 0))
+
     def set_trace(self, enable=True):
         return _abi.check(_abi.lib().hb_conv_set_trace(self._h, 1 if enable else 0))
 

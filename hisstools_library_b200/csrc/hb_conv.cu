@@ -107,8 +107,13 @@ struct hb_conv
     cudaStream_t s_tail = nullptr;
     cudaEvent_t ev_fwd = nullptr, ev_tail[2] = {nullptr, nullptr};
     bool tail_valid = false;        // d_St[tail_par] holds the tail of the upcoming hop
+    bool tail_missing = false;      // a multi-hop batch ran last: nothing was computed ahead for the upcoming hop
     int tail_par = 0;
     DevBuf d_trace;                 // optional kernel timeline (hb_conv_set_trace)
+    DevBuf d_Smh;                   // partial segments of a multi-hop launch: [hop][cta + tile][row][TBV]
+    int multi_hop = 1;              // hb_conv_set_multi_hop: batch the hops of one call over a single pass of the IR spectra
+    bool mh_ok = false;             // eligible for the current geometry (plan_geometry)
+    int mh_stages = 3;
     BigScratch big;                 // four-step scratch for FFT sizes above the single-CTA limit (hb_conv_big.cuh)
     DevBuf d_nyq;
 
@@ -244,6 +249,15 @@ void plan_geometry(hb_conv *c)
     if (env_rs && c->split) reserve = std::min<uint64_t>((uint64_t) atoi(env_rs), sms - 1);
     c->nstages = std::max(2, st);
     c->cmac_smem = size_t(c->nstages) * stage + size_t(c->nstages) * 8;
+    // multi-hop reuse (k_cmac_tma_mh): HBM-bound engines with full-height tiles (the FDL tile is 1/OT of the IR unit, so the
+    // extra hops add little traffic), TMA variant, single-CTA transforms
+    {
+        const size_t stage_mh = size_t(g.Q + MH_MAX * g.TBV) * 16;
+        c->mh_stages = (int) std::min<size_t>(3, (200 * 1024) / stage_mh);
+        c->mh_ok = c->multi_hop && c->variant == 1 && !c->fused && tail_bytes >= (uint64_t(4) << 20) && g.OT >= 8 &&
+                   ((g.XA == 1 && g.OB == 8) || (g.XA == 2 && g.OB == 4)) && (int) log2m <= (c->dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m) &&
+                   c->mh_stages >= 2;
+    }
     c->r_full = make_range(0, g.P, sms * per_sm);
     c->r_head = make_range(0, g.P ? 1 : 0, sms);
     c->r_tail = make_range(1, g.P ? g.P - 1 : 0, (sms - reserve) * per_sm);
@@ -265,7 +279,7 @@ void free_device(hb_conv *c)
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = c->d_tw = nullptr;
     c->d_S.release();
     c->d_St[0].release(); c->d_St[1].release(); c->d_trace.release();
-    c->big.release(); c->d_nyq.release();
+    c->big.release(); c->d_nyq.release(); c->d_Smh.release();
     if (c->s_tail) cudaStreamDestroy(c->s_tail);
     if (c->ev_fwd) cudaEventDestroy(c->ev_fwd);
     for (int k = 0; k < 2; k++) if (c->ev_tail[k]) cudaEventDestroy(c->ev_tail[k]);
@@ -391,6 +405,35 @@ int launch_cmac(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t s
         case 8 * 16 + 1: return launch_cmac_inst<T, 8, 1>(c, r, S, variant, st);
     }
     set_error("internal: no multiply-accumulate kernel for XA=%u OB=%u", c->g.XA, c->g.OB);
+    return HB_ERR_UNSUPPORTED;
+}
+
+template <class T, int XA, int OB, int NH>
+int launch_cmac_mh_inst(hb_conv *c, const Range &r, void *S, uint64_t set_stride, cudaStream_t st)
+{
+    typedef typename VecOf<T>::type V;
+    const Geom &g = c->g;
+    const size_t smem = size_t(c->mh_stages) * size_t(g.Q + NH * g.TBV) * 16 + size_t(c->mh_stages) * 8;
+    int rc = allow_smem(k_cmac_tma_mh<T, XA, OB, NH>, smem);
+    if (rc) return rc;
+    k_cmac_tma_mh<T, XA, OB, NH><<<r.G, 256, smem, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, c->mh_stages, set_stride);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+// NH (2 or 4) hops over one pass of the IR spectra; S holds NH partial-segment sets set_stride vectors apart
+template <class T>
+int launch_cmac_mh(hb_conv *c, const Range &r, void *S, int nh, uint64_t set_stride, cudaStream_t st)
+{
+    const uint32_t key = (c->g.XA * 16 + c->g.OB) * 8 + (uint32_t) nh;
+    switch (key)
+    {
+        case (1 * 16 + 8) * 8 + 2: return launch_cmac_mh_inst<T, 1, 8, 2>(c, r, S, set_stride, st);
+        case (1 * 16 + 8) * 8 + 4: return launch_cmac_mh_inst<T, 1, 8, 4>(c, r, S, set_stride, st);
+        case (2 * 16 + 4) * 8 + 2: return launch_cmac_mh_inst<T, 2, 4, 2>(c, r, S, set_stride, st);
+        case (2 * 16 + 4) * 8 + 4: return launch_cmac_mh_inst<T, 2, 4, 4>(c, r, S, set_stride, st);
+    }
+    set_error("internal: no multi-hop kernel for XA=%u OB=%u NH=%d", c->g.XA, c->g.OB, nh);
     return HB_ERR_UNSUPPORTED;
 }
 
@@ -688,6 +731,7 @@ int do_reset(hb_conv *c, cudaStream_t st)
     // a tail launched ahead for a hop that will not come any more may still be running on its stream
     if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));
     c->tail_valid = false;
+    c->tail_missing = false;
     plan_geometry(c);
     const Geom &g = c->g;
     int rc = c->d_S.ensure(std::max<size_t>((size_t(std::max(c->r_full.G, c->r_head.G)) + g.tiles) * g.Q * 16, 16));
@@ -777,6 +821,28 @@ int profile_begin_hop(hb_conv *c, cudaEvent_t **out)
     return HB_OK;
 }
 
+// Overlapped schedule: launch the tail of the NEXT hop on the tail stream.  It needs nothing newer than the spectrum at
+// c->g.slot (just written on st): its frame will go to slot - 1, so partition p meets slot - 1 + p -- the newest spectrum
+// at p = 1, the oldest one kept at p = P - 1.  Leaves tail_par / tail_valid describing that launch.
+template <class T>
+int launch_tail_ahead(hb_conv *c, cudaStream_t st, cudaEvent_t *pe)
+{
+    int r;
+    HB_CUDA(cudaEventRecord(c->ev_fwd, st));
+    const int np = c->tail_par ^ 1;
+    Range rt = c->r_tail;
+    rt.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
+    rt.kind = 2;
+    HB_CUDA(cudaStreamWaitEvent(c->s_tail, c->ev_fwd, 0));
+    if (pe) { HB_CUDA(cudaEventRecord(pe[5], c->s_tail)); c->ev_has_tail[c->ev_used - 1] = 1; }
+    if ((r = launch_cmac<T>(c, rt, c->d_St[np].p, c->variant, c->s_tail))) return r;
+    if (pe) HB_CUDA(cudaEventRecord(pe[6], c->s_tail));
+    HB_CUDA(cudaEventRecord(c->ev_tail[np], c->s_tail));
+    c->tail_par = np;
+    c->tail_valid = true;
+    return HB_OK;
+}
+
 // One hop: forward FFTs of the newest frame, multiply-accumulate, inverse FFTs (PartitionedConvolve.cpp:352-377).
 // Serial schedule: the three kernels in a row on st.  Overlapped schedule: see hb_conv::schedule.
 template <class T>
@@ -812,18 +878,23 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     }
     else
     {
-        // fork: the tail of the NEXT hop needs nothing newer than the spectrum just written.  Its frame will go to
-        // slot - 1, so partition p meets slot - 1 + p: this hop's spectrum at p = 1, the oldest one kept at p = P - 1.
-        HB_CUDA(cudaEventRecord(c->ev_fwd, st));
-        const int np = c->tail_par ^ 1;
-        Range rt = c->r_tail;
-        rt.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
-        rt.kind = 2;
-        HB_CUDA(cudaStreamWaitEvent(c->s_tail, c->ev_fwd, 0));
-        if (pe) { HB_CUDA(cudaEventRecord(pe[5], c->s_tail)); c->ev_has_tail[c->ev_used - 1] = 1; }
-        if ((r = launch_cmac<T>(c, rt, c->d_St[np].p, c->variant, c->s_tail))) return r;
-        if (pe) HB_CUDA(cudaEventRecord(pe[6], c->s_tail));
-        HB_CUDA(cudaEventRecord(c->ev_tail[np], c->s_tail));
+        // fork: the tail of the NEXT hop (launch_tail_ahead)
+        const bool had_tail = c->tail_valid;
+        const int old_par = c->tail_par;
+        if ((r = launch_tail_ahead<T>(c, st, pe))) return r;
+        if (c->tail_missing)
+        {
+            // the hop after a multi-hop batch: its tail was not computed ahead, so it runs all partitions itself
+            c->tail_missing = false;
+            Range rf = c->r_full;
+            rf.slot = c->g.slot; rf.kind = 2;
+            if ((r = launch_cmac<T>(c, rf, c->d_S.p, c->variant, st))) return r;
+            if (pe) { HB_CUDA(cudaEventRecord(pe[2], st)); HB_CUDA(cudaEventRecord(pe[3], st)); }
+            sets.n = 1;
+            sets.s[0].S = c->d_S.p; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
+        }
+        else
+        {
         // critical path: partition 0 against the newest spectrum (direct loads: no shared memory, so its CTAs fit
         // beside the tail's on every SM)
         Range rh = c->r_head;
@@ -833,15 +904,14 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
         sets.n = 1;
         sets.s[0].S = c->d_S.p; sets.s[0].U = rh.U; sets.s[0].upt = rh.upt; sets.s[0].G = rh.G;
         // join: the tail of THIS hop was launched during the previous one
-        if (c->tail_valid)
+        if (had_tail)
         {
-            HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
+            HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[old_par], 0));
             sets.n = 2;
-            sets.s[1].S = c->d_St[c->tail_par].p; sets.s[1].U = c->r_tail.U; sets.s[1].upt = c->r_tail.upt; sets.s[1].G = c->r_tail.G;
+            sets.s[1].S = c->d_St[old_par].p; sets.s[1].U = c->r_tail.U; sets.s[1].upt = c->r_tail.upt; sets.s[1].G = c->r_tail.G;
         }
         if (pe) HB_CUDA(cudaEventRecord(pe[3], st));
-        c->tail_par = np;
-        c->tail_valid = true;
+        }
     }
     if ((r = launch_inv<T>(c, sets, io, st, peer))) return r;
     if (pe) HB_CUDA(cudaEventRecord(pe[4], st));
@@ -879,7 +949,8 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
         const int cur = c->cur, nxt = cur ^ 1;
         const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
         const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
-        for (size_t h = 0; h < nh; h++)
+        // where hop h of this call reads its frame and leaves its block
+        auto inv_io = [&](size_t h) -> InvIO<T>
         {
             const bool first = h == 0, last = h + 1 == nh;
             InvIO<T> io;
@@ -887,9 +958,57 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
             io.add_result = last ? 0 : accumulate;
             io.carry_src = first ? y_keep : nullptr; io.carry_src_ld = c->yout_ld;
             io.carry_dst = (first && d_out) ? d_out : nullptr; io.carry_dst_ld = out_ld; io.add_carry = accumulate;
-            rc = hop(first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
-                     last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, io);
-            if (rc) return rc;
+            return io;
+        };
+        size_t h = 0;
+        while (h < nh)
+        {
+            const size_t left = nh - h;
+            const int nb = (c->mh_ok && left >= 4) ? 4 : ((c->mh_ok && left >= 2) ? 2 : 1);
+            if (nb == 1)
+            {
+                const bool first = h == 0, last = h + 1 == nh;
+                rc = hop(first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                         last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, inv_io(h));
+                if (rc) return rc;
+                h++;
+                continue;
+            }
+            // ---- multi-hop reuse: nb hops over ONE pass of the IR spectra (k_cmac_tma_mh) ----
+            // a tail launched ahead for the first of these hops is not used: the batch covers all partitions itself
+            if (c->split && c->tail_valid) HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
+            c->tail_valid = false;
+            uint32_t slots[MH_MAX];
+            for (int j = 0; j < nb; j++)
+            {
+                const size_t hh = h + j;
+                const bool first = hh == 0, last = hh + 1 == nh;
+                c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
+                c->g.hop++;
+                c->g.trace = (unsigned long long *) c->d_trace.p;
+                slots[j] = c->g.slot;
+                if ((rc = launch_fwd<T>(c, first ? x_keep : d_in + (hh - 1) * B, first ? c->xin_ld : in_ld, d_in + hh * B, in_ld,
+                                        last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st))) return rc;
+            }
+            Range rf = c->r_full;
+            rf.slot = slots[0]; rf.kind = 2;
+            const uint64_t set_stride = uint64_t(rf.G + c->g.tiles) * c->g.Q;
+            if ((rc = c->d_Smh.ensure(size_t(MH_MAX) * set_stride * 16))) return rc;
+            if ((rc = launch_cmac_mh<T>(c, rf, c->d_Smh.p, nb, set_stride, st))) return rc;
+            for (int j = 0; j < nb; j++)
+            {
+                SegSets sets;
+                memset(&sets, 0, sizeof(sets));
+                sets.n = 1;
+                sets.s[0].S = (const char *) c->d_Smh.p + size_t(j) * set_stride * 16; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
+                c->g.slot = slots[j];                               // the Nyquist products of hop j run from its own newest slot
+                if ((rc = launch_inv<T>(c, sets, inv_io(h + j), st))) return rc;
+            }
+            c->g.slot = slots[nb - 1];
+            // nothing is launched ahead for the hop after a batch (the next call is most likely another batch, which
+            // would discard it): a following single hop of the overlapped schedule runs all its partitions itself
+            if (c->split) c->tail_missing = true;
+            h += nb;
         }
         c->cur = nxt;
         c->x_tail = c->y_tail = 0;
@@ -1460,6 +1579,15 @@ extern "C" int hb_conv_set_schedule(hb_conv *c, int overlapped)
     if (overlapped < 0 || overlapped > 3) { set_error("schedule must be 0 (serial), 1 (overlapped), 2 (automatic) or 3 (fused where eligible)"); return HB_ERR_BAD_ARG; }
     c->schedule = overlapped;
     c->need_reset = true;           // the partial-segment sets depend on the schedule
+    return HB_OK;
+}
+
+extern "C" int hb_conv_set_multi_hop(hb_conv *c, int enable)
+{
+    if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    c->multi_hop = enable ? 1 : 0;
+    c->need_reset = true;
     return HB_OK;
 }
 

@@ -318,6 +318,127 @@ __global__ void HB_CMAC_BOUNDS k_cmac_tma(const Geom g, const Range rg, const ty
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_cmac_tma_mh: the TMA variant for NH consecutive hops in ONE pass over the impulse-response spectra ("multi-hop
+// reuse").  A call that brings several hops at once (numSamples >= 2B) has all their input spectra in the delay line
+// before any output is needed, so every IR unit is streamed from HBM once and multiplied into NH accumulator sets:
+// hop j (0 = oldest) of partition p meets slot rg.slot - j + p.  The kernel stays HBM-bound up to NH = 4 (8 x NH x 8
+// FMAs per thread and unit against 1290 cycles of unit transfer time), i.e. NH hops cost about one.
+// shared memory: nstages * (Q + NH * TBV) vectors, then nstages mbarriers.  Partials: S[hop][cta + tile][row][TBV].
+// ---------------------------------------------------------------------------------------------
+template <class T, int XA, int OB, int NH>
+__global__ void __launch_bounds__(256, 1) k_cmac_tma_mh(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
+                                                        const typename VecOf<T>::type *__restrict__ X,
+                                                        typename VecOf<T>::type *__restrict__ S, const int nstages, const uint64_t set_stride)
+{
+    typedef typename VecOf<T>::type V;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t stage_vecs = g.Q + NH * g.TBV;
+    V *ring = reinterpret_cast<V *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(nstages) * stage_vecs * sizeof(V));
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tx = tid % g.TX, ty = tid / g.TX;
+    const bool active = ty < g.TY;
+    trace_mark(g, rg.kind, 0);
+
+    const uint64_t u0 = unit_begin(blockIdx.x, rg.U, rg.G), u1 = unit_begin(blockIdx.x + 1, rg.U, rg.G);
+    const uint32_t n = (uint32_t) (u1 - u0);
+
+    if (tid == 0)
+    {
+        for (int s = 0; s < nstages; s++) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    Cursor prod;
+    uint64_t pol_h = 0, pol_x = 0;
+    uint32_t issued = 0;
+    const uint32_t h_bytes = g.Q * (uint32_t) sizeof(V), x_bytes = g.TBV * (uint32_t) sizeof(V);
+    // one stage = the IR unit and the FDL tiles of the NH hops that meet it
+    auto issue = [&](uint32_t st)
+    {
+        V *dst = ring + size_t(st) * stage_vecs;
+        mbar_expect_tx(&full[st], h_bytes + NH * x_bytes);
+        bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[st], pol_h);
+        const uint64_t x0 = prod.x_off(g, rg);                       // hop 0: slot rg.slot + p
+        uint32_t s = rg.slot + prod.p;
+        if (s >= g.R) s -= g.R;
+#pragma unroll
+        for (int j = 0; j < NH; j++)
+        {
+            // slot of hop j: s - j (mod R); the tiles of one (group, in, bin-tile) are TBV apart per slot
+            const uint32_t sj = s >= (uint32_t) j ? s - j : s + g.R - j;
+            bulk_g2s(dst + g.Q + j * g.TBV, X + x0 + (int64_t(sj) - int64_t(s)) * g.TBV, x_bytes, &full[st], pol_x);
+        }
+        prod.advance(g, rg);
+        issued++;
+    };
+    if (tid == 0)
+    {
+        pol_h = l2_policy_evict_first();
+        pol_x = l2_policy_evict_last();
+        prod.seek(rg, u0);
+        while (issued < n && issued + 1 < (uint32_t) nstages) issue(issued);
+    }
+
+    Cursor cons;
+    cons.seek(rg, u0);
+    V acc[NH][XA * OB];
+#pragma unroll
+    for (int j = 0; j < NH; j++)
+#pragma unroll
+        for (int r = 0; r < XA * OB; r++) vzero(acc[j][r]);
+
+    uint32_t stage = 0, parity = 0;
+    for (uint32_t k = 0; k < n; k++)
+    {
+        if (tid == 0 && issued < n) issue(stage ? stage - 1 : nstages - 1);
+        mbar_wait(&full[stage], parity);
+        if (active)
+        {
+            const V *hs = ring + size_t(stage) * stage_vecs;
+            const V *xs = hs + g.Q;
+            V xv[NH][XA];
+#pragma unroll
+            for (int j = 0; j < NH; j++)
+#pragma unroll
+                for (int a = 0; a < XA; a++) xv[j][a] = xs[j * g.TBV + tx + g.TX * a];
+#pragma unroll
+            for (int b = 0; b < OB; b++)
+#pragma unroll
+                for (int a = 0; a < XA; a++)
+                {
+                    const V h = hs[(ty + g.TY * b) * g.TBV + tx + g.TX * a];
+#pragma unroll
+                    for (int j = 0; j < NH; j++) cmac(acc[j][b * XA + a], xv[j][a], h);
+                }
+        }
+        const uint32_t tile_done = cons.tile;
+        const bool last = cons.advance(g, rg) || (k + 1 == n);
+        if (last && active)
+        {
+#pragma unroll
+            for (int j = 0; j < NH; j++)
+            {
+                V *seg = S + uint64_t(j) * set_stride + (uint64_t(blockIdx.x) + tile_done) * g.Q;
+#pragma unroll
+                for (int b = 0; b < OB; b++)
+#pragma unroll
+                    for (int a = 0; a < XA; a++)
+                    {
+                        seg[(ty + g.TY * b) * g.TBV + tx + g.TX * a] = acc[j][b * XA + a];
+                        vzero(acc[j][b * XA + a]);
+                    }
+            }
+        }
+        if (++stage == (uint32_t) nstages) { stage = 0; parity ^= 1; }
+        __syncthreads();
+    }
+    trace_mark(g, rg.kind, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_cmac, variant "ldg": same decomposition, every thread loads its own vectors straight from global
 // memory (read-once, L1 bypass).  Kept as the comparison point for the TMA ring (profiles/).
 // ---------------------------------------------------------------------------------------------

@@ -184,6 +184,11 @@ int hb_conv_schedule(const hb_conv *c);
 /* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in
  * the overlapped one the tail's share, 2sB(P-1)(K+I) */
 uint64_t hb_conv_bytes_per_launch(const hb_conv *c);
+/* Multi-hop reuse (default on): a hop-aligned call that brings several hops at once (numSamples >= 2 * fft_size / 2) has all
+ * their input spectra in the delay line before any output is needed, so HBM-bound engines stream every impulse-response
+ * spectrum ONCE for up to four hops (k_cmac_tma_mh) instead of once per hop.  Same result up to summation order;
+ * enable = 0 processes such calls hop by hop.  Takes effect with a reset. */
+int hb_conv_set_multi_hop(hb_conv *c, int enable);
 /* Kernel timeline (debug): while enabled, thread 0 of every CTA of the hop kernels stamps %globaltimer at entry
  * and exit.  hb_conv_get_trace synchronises the device and copies the HB_TRACE_WORDS stamps out:
  * out[(((hop % 16) * 5 + kind) * 2 + exit) * 256 + cta], kind 0 forward FFT, 1 head, 2 tail / whole

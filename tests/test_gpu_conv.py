@@ -168,6 +168,48 @@ def test_fused_hop_against_serial_and_truth(hb, dtype, ins, groups, B, L):
         assert ck.rel_rms(outs["auto"][g], truth) <= tol * (1 if dtype == np.float32 else 10)
 
 
+@pytest.mark.parametrize("dtype,schedule", [(np.float32, None), (np.float32, False), (np.float64, None)])
+def test_multi_hop_reuse_matches_hop_by_hop(hb, dtype, schedule):
+    """Calls that bring several hops at once run batches of 4 / 2 hops over one pass of the IR spectra (k_cmac_tma_mh) on
+    HBM-bound engines: a 4-in x 16-out matrix with 32 partitions, call sizes of 7, 3, 1, 4, 2 ... hops mixed with ragged
+    calls, against the same engine with the batching off (summation order only) and float64 direct convolution; with the
+    overlapped schedule around the batches (tail launched ahead after a batch, discarded before one) and the serial one."""
+    from hisstools_library_b200.convolve import _Engine
+    n_in, n_out, B = 4, 16, 256
+    L = 32 * B
+    tol = TOL32 if dtype == np.float32 else TOL64
+    rng = np.random.default_rng(99)
+    irs = (rng.standard_normal((n_out, n_in, L)) * np.exp(-6.9 * np.arange(L) / L)).astype(dtype)
+    calls = [7 * B, B, 3 * B, 100, B - 100, 4 * B, 2 * B, B, 9 * B, 5, 6 * B + 5 - 10, 5, 8 * B]
+    n = sum(calls)
+    xs = np.stack([ck.synth_audio(n, 800 + i) for i in range(n_in)]).astype(dtype)
+    outs = {}
+    for mh in (True, False):
+        e = _Engine(dtype, 1, n_in, n_out, 2 * B, L, 0, 0, 0)
+        e.set_schedule(schedule)
+        e.set_multi_hop(mh)
+        e.set_reset_offset(0)
+        for o in range(n_out):
+            for i in range(n_in):
+                e.set_ir(0, i, o, irs[o, i], L)
+        y = np.zeros((n_out, n), dtype)
+        pos = 0
+        for m in calls:
+            yo = [np.zeros(m, dtype) for _ in range(n_out)]
+            e.process([np.ascontiguousarray(xs[r, pos:pos + m]) for r in range(n_in)], yo, m)
+            for o in range(n_out):
+                y[o, pos:pos + m] = yo[o]
+            pos += m
+        assert e.schedule == ("overlapped" if schedule is None else "serial")
+        outs[mh] = y
+        e.close()
+    for o in range(n_out):
+        assert ck.rel_rms(outs[True][o], outs[False][o]) <= tol / 5
+    for o in (0, 7, 15):
+        truth = sum(ck.direct_convolve_delayed_fft(irs[o, i], xs[i], B) for i in range(n_in))
+        assert ck.rel_rms(outs[True][o], truth) <= tol * (1 if dtype == np.float32 else 10)
+
+
 def test_pconv_call_sizes_do_not_matter(hb):
     """any chunking of the stream gives the same samples (SURVEY B: bit-identical in the reference)."""
     ir = ck.synth_ir(3000, 1)
