@@ -19,8 +19,11 @@ Printed JSON (one line, rank 0):
              max over ranks
   e2e        the same metric through the host-pointer C-ABI call (hb_conv_process; host<->device
              copies inside the timed region)
-  roofline   the multiply-accumulate kernel: algorithmic bytes per launch / its mean launch
-             duration measured with CUDA events inside the library, against MEASURED_PEAKS.json
+  roofline   the dominant multiply-accumulate launch (the tail launch of the overlapped schedule):
+             its algorithmic bytes / its mean duration measured with CUDA events inside the library on the
+             stream it is launched on, against MEASURED_PEAKS.json; hop_frac = bytes per hop / whole hop period
+  multi_hop_reuse  the same engine fed 4 blocks per call (every IR spectrum read once per call): reported
+             separately, the per-hop byte figure does not apply to it
   cpu_baseline  the unmodified reference (oracle/_ref, compiled from /root/reference by oracle/Makefile)
              timed on this box's host cores on a bounded sample of the same workload (rank 0, N = 1)
 
