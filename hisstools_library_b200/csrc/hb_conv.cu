@@ -416,7 +416,7 @@ int launch_cmac_mh_inst(hb_conv *c, const Range &r, void *S, uint64_t set_stride
     const size_t smem = size_t(c->mh_stages) * size_t(g.Q + NH * g.TBV) * 16 + size_t(c->mh_stages) * 8;
     int rc = allow_smem(k_cmac_tma_mh<T, XA, OB, NH>, smem);
     if (rc) return rc;
-    k_cmac_tma_mh<T, XA, OB, NH><<<r.G, 256, smem, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, c->mh_stages, set_stride);
+    k_cmac_tma_mh<T, XA, OB, NH><<<r.G, 288, smem, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, c->mh_stages, set_stride);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }

@@ -326,7 +326,7 @@ __global__ void HB_CMAC_BOUNDS k_cmac_tma(const Geom g, const Range rg, const ty
 // shared memory: nstages * (Q + NH * TBV) vectors, then nstages mbarriers.  Partials: S[hop][cta + tile][row][TBV].
 // ---------------------------------------------------------------------------------------------
 template <class T, int XA, int OB, int NH>
-__global__ void __launch_bounds__(256, 1) k_cmac_tma_mh(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
+__global__ void __launch_bounds__(288, 1) k_cmac_tma_mh(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
                                                         const typename VecOf<T>::type *__restrict__ X,
                                                         typename VecOf<T>::type *__restrict__ S, const int nstages, const uint64_t set_stride)
 {
@@ -336,9 +336,12 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma_mh(const Geom g, const Rang
     V *ring = reinterpret_cast<V *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(nstages) * stage_vecs * sizeof(V));
 
+    // 8 consumer warps (the thread grid of the single-hop kernel) + 1 producer warp whose lane 0 issues the copies, so
+    // that the address arithmetic of the NH + 1 copies of a stage runs beside the arithmetic instead of in front of it
     const uint32_t tid = threadIdx.x;
+    const bool producer = tid >= 256;
     const uint32_t tx = tid % g.TX, ty = tid / g.TX;
-    const bool active = ty < g.TY;
+    const bool active = !producer && ty < g.TY;
     trace_mark(g, rg.kind, 0);
 
     const uint64_t u0 = unit_begin(blockIdx.x, rg.U, rg.G), u1 = unit_begin(blockIdx.x + 1, rg.U, rg.G);
@@ -355,7 +358,9 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma_mh(const Geom g, const Rang
     uint64_t pol_h = 0, pol_x = 0;
     uint32_t issued = 0;
     const uint32_t h_bytes = g.Q * (uint32_t) sizeof(V), x_bytes = g.TBV * (uint32_t) sizeof(V);
-    // one stage = the IR unit and the FDL tiles of the NH hops that meet it
+    // one stage = the IR unit and the FDL tiles of the NH hops that meet it.  Hop j reads slot s - j (mod R): the NH tiles
+    // are adjacent in memory (ascending from hop NH - 1 to hop 0) unless the ring wraps inside them, so they normally
+    // arrive as one copy; shared-memory order is therefore hop NH - 1 first.
     auto issue = [&](uint32_t st)
     {
         V *dst = ring + size_t(st) * stage_vecs;
@@ -364,17 +369,21 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma_mh(const Geom g, const Rang
         const uint64_t x0 = prod.x_off(g, rg);                       // hop 0: slot rg.slot + p
         uint32_t s = rg.slot + prod.p;
         if (s >= g.R) s -= g.R;
-#pragma unroll
-        for (int j = 0; j < NH; j++)
+        if (s >= uint32_t(NH - 1))
+            bulk_g2s(dst + g.Q, X + x0 - uint64_t(NH - 1) * g.TBV, NH * x_bytes, &full[st], pol_x);
+        else
         {
-            // slot of hop j: s - j (mod R); the tiles of one (group, in, bin-tile) are TBV apart per slot
-            const uint32_t sj = s >= (uint32_t) j ? s - j : s + g.R - j;
-            bulk_g2s(dst + g.Q + j * g.TBV, X + x0 + (int64_t(sj) - int64_t(s)) * g.TBV, x_bytes, &full[st], pol_x);
+#pragma unroll
+            for (int j = 0; j < NH; j++)
+            {
+                const uint32_t sj = s >= (uint32_t) j ? s - j : s + g.R - j;
+                bulk_g2s(dst + g.Q + (NH - 1 - j) * g.TBV, X + x0 + (int64_t(sj) - int64_t(s)) * g.TBV, x_bytes, &full[st], pol_x);
+            }
         }
         prod.advance(g, rg);
         issued++;
     };
-    if (tid == 0)
+    if (tid == 256)
     {
         pol_h = l2_policy_evict_first();
         pol_x = l2_policy_evict_last();
@@ -393,43 +402,50 @@ __global__ void __launch_bounds__(256, 1) k_cmac_tma_mh(const Geom g, const Rang
     uint32_t stage = 0, parity = 0;
     for (uint32_t k = 0; k < n; k++)
     {
-        if (tid == 0 && issued < n) issue(stage ? stage - 1 : nstages - 1);
-        mbar_wait(&full[stage], parity);
-        if (active)
+        if (producer)
         {
-            const V *hs = ring + size_t(stage) * stage_vecs;
-            const V *xs = hs + g.Q;
-            V xv[NH][XA];
-#pragma unroll
-            for (int j = 0; j < NH; j++)
-#pragma unroll
-                for (int a = 0; a < XA; a++) xv[j][a] = xs[j * g.TBV + tx + g.TX * a];
-#pragma unroll
-            for (int b = 0; b < OB; b++)
-#pragma unroll
-                for (int a = 0; a < XA; a++)
-                {
-                    const V h = hs[(ty + g.TY * b) * g.TBV + tx + g.TX * a];
-#pragma unroll
-                    for (int j = 0; j < NH; j++) cmac(acc[j][b * XA + a], xv[j][a], h);
-                }
+            // stage (k + nstages - 1) % nstages was drained in step k-1 (barrier at the end of that step)
+            if (tid == 256 && issued < n) issue(stage ? stage - 1 : nstages - 1);
         }
-        const uint32_t tile_done = cons.tile;
-        const bool last = cons.advance(g, rg) || (k + 1 == n);
-        if (last && active)
+        else
         {
-#pragma unroll
-            for (int j = 0; j < NH; j++)
+            mbar_wait(&full[stage], parity);
+            if (active)
             {
-                V *seg = S + uint64_t(j) * set_stride + (uint64_t(blockIdx.x) + tile_done) * g.Q;
+                const V *hs = ring + size_t(stage) * stage_vecs;
+                const V *xs = hs + g.Q;
+                V xv[NH][XA];
+#pragma unroll
+                for (int j = 0; j < NH; j++)
+#pragma unroll
+                    for (int a = 0; a < XA; a++) xv[j][a] = xs[(NH - 1 - j) * g.TBV + tx + g.TX * a];
 #pragma unroll
                 for (int b = 0; b < OB; b++)
 #pragma unroll
                     for (int a = 0; a < XA; a++)
                     {
-                        seg[(ty + g.TY * b) * g.TBV + tx + g.TX * a] = acc[j][b * XA + a];
-                        vzero(acc[j][b * XA + a]);
+                        const V h = hs[(ty + g.TY * b) * g.TBV + tx + g.TX * a];
+#pragma unroll
+                        for (int j = 0; j < NH; j++) cmac(acc[j][b * XA + a], xv[j][a], h);
                     }
+            }
+            const uint32_t tile_done = cons.tile;
+            const bool last = cons.advance(g, rg) || (k + 1 == n);
+            if (last && active)
+            {
+#pragma unroll
+                for (int j = 0; j < NH; j++)
+                {
+                    V *seg = S + uint64_t(j) * set_stride + (uint64_t(blockIdx.x) + tile_done) * g.Q;
+#pragma unroll
+                    for (int b = 0; b < OB; b++)
+#pragma unroll
+                        for (int a = 0; a < XA; a++)
+                        {
+                            seg[(ty + g.TY * b) * g.TBV + tx + g.TX * a] = acc[j][b * XA + a];
+                            vzero(acc[j][b * XA + a]);
+                        }
+                }
             }
         }
         if (++stage == (uint32_t) nstages) { stage = 0; parity ^= 1; }
