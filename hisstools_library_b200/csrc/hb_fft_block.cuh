@@ -94,26 +94,26 @@ __device__ __forceinline__ void block_real_split(Cx<T> *s, uint32_t M, int log2N
 // transform) copied from the device table into shared memory, EPT per thread.  The loads are returned in
 // registers so that the caller can issue them together with its own input loads and store later.
 template <class T, int EPT>
-__device__ __forceinline__ void twiddle_stage_load(Cx<T> *r, const Cx<T> *__restrict__ tw, int tw_log2, int log2n)
+__device__ __forceinline__ void twiddle_stage_load(Cx<T> *r, const Cx<T> *__restrict__ tw, int tw_log2, int log2n, int quarter = 0)
 {
-    const uint32_t half = 1u << (log2n - 1);
+    const uint32_t count = (1u << (log2n - 1)) >> (quarter ? 1 : 0);
     const int sh = tw_log2 - log2n;
 #pragma unroll
     for (int e = 0; e < EPT; e++)
     {
         const uint32_t q = threadIdx.x + e * blockDim.x;
-        if (q < half) r[e] = tw[size_t(q) << sh];
+        if (q < count) r[e] = tw[size_t(q) << sh];
     }
 }
 template <class T, int EPT>
-__device__ __forceinline__ void twiddle_stage_store(Cx<T> *stw, const Cx<T> *r, int log2n)
+__device__ __forceinline__ void twiddle_stage_store(Cx<T> *stw, const Cx<T> *r, int log2n, int quarter = 0)
 {
-    const uint32_t half = 1u << (log2n - 1);
+    const uint32_t count = (1u << (log2n - 1)) >> (quarter ? 1 : 0);
 #pragma unroll
     for (int e = 0; e < EPT; e++)
     {
         const uint32_t q = threadIdx.x + e * blockDim.x;
-        if (q < half) stw[q] = r[e];
+        if (q < count) stw[q] = r[e];
     }
 }
 
