@@ -72,6 +72,7 @@ SIGNATURES = {
     "hb_spectral_convolved_size": (UP, [V, UP, UP, C.c_int]),
     "hb_spectral_convolve": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_spectral_correlate": (C.c_int, [V, V, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
+    "hb_spectral_change_phase": (C.c_int, [V, V, V, UP, C.c_double, C.c_double, C.POINTER(UP)]),
     "hb_spectral_convolve_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_spectral_correlate_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_audio_probe": (C.c_int, [C.c_char_p, V]),

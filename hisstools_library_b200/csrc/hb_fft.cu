@@ -365,6 +365,26 @@ static int launch_rifft(const T *re_in, const T *im_in, T *re_out, T *im_out, si
     return HB_OK;
 }
 
+// real transforms on split planes in device memory for other translation units (hb_spectral.cu): forward from a real
+// array x (zero-padded from in_length; x == nullptr: in place on the planes), inverse to the planes and / or an
+// interleaved real array y
+int rfft_planes(int dtype, const void *x, size_t in_length, void *re, void *im, int log2n, const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs)
+{
+    if (dtype == HB_F64)
+        return launch_rfft<double, double>((const double *) x, in_length, 0, (const double *) re, (const double *) im, (double *) re, (double *) im, 0, log2n, 1,
+                                           (const Cx<double> *) tw, tw_log2, st, bs);
+    return launch_rfft<float, float>((const float *) x, in_length, 0, (const float *) re, (const float *) im, (float *) re, (float *) im, 0, log2n, 1,
+                                     (const Cx<float> *) tw, tw_log2, st, bs);
+}
+int rifft_planes(int dtype, void *re, void *im, void *y, int log2n, const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs)
+{
+    if (dtype == HB_F64)
+        return launch_rifft<double>((const double *) re, (const double *) im, (double *) re, (double *) im, 0, (double *) y, 0, log2n, 1,
+                                    (const Cx<double> *) tw, tw_log2, st, bs);
+    return launch_rifft<float>((const float *) re, (const float *) im, (float *) re, (float *) im, 0, (float *) y, 0, log2n, 1,
+                               (const Cx<float> *) tw, tw_log2, st, bs);
+}
+
 } // namespace hb
 
 // ---------------------------------------------------------------------------------------------

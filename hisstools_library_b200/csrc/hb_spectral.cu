@@ -23,6 +23,8 @@ namespace hb
 {
 int cfft_planes(int dtype, const void *re_in, const void *im_in, void *re_out, void *im_out, int log2n, int swap, size_t batch, size_t stride,
                 const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs);          // hb_fft.cu
+int rfft_planes(int dtype, const void *x, size_t in_length, void *re, void *im, int log2n, const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs);
+int rifft_planes(int dtype, void *re, void *im, void *y, int log2n, const void *tw, int tw_log2, cudaStream_t st, BigScratch *bs);
 }
 
 namespace
@@ -223,6 +225,71 @@ __global__ void k_cspec_arrange(const SpecGeom g, const T *__restrict__ planes, 
     T *dst = out + size_t(blockIdx.y) * g.arr.result;
     auto lin = [&](uint32_t i) -> T { return src[i]; };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.arr.result; i += gridDim.x * blockDim.x) dst[i] = arrange_eval(g.arr, i, lin);
+}
+
+// ---- change_phase: per-bin stages of ir_phase (SpectralFunctions.hpp:283-336, 405-418) on the packed half spectrum ----
+// planes re / im of fft/2 bins; bin 0 carries DC in re[0] and Nyquist in im[0], both handled as real values with a zero
+// imaginary part (real_operation, :86-108).  stage: 0 log of the power spectrum (:177-185), 1 causal window of the real
+// cepstrum (:307-327), 2 exponential (:187-195), 3 interpolated phase (:209-230), 4 linear-phase amplitude (:158-165).
+struct PhaseArgs { uint32_t half; int stage; double scale, min_factor, lin_factor; };
+
+template <class T>
+__global__ void k_phase_stage(const PhaseArgs a, T *__restrict__ re, T *__restrict__ im)
+{
+    const uint32_t fft = a.half * 2;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.half; i += gridDim.x * blockDim.x)
+    {
+        const T r = re[i], m = im[i];
+        T ro, mo;
+        switch (a.stage)
+        {
+            case 0:
+            {
+                const T min_power = (T) 1e-30;                                     // pow(10, -300 / 10)
+                if (i == 0) { ro = T(0.5) * log(max(r * r, min_power)); mo = T(0.5) * log(max(m * m, min_power)); }
+                else { ro = T(0.5) * log(max(r * r + m * m, min_power)); mo = T(0); }
+                break;
+            }
+            case 1:
+            {
+                // sequential semantics of :312-327 (for fft = 2 the first and the third rule both hit bin 0)
+                const uint32_t q = fft >> 2;
+                ro = r; mo = m;
+                if (i == 0) { ro = ro * T(0.5 * a.scale); mo = mo * T(a.scale); }
+                if (i >= 1 && i < q) { ro = ro * T(a.scale); mo = mo * T(a.scale); }
+                if (i == q) { ro = ro * T(0.5 * a.scale); mo = T(0); }
+                if (i > q) { ro = T(0); mo = T(0); }
+                break;
+            }
+            case 2:
+                if (i == 0) { ro = exp(r); mo = exp(m); }
+                else { const T e = exp(r); T sn, cs; sincos(m, &sn, &cs); ro = e * cs; mo = e * sn; }
+                break;
+            case 3:
+                if (i == 0)
+                {
+                    ro = T(exp(double(r)));                                        // phase = lin * 0 + min * 0
+                    mo = T(exp(double(m)) * cos(a.lin_factor * double(fft >> 1)));
+                }
+                else
+                {
+                    const double amp = exp(double(r)), ph = a.lin_factor * double(i) + a.min_factor * double(m);
+                    ro = T(amp * cos(ph)); mo = T(amp * sin(ph));
+                }
+                break;
+            default:
+                if (i == 0) { ro = sqrt(r * r); mo = sqrt(m * m) * (((fft >> 1) & 1u) ? T(-1) : T(1)); }
+                else { ro = sqrt(r * r + m * m) * ((i & 1u) ? T(-1) : T(1)); mo = T(0); }
+                break;
+        }
+        re[i] = ro; im[i] = mo;
+    }
+}
+
+template <class T>
+__global__ void k_scale(T *__restrict__ y, size_t n, T scale)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) y[i] *= scale;
 }
 
 uint32_t ceil_log2(uintptr_t value)
@@ -456,6 +523,73 @@ int binary_complex(hb_spectral *s, T *r_out, T *i_out, const T *r1, uintptr_t nr
     return HB_OK;
 }
 
+// change_phase (SpectralProcessor.hpp:186-208): output receives fft_size samples
+template <class T>
+int change_phase(hb_spectral *s, T *output, const T *input, uintptr_t size, double phase, double time_multiplier, uintptr_t *written)
+{
+    if (written) *written = 0;
+    if (!size) return HB_OK;
+    if (size == 1) { output[0] = input[0]; if (written) *written = 1; return HB_OK; }
+    // calc_fft_size_log2(round(size * time_multiplier)) (:189, 229-240)
+    const uintptr_t target = (uintptr_t) std::llround(double(size) * time_multiplier);
+    uint32_t log2n = 0;
+    while (target >> log2n) log2n++;
+    if (log2n && target == (uintptr_t(1) << (log2n - 1))) log2n--;
+    if (log2n < 1 || log2n > s->max_log2)
+    {
+        set_error("hb_spectral_change_phase: FFT size 2^%u outside 2 .. the processor's maximum 2^%u", log2n, s->max_log2);
+        return HB_ERR_BAD_ARG;
+    }
+    const size_t n = size_t(1) << log2n, half = n >> 1, len = std::min<size_t>(size, n);
+    int rc;
+    if ((rc = s->d_in1.ensure(len * sizeof(T))) || (rc = s->d_planes.ensure(2 * half * sizeof(T))) || (rc = s->d_out.ensure(n * sizeof(T)))) return rc;
+    HB_CUDA(cudaMemcpyAsync(s->d_in1.p, input, len * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    T *re = (T *) s->d_planes.p, *im = re + half;
+    if ((rc = rfft_planes(s->dtype, s->d_in1.p, len, re, im, (int) log2n, s->tw, s->tw_log2, s->stream, &s->big))) return rc;
+    PhaseArgs a;
+    a.half = (uint32_t) half; a.scale = 1.0 / double(n); a.min_factor = 0; a.lin_factor = 0;
+    const unsigned blocks = (unsigned) std::min<size_t>((half + 255) / 256, 1024);
+    auto stage = [&](int st) -> int
+    {
+        a.stage = st;
+        k_phase_stage<T><<<blocks, 256, 0, s->stream>>>(a, re, im);
+        HB_LAUNCH_CHECK();
+        return HB_OK;
+    };
+    if (phase == 0.5)
+    {
+        if ((rc = stage(4))) return rc;                                          // ir_phase :407-413, zero_center = false
+    }
+    else
+    {
+        // minimum_phase_components (:283-336): log power -> real cepstrum -> causal window -> back to the spectrum
+        if ((rc = stage(0))) return rc;
+        if ((rc = rifft_planes(s->dtype, re, im, nullptr, (int) log2n, s->tw, s->tw_log2, s->stream, &s->big))) return rc;
+        if ((rc = stage(1))) return rc;
+        if ((rc = rfft_planes(s->dtype, nullptr, 0, re, im, (int) log2n, s->tw, s->tw_log2, s->stream, &s->big))) return rc;
+        if (phase == 0.0)
+        {
+            if ((rc = stage(2))) return rc;
+        }
+        else
+        {
+            // phase_interpolate (:199-230), zero_center = false
+            const double delay_factor = (phase <= 0.5) ? 0.0 : 1.0 / double(n);
+            const double ph = std::max(0.0, std::min(1.0, phase));
+            a.min_factor = 1.0 - 2.0 * ph;
+            a.lin_factor = -2.0 * M_PI * (ph - delay_factor);
+            if ((rc = stage(3))) return rc;
+        }
+    }
+    if ((rc = rifft_planes(s->dtype, re, im, s->d_out.p, (int) log2n, s->tw, s->tw_log2, s->stream, &s->big))) return rc;
+    k_scale<T><<<(unsigned) std::min<size_t>((n + 255) / 256, 1024), 256, 0, s->stream>>>((T *) s->d_out.p, n, T(0.5) / T(n));
+    HB_LAUNCH_CHECK();
+    HB_CUDA(cudaMemcpyAsync(output, s->d_out.p, n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HB_CUDA(cudaStreamSynchronize(s->stream));
+    if (written) *written = n;
+    return HB_OK;
+}
+
 int real_entry(hb_spectral *s, void *output, const void *in1, uintptr_t n1, const void *in2, uintptr_t n2, int mode, int op, uintptr_t *written, const char *who)
 {
     if (!s || mode < MODE_LINEAR || mode > MODE_FOLD_REPEAT || ((!output || !in1 || !in2) && n1 && n2))
@@ -555,4 +689,14 @@ extern "C" int hb_spectral_correlate_complex(hb_spectral *s, void *r_out, void *
                                              const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written)
 {
     return complex_entry(s, r_out, i_out, r_in1, nr1, i_in1, ni1, r_in2, nr2, i_in2, ni2, mode, 1, written, "hb_spectral_correlate_complex");
+}
+
+extern "C" int hb_spectral_change_phase(hb_spectral *s, void *output, const void *input, uintptr_t size, double phase, double time_multiplier, uintptr_t *written)
+{
+    if (!s || (size && (!output || !input))) { set_error("hb_spectral_change_phase: bad argument"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(s->lock);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return s->dtype == HB_F64 ? change_phase<double>(s, (double *) output, (const double *) input, size, phase, time_multiplier, written)
+                              : change_phase<float>(s, (float *) output, (const float *) input, size, phase, time_multiplier, written);
 }

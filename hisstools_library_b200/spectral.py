@@ -3,7 +3,7 @@
 Mirror of the reference's spectral_processor<T> (SpectralProcessor.hpp:11-683): same class name, `EdgeMode`
 values, `convolve` / `correlate` for real inputs (output, in1, in2, mode) and for complex inputs
 (r_out, i_out, r_in1, i_in1, r_in2, i_in2, mode), `convolved_size` / `correlated_size`,
-`set_max_fft_size` / `max_fft_size`.  change_phase is not provided.  The transforms, the
+`set_max_fft_size` / `max_fft_size`, `change_phase`.  The transforms, the
 per-bin product and the edge-mode arrangement run as CUDA kernels behind hb_spectral_* of
 include/hisstools_b200.h.
 """
@@ -95,3 +95,14 @@ class spectral_processor:
         if len(args) in (3, 4):
             return self._real(_abi.lib().hb_spectral_correlate, args[0], args[1], args[2], args[3] if len(args) == 4 else EdgeMode.Linear)
         return self._complex(_abi.lib().hb_spectral_correlate_complex, args[0], args[1], args[2:6], args[6])
+
+    def change_phase(self, output, input, size, phase, time_multiplier=1.0):
+        """change_phase (SpectralProcessor.hpp:186-208): output[:fft_size] = the input with its phase moved towards minimum
+        (phase 0), linear (0.5) or maximum (1) phase; returns the number of samples written (the FFT size)."""
+        x = np.ascontiguousarray(input, self.dtype)
+        if output.dtype != self.dtype or not output.flags["C_CONTIGUOUS"]:
+            raise ValueError("output must be a contiguous %s array" % self.dtype)
+        written = C.c_size_t(0)
+        _abi.check(_abi.lib().hb_spectral_change_phase(self._h, output.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), int(size),
+                                                       float(phase), float(time_multiplier), C.byref(written)))
+        return int(written.value)

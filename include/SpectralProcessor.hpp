@@ -2,8 +2,8 @@
 // spectral_processor<T> (SpectralProcessor.hpp:11-683): convolve and correlate for real inputs (T*, in_ptr, in_ptr,
 // EdgeMode) and complex inputs (T*, T*, in_ptr x 4, EdgeMode), convolved_size / correlated_size, set_max_fft_size /
 // max_fft_size.  The transforms, the per-bin products (SpectralFunctions.hpp:49-84, 265-281) and the edge-mode
-// arrangements (:445-538) run on the GPU through hb_spectral_* of hisstools_b200.h.  change_phase and the raw
-// fft / rfft members are not provided.
+// arrangements (:445-538) run on the GPU through hb_spectral_* of hisstools_b200.h, as does change_phase (:186-208).
+// The raw fft / rfft members are not provided (use HISSTools_FFT.h).
 #ifndef HISSTOOLS_B200_SPECTRALPROCESSOR_HPP
 #define HISSTOOLS_B200_SPECTRALPROCESSOR_HPP
 
@@ -75,6 +75,11 @@ public:
     }
 
     uintptr_t correlated_size(uintptr_t size1, uintptr_t size2, EdgeMode mode) const { return convolved_size(size1, size2, mode); }
+
+    void change_phase(T *output, const T *input, uintptr_t size, double phase, double time_multiplier = 1.0)
+    {
+        hisstools_b200_detail::check(hb_spectral_change_phase(m_handle, output, input, size, phase, time_multiplier, nullptr));
+    }
 
 private:
 

@@ -280,6 +280,12 @@ int hb_spectral_convolve_complex(hb_spectral *s, void *r_out, void *i_out, const
                                  const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written);
 int hb_spectral_correlate_complex(hb_spectral *s, void *r_out, void *i_out, const void *r_in1, uintptr_t nr1, const void *i_in1, uintptr_t ni1,
                                   const void *r_in2, uintptr_t nr2, const void *i_in2, uintptr_t ni2, int mode, uintptr_t *written);
+/* change_phase(T *output, const T *input, uintptr_t size, double phase, double time_multiplier = 1.0): SpectralProcessor.hpp:186-208
+ * with ir_phase and minimum_phase_components (SpectralFunctions.hpp:283-336, 405-418): phase 0 = minimum, 0.5 = linear,
+ * 1 = maximum phase version of the input.  output receives the FFT size (next power of two of round(size *
+ * time_multiplier)) samples; *written = that count.  Unlike the reference (which indexes past its setup) an FFT above the
+ * processor's maximum returns HB_ERR_BAD_ARG. */
+int hb_spectral_change_phase(hb_spectral *s, void *output, const void *input, uintptr_t size, double phase, double time_multiplier, uintptr_t *written);
 
 /* ---------------------------------------------------------------------------------------------
  * Impulse responses from WAV / AIFF / AIFC files -- replaces the reading half of the reference's AudioFile component

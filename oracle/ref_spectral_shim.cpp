@@ -69,3 +69,18 @@ SHIM uintptr_t ref_spectral_binary_complex_f32(float *r_out, float *i_out, const
 SHIM uintptr_t ref_spectral_binary_complex_f64(double *r_out, double *i_out, const double *r1, uintptr_t nr1, const double *i1, uintptr_t ni1,
                                                const double *r2, uintptr_t nr2, const double *i2, uintptr_t ni2, int mode, int op, uintptr_t maxFFT)
 { return spectral_binary_complex<double>(r_out, i_out, r1, nr1, i1, ni1, r2, nr2, i2, ni2, mode, op, maxFFT); }
+
+// change_phase (SpectralProcessor.hpp:186-208); out must hold the FFT size, which is returned
+template <class T>
+static uintptr_t spectral_change_phase(T *out, const T *in, uintptr_t size, double phase, double time_multiplier, uintptr_t maxFFT)
+{
+    typedef spectral_processor<T> Proc;
+    Proc proc(maxFFT);
+    proc.change_phase(out, in, size, phase, time_multiplier);
+    if (size <= 1) return size;
+    return uintptr_t(1) << Proc::calc_fft_size_log2((uintptr_t) std::round(size * time_multiplier));
+}
+SHIM uintptr_t ref_spectral_change_phase_f32(float *out, const float *in, uintptr_t size, double phase, double tm, uintptr_t maxFFT)
+{ return spectral_change_phase<float>(out, in, size, phase, tm, maxFFT); }
+SHIM uintptr_t ref_spectral_change_phase_f64(double *out, const double *in, uintptr_t size, double phase, double tm, uintptr_t maxFFT)
+{ return spectral_change_phase<double>(out, in, size, phase, tm, maxFFT); }

@@ -95,6 +95,7 @@ def oracle():
             sig("orc_mono_process", None, V, P, P, SZ, C.c_int)
             sig("orc_spectral_convolve", SZ, P, P, SZ, P, SZ, C.c_int, SZ)
             sig("orc_spectral_binary", SZ, P, P, SZ, P, SZ, C.c_int, C.c_int, SZ)
+            sig("orc_spectral_change_phase", SZ, P, P, SZ, C.c_double, C.c_double)
             sig("orc_spectral_binary_complex", SZ, P, P, P, SZ, P, SZ, P, SZ, P, SZ, C.c_int, C.c_int, SZ)
         _oracle = lib
     return _oracle
@@ -197,6 +198,9 @@ def ref_spectral():
             fn = getattr(lib, "ref_spectral_binary_complex" + suf)
             fn.restype = SZ
             fn.argtypes = [P, P, P, SZ, P, SZ, P, SZ, P, SZ, C.c_int, C.c_int, SZ]
+            fn = getattr(lib, "ref_spectral_change_phase" + suf)
+            fn.restype = SZ
+            fn.argtypes = [P, P, SZ, C.c_double, C.c_double, SZ]
         _ref_spec = lib
     return _ref_spec
 

@@ -162,6 +162,16 @@ def main():
                                                                             ck.fptr(b), n2, ck.fptr(bi), n2, mode, op, 32768)
                     g["cspec%s_%d_%d_op%d_m%d" % (suf, n1, n2, op, mode)] = np.stack([yr[:size], yi[:size]])
 
+    # ---- spectral_processor::change_phase: minimum / interpolated / linear / maximum phase ------------
+    for dtype, suf in ((np.float32, "_f32"), (np.float64, "_f64")):
+        for size in (2, 5, 300, 1024):
+            x = (rng.standard_normal(size) * np.exp(-5.0 * np.arange(size) / size)).astype(dtype)
+            g["phase%s_%d_x" % (suf, size)] = x
+            for k, (phase, tm) in enumerate(((0.0, 1.0), (0.3, 1.0), (0.5, 1.0), (1.0, 1.0), (0.8, 2.0))):
+                y = np.zeros(4 * size + 16, dtype)
+                n = getattr(rs, "ref_spectral_change_phase" + suf)(ck.fptr(y), ck.fptr(x), size, phase, tm, 1 << 16)
+                g["phase%s_%d_k%d" % (suf, size, k)] = y[:n]
+
     path = os.path.join(HERE, "golden.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes,", len(g), "arrays")

@@ -126,6 +126,53 @@ def test_correlate_and_complex_against_oracle(hb, suf):
                         assert ck.rel_rms(np.concatenate([gr[:size], gi[:size]]), np.concatenate([wr[:size], wi[:size]])) <= TOL[suf], (suf, planes, op, mode)
 
 
+PHASES = ((0.0, 1.0), (0.3, 1.0), (0.5, 1.0), (1.0, 1.0), (0.8, 2.0))
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("size", [2, 5, 300, 1024])
+def test_golden_change_phase(hb, suf, size):
+    """change_phase against fixtures made by the unmodified reference: minimum (0), interpolated (0.3, 0.8 with a doubled
+    FFT), linear (0.5) and maximum (1) phase."""
+    sp = hb.spectral_processor(MAXFFT[suf], DT[suf])
+    x = G["phase_%s_%d_x" % (suf, size)]
+    for k, (phase, tm) in enumerate(PHASES):
+        want = G["phase_%s_%d_k%d" % (suf, size, k)]
+        out = np.zeros(len(want) + 3, DT[suf])
+        assert sp.change_phase(out, x, size, phase, tm) == len(want)
+        assert ck.rel_rms(out[:len(want)], want) <= TOL[suf], (suf, size, k)
+        assert np.all(out[len(want):] == 0)
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_change_phase_against_oracle_and_properties(hb, suf):
+    """larger sizes (single-CTA and four-step transforms) against the C oracle; the minimum- and maximum-phase versions keep
+    the magnitude spectrum, the maximum-phase one is the time reverse of the minimum-phase one delayed by a sample."""
+    dt = DT[suf]
+    lib = ck.oracle()
+    fn = getattr(lib, "orc_spectral_change_phase_" + suf)
+    sp = hb.spectral_processor(1 << 17, dt)
+    rng = np.random.default_rng(12)
+    for size in (7, 2048, 20000, 40000):
+        x = (rng.standard_normal(size) * np.exp(-6.0 * np.arange(size) / size)).astype(dt)
+        for phase, tm in ((0.0, 1.0), (0.25, 1.0), (0.5, 1.0), (1.0, 1.0), (0.6, 2.0)):
+            want = np.zeros(4 * size + 16, dt)
+            n = fn(ck.fptr(want), ck.fptr(x), size, phase, tm)
+            got = np.zeros(4 * size + 16, dt)
+            assert sp.change_phase(got, x, size, phase, tm) == n
+            # log / exp of the spectrum amplify rounding differences between two FFT factorizations with the transform
+            # length: 1e-12 holds up to 1024 points (golden test above), 1e-10 is asserted at 65536
+            assert ck.rel_rms(got[:n], want[:n]) <= (TOL[suf] if suf == "f32" else 1e-10), (suf, size, phase, tm)
+        n = sp.change_phase(got, x, size, 0.0, 1.0)
+        mn = got[:n].astype(np.float64)
+        mag_in = np.abs(np.fft.rfft(x.astype(np.float64), n))
+        assert ck.rel_rms(np.abs(np.fft.rfft(mn)), mag_in) <= (1e-4 if suf == "f32" else 1e-9)
+    with pytest.raises(hb.HissError):
+        sp.change_phase(np.zeros(1 << 19, dt), np.zeros(200000, dt), 200000, 0.0, 1.0)     # FFT above the processor's maximum
+    one = np.zeros(1, dt)
+    assert sp.change_phase(one, np.array([0.75], dt), 1, 0.3) == 1 and one[0] == dt(0.75)
+
+
 def test_limits_and_noops(hb):
     sp = hb.spectral_processor(1024)
     assert sp.max_fft_size() == 1024

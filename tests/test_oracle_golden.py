@@ -151,3 +151,21 @@ def test_spectral_correlate_and_complex(suf, n1, n2):
                                                                      ck.fptr(b), n2, ck.fptr(bi), n2, mode, op, 32768)
             assert size == want.shape[1]
             assert ck.rel_rms(np.concatenate([yr[:size], yi[:size]]), want.ravel()) < TOL[suf], (op, mode)
+
+
+PHASES = ((0.0, 1.0), (0.3, 1.0), (0.5, 1.0), (1.0, 1.0), (0.8, 2.0))
+
+
+@pytest.mark.parametrize("suf", ["_f32", "_f64"])
+@pytest.mark.parametrize("size", [2, 5, 300, 1024])
+def test_spectral_change_phase(suf, size):
+    """oracle restatement of change_phase (minimum-phase cepstrum, interpolated, linear and maximum phase) against
+    fixtures made by the unmodified reference."""
+    lib = ck.oracle()
+    x = np.ascontiguousarray(G["phase%s_%d_x" % (suf, size)])
+    for k, (phase, tm) in enumerate(PHASES):
+        want = G["phase%s_%d_k%d" % (suf, size, k)]
+        y = np.zeros(4 * size + 16, x.dtype)
+        n = getattr(lib, "orc_spectral_change_phase" + suf)(ck.fptr(y), ck.fptr(x), size, phase, tm)
+        assert n == len(want)
+        assert ck.rel_rms(y[:n], want) < (3e-6 if suf == "_f32" else 1e-12), (k,)
