@@ -2,10 +2,11 @@
 // (HISSTools_FFT.h, PartitionedConvolve.h, MonoConvolve.h, NToMonoConvolve.h, Convolver.h), compiled
 // against this repo's include/ instead and linked to libhisstools_b200.so.  It writes every result to a
 // raw float32 file; tests/test_gpu_cpp_dropin.py regenerates the same inputs and checks them against
-// the oracle.  Usage: dropin_test <output file>
+// the oracle.  Usage: dropin_test <output file> [audio file]
 #include "HISSTools_FFT/HISSTools_FFT.h"
 #include "HIRT_Multichannel_Convolution/Convolver.h"
 #include "SpectralProcessor.hpp"
+#include "AudioFile/IAudioFile.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -163,6 +164,43 @@ int main(int argc, char **argv)
         sp.convolve(wc.data(), spectral_processor<float>::in_ptr(a.data(), a.size()), spectral_processor<float>::in_ptr(b.data(), b.size()),
                     spectral_processor<float>::EdgeMode::WrapCentre);
         dump(wc);
+    }
+
+    // 8. spectral_processor<float>: correlate (Wrap), complex-input convolve (Linear), change_phase (minimum phase)
+    {
+        typedef spectral_processor<float> SP;
+        SP sp;
+        std::vector<float> a = noise(700, 92), b = decaying(300, 93), ai = noise(350, 94), bi = noise(300, 95);
+        std::vector<float> corr(700), cr(999), ci(999), mp(1024);
+        dump_code(int(sp.correlated_size(700, 300, SP::EdgeMode::Wrap)));
+        sp.correlate(corr.data(), SP::in_ptr(a.data(), a.size()), SP::in_ptr(b.data(), b.size()), SP::EdgeMode::Wrap);
+        dump(corr);
+        sp.convolve(cr.data(), ci.data(), SP::in_ptr(a.data(), a.size()), SP::in_ptr(ai.data(), ai.size()), SP::in_ptr(b.data(), b.size()),
+                    SP::in_ptr(bi.data(), bi.size()), SP::EdgeMode::Linear);
+        dump(cr); dump(ci);
+        sp.change_phase(mp.data(), b.data(), 300, 0.0, 3.0);       // FFT 1024
+        dump(mp);
+    }
+
+    // 9. HISSTools::IAudioFile: header getters, readChannel after a seek, readInterleaved
+    if (argc > 2)
+    {
+        HISSTools::IAudioFile f(argv[2]);
+        dump_code(f.isOpen() ? 1 : 0);
+        dump_code(f.getErrorFlags());
+        dump_code(int(f.getFileType())); dump_code(int(f.getPCMFormat())); dump_code(f.getChannels()); dump_code(int(f.getFrames()));
+        dump_code(int(f.getSamplingRate())); dump_code(f.getBitDepth()); dump_code(int(f.getFrameByteCount()));
+        std::vector<float> ch(100), inter(size_t(f.getFrames()) * f.getChannels());
+        f.seek(17);
+        f.readChannel(ch.data(), 100, 1);
+        dump_code(int(f.getPosition()));
+        dump(ch);
+        f.seek();
+        f.readInterleaved(inter.data(), f.getFrames());
+        dump(inter);
+        HISSTools::IAudioFile missing("/nonexistent/file.wav");
+        dump_code(missing.isOpen() ? 1 : 0);
+        dump_code(missing.getErrorFlags());
     }
 
     fclose(out_file);

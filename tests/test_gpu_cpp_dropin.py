@@ -52,7 +52,8 @@ def test_cpp_headers_compile_against_reference_style_caller():
 def test_cpp_dropin_results():
     exe, d = build_program()
     out = os.path.join(d, "out.bin")
-    res = subprocess.run([exe, out], capture_output=True, text=True)
+    wav = os.path.join(ROOT, "tests", "golden", "audio", "wave_i24.wav")
+    res = subprocess.run([exe, out, wav], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert "kernel launches" in res.stdout and int(res.stdout.split()[1]) > 0
     data = np.fromfile(out, np.float32)
@@ -135,4 +136,26 @@ def test_cpp_dropin_results():
     want = np.zeros(1200, np.float32)
     size = lib.orc_spectral_convolve_f32(ck.fptr(want), ck.fptr(a), 900, ck.fptr(b), 250, 2, 32768)
     assert size == 900 and ck.rel_rms(take(900), want[:900]) <= TOL32
+    # 8. correlate (Wrap), complex-input convolve (Linear), change_phase (minimum phase, FFT 1024)
+    a, b, ai, bi = lcg_noise(700, 92), decaying(300, 93), lcg_noise(350, 94), lcg_noise(300, 95)
+    assert code() == 700
+    want = np.zeros(1100, np.float32)
+    assert lib.orc_spectral_binary_f32(ck.fptr(want), ck.fptr(a), 700, ck.fptr(b), 300, 1, 1, 32768) == 700
+    assert ck.rel_rms(take(700), want[:700]) <= TOL32
+    wr, wi = np.zeros(1100, np.float32), np.zeros(1100, np.float32)
+    assert lib.orc_spectral_binary_complex_f32(ck.fptr(wr), ck.fptr(wi), ck.fptr(a), 700, ck.fptr(ai), 350, ck.fptr(b), 300, ck.fptr(bi), 300, 0, 0, 32768) == 999
+    assert ck.rel_rms(np.concatenate([take(999), take(999)]), np.concatenate([wr[:999], wi[:999]])) <= TOL32
+    want = np.zeros(1100, np.float32)
+    assert lib.orc_spectral_change_phase_f32(ck.fptr(want), ck.fptr(b), 300, 0.0, 3.0) == 1024
+    assert ck.rel_rms(take(1024), want[:1024]) <= TOL32
+    # 9. IAudioFile on a fixture written and read back by the reference (bit-exact)
+    GA = np.load(os.path.join(ROOT, "tests", "golden", "golden_audio.npz"))
+    meta = GA["wave_i24_wav_meta"]
+    assert code() == 1 and code() == 0
+    assert [code() for _ in range(4)] == [int(meta[1]), int(meta[2]), int(meta[5]), int(meta[6])]
+    assert code() == int(GA["wave_i24_wav_rate"][0]) and code() == 24 and code() == 3 * int(meta[5])
+    assert code() == 117
+    assert np.array_equal(take(100).view(np.uint32), GA["wave_i24_wav_ch1_from17_f32"].view(np.uint32))
+    assert np.array_equal(take(int(meta[5]) * int(meta[6])).view(np.uint32), GA["wave_i24_wav_inter_f32"].view(np.uint32))
+    assert code() == 0 and code() == 4
     assert pos[0] == len(data)
