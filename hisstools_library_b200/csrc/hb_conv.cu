@@ -443,7 +443,7 @@ int launch_cmac_mh(hb_conv *c, const Range &r, void *S, int nh, uint64_t set_str
 }
 
 template <class T, int EPT>
-int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
+int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st, uint32_t nh)
 {
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
@@ -451,7 +451,7 @@ int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) / stage_tw : 0);
     int rc = allow_smem(k_fwd<T, EPT>, smem);
     if (rc) return rc;
-    k_fwd<T, EPT><<<g.groups * g.ins, fft_threads(log2m, EPT), smem, st>>>(g, prev, prev_ld, newest, new_ld, save, save_ld, (Cx<T> *) c->d_X, (T *) c->d_Xnyq,
+    k_fwd<T, EPT><<<dim3(g.groups * g.ins, nh), fft_threads(log2m, EPT), smem, st>>>(g, prev, prev_ld, newest, new_ld, save, save_ld, (Cx<T> *) c->d_X, (T *) c->d_Xnyq,
                                                                         (const Cx<T> *) c->d_tw, c->tw_log2, stage_tw);
     HB_LAUNCH_CHECK();
     return HB_OK;
@@ -480,11 +480,13 @@ int launch_fwd_big(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     return HB_OK;
 }
 
+// nh > 1: the forward transforms of nh consecutive hops in one launch (hop j from block j of the caller's rows into slot
+// c->g.slot - j; single-CTA transforms only)
 template <class T>
-int launch_fwd(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
+int launch_fwd(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st, uint32_t nh = 1)
 {
     if (is_big<T>(c)) return launch_fwd_big<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st);
-    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_fwd_ept<T, EPT>(c, prev, prev_ld, newest, new_ld, save, save_ld, st));
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_fwd_ept<T, EPT>(c, prev, prev_ld, newest, new_ld, save, save_ld, st, nh));
 }
 
 // what k_inv does besides the transform: where the block goes and which finished block it hands over first
@@ -495,7 +497,7 @@ template <class T> struct InvIO
 };
 
 template <class T, int EPT>
-int launch_inv_ept(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer)
+int launch_inv_ept(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer, uint32_t nh, const InvBatch &ib)
 {
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
@@ -503,9 +505,9 @@ int launch_inv_ept(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStre
     const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) / stage_tw : 0);
     int rc = allow_smem(k_inv<T, EPT>, smem);
     if (rc) return rc;
-    k_inv<T, EPT><<<g.groups * g.outs, fft_threads(log2m, EPT), smem, st>>>(g, sets, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off,
+    k_inv<T, EPT><<<dim3(g.groups * g.outs, nh), fft_threads(log2m, EPT), smem, st>>>(g, sets, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off,
                                                                          io.add_result, io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry,
-                                                                         (const Cx<T> *) c->d_tw, c->tw_log2, stage_tw, peer);
+                                                                         (const Cx<T> *) c->d_tw, c->tw_log2, stage_tw, peer, ib);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
@@ -534,15 +536,20 @@ int launch_inv_big(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStre
     return HB_OK;
 }
 
+inline InvBatch no_batch() { InvBatch ib; memset(&ib, 0, sizeof(ib)); ib.last_j = -1; return ib; }
+
+// nh > 1: the inverse transforms of nh consecutive hops in one launch (hop j: segment sets ib.set_stride apart, block j of the
+// caller's row; see InvBatch)
 template <class T>
-int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer = PeerOut())
+int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st, const PeerOut &peer = PeerOut(), uint32_t nh = 1,
+               const InvBatch &ib = no_batch())
 {
     if (is_big<T>(c))
     {
         if (peer.world) { set_error("the fused multi-GPU exchange is not implemented for FFT sizes above the single-CTA limit"); return HB_ERR_UNSUPPORTED; }
         return launch_inv_big<T>(c, sets, io, st);
     }
-    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer));
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer, nh, ib));
 }
 
 // the whole hop in one cluster launch (hb_conv_fused.cuh); eligibility is decided in plan_geometry
@@ -983,33 +990,37 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
             // a tail launched ahead for the first of these hops is not used: the batch covers all partitions itself
             if (c->split && c->tail_valid) HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
             c->tail_valid = false;
-            uint32_t slots[MH_MAX];
-            for (int j = 0; j < nb; j++)
-            {
-                const size_t hh = h + j;
-                const bool first = hh == 0, last = hh + 1 == nh;
-                c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
-                c->g.hop++;
-                c->g.trace = (unsigned long long *) c->d_trace.p;
-                slots[j] = c->g.slot;
-                if ((rc = launch_fwd<T>(c, first ? x_keep : d_in + (hh - 1) * B, first ? c->xin_ld : in_ld, d_in + hh * B, in_ld,
-                                        last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st))) return rc;
-            }
+            // forward transforms of the nb hops in one launch: hop j = block h + j of the caller's rows into slot slot0 - j
+            const bool first = h == 0, last_in_batch = h + nb == nh;
+            c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
+            const uint32_t slot0 = c->g.slot;
+            c->g.hop += nb;
+            c->g.trace = (unsigned long long *) c->d_trace.p;
+            if ((rc = launch_fwd<T>(c, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                    last_in_batch ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st, (uint32_t) nb))) return rc;
             Range rf = c->r_full;
-            rf.slot = slots[0]; rf.kind = 2;
+            rf.slot = slot0; rf.kind = 2;
             const uint64_t set_stride = uint64_t(rf.G + c->g.tiles) * c->g.Q;
             if ((rc = c->d_Smh.ensure(size_t(MH_MAX) * set_stride * 16))) return rc;
             if ((rc = launch_cmac_mh<T>(c, rf, c->d_Smh.p, nb, set_stride, st))) return rc;
-            for (int j = 0; j < nb; j++)
+            // inverse transforms of the nb hops in one launch: hop j sums set j, runs its Nyquist products from slot0 - j and
+            // leaves its block B samples further on; the last hop of the call stays behind in the staging row
             {
                 SegSets sets;
                 memset(&sets, 0, sizeof(sets));
                 sets.n = 1;
-                sets.s[0].S = (const char *) c->d_Smh.p + size_t(j) * set_stride * 16; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
-                c->g.slot = slots[j];                               // the Nyquist products of hop j run from its own newest slot
-                if ((rc = launch_inv<T>(c, sets, inv_io(h + j), st))) return rc;
+                sets.s[0].S = c->d_Smh.p; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
+                InvIO<T> io;
+                io.yout = d_out; io.ld = out_ld; io.off = (h + 1) * B; io.add_result = accumulate;
+                io.carry_src = first ? y_keep : nullptr; io.carry_src_ld = c->yout_ld;
+                io.carry_dst = (first && d_out) ? d_out : nullptr; io.carry_dst_ld = out_ld; io.add_carry = accumulate;
+                InvBatch ib = no_batch();
+                ib.set_stride = set_stride;
+                if (last_in_batch) { ib.last_j = nb - 1; ib.last_yout = c->d_yout[nxt].p; ib.last_ld = c->yout_ld; }
+                if ((rc = launch_inv<T>(c, sets, io, st, PeerOut(), (uint32_t) nb, ib))) return rc;
             }
-            c->g.slot = slots[nb - 1];
+            // the newest spectrum now sits nb - 1 slots below slot0
+            c->g.slot = slot0 >= uint32_t(nb - 1) ? slot0 - (nb - 1) : slot0 + c->g.R - (nb - 1);
             // nothing is launched ahead for the hop after a batch (the next call is most likely another batch, which
             // would discard it): a following single hop of the overlapped schedule runs all its partitions itself
             if (c->split) c->tail_missing = true;

@@ -603,6 +603,17 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
     const uint32_t B = g.B;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     trace_mark(g, 0, 0);
+    // blockIdx.y = hop j of a multi-hop batch (gridDim.y hops, consecutive blocks of the caller's rows): hop j's frame is
+    // [block j | block j - 1] and goes to slot g.slot - j; only the last hop leaves its block behind in `save`
+    uint32_t slot = g.slot;
+    if (blockIdx.y)
+    {
+        const uint32_t j = blockIdx.y;
+        prev = newest + size_t(j - 1) * B; prev_ld = new_ld;
+        newest += size_t(j) * B;
+        slot = slot >= j ? slot - j : slot + g.R - j;
+    }
+    if (blockIdx.y + 1 != gridDim.y) save = nullptr;
     // twiddles of this transform size staged in shared memory behind the data (one global round trip
     // instead of one per pass); the loads are issued together with the input loads below
     Cx<T> *stw = s + padded_elems<HB_PADSH>(B);
@@ -651,11 +662,11 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
             Cx<T> z = s[sidx<HB_PADSH>(k)];
             if (k == 0)
             {
-                Xnyq[size_t(ch) * g.R + g.slot] = z.y;
+                Xnyq[size_t(ch) * g.R + slot] = z.y;
                 z.y = T(0);
             }
             const uint32_t bt = k / TB, j = k - bt * TB;
-            xrow[(size_t(bt) * g.R + g.slot) * TB + j] = z;
+            xrow[(size_t(bt) * g.R + slot) * TB + j] = z;
         }
     }
     trace_mark(g, 0, 1);
@@ -683,6 +694,16 @@ struct PeerOut
     uint64_t slot;                     // elements per inbox block (hop capacity)
 };
 
+// multi-hop batch description for k_inv (all zero / last_j = -1 for a single hop)
+struct InvBatch
+{
+    uint64_t set_stride;   // vectors between the partial-segment sets of consecutive hops
+    void *last_yout;       // where the hop flagged last_j leaves its block (staging row), leading dimension last_ld
+    uint64_t last_ld;
+    int32_t last_j;
+    int32_t pad;
+};
+
 // partial segments k_inv sums: one set per multiply-accumulate launch that contributed to this hop
 struct SegSet
 {
@@ -702,11 +723,28 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
                                               T *__restrict__ yout, size_t ld, size_t off, int add_result,
                                               const T *__restrict__ carry_src, size_t carry_src_ld,
                                               T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
-                                              const Cx<T> *__restrict__ tw, int tw_log2, int stage_tw, const PeerOut peer)
+                                              const Cx<T> *__restrict__ tw, int tw_log2, int stage_tw, const PeerOut peer, const InvBatch ib)
 {
     typedef typename VecOf<T>::type V;
     constexpr int CPV = VecOf<T>::CPV;
     constexpr int VPT = EPT / CPV;                  // 16-byte vectors of the spectrum per thread
+    // blockIdx.y = hop j of a multi-hop batch: its partial segments are set_stride vectors further on, its Nyquist products
+    // run from slot g.slot - j, its block goes B samples further in the caller's row -- except the hop flagged as the last of
+    // the call, which stays behind in the staging row (ib.last_*); only hop 0 hands over the previous block
+    uint32_t nyq_slot = g.slot;
+    uint64_t seg_shift = 0;
+    if (blockIdx.y)
+    {
+        const uint32_t j = blockIdx.y;
+        nyq_slot = nyq_slot >= j ? nyq_slot - j : nyq_slot + g.R - j;
+        seg_shift = uint64_t(j) * ib.set_stride;
+        off += size_t(j) * g.B;
+        carry_dst = nullptr;
+    }
+    if (ib.last_j >= 0 && blockIdx.y == (uint32_t) ib.last_j)
+    {
+        yout = reinterpret_cast<T *>(ib.last_yout); ld = ib.last_ld; off = 0; add_result = 0;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
     __shared__ T red[40];
@@ -769,7 +807,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
 #pragma unroll 1
         for (int q = 0; q < sets.n; q++)
         {
-            const V *__restrict__ S = reinterpret_cast<const V *>(sets.s[q].S);
+            const V *__restrict__ S = reinterpret_cast<const V *>(sets.s[q].S) + seg_shift;
             const uint64_t sU = sets.s[q].U;
             const uint32_t sG = sets.s[q].G, supt = sets.s[q].upt;
             uint32_t seg_lo[GV], seg_hi[GV];
@@ -841,7 +879,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
             if (idx < g.upt)
             {
                 const uint32_t in = idx / g.P, p = idx - in * g.P;
-                uint32_t sl = g.slot + p;
+                uint32_t sl = nyq_slot + p;
                 if (sl >= g.R) sl -= g.R;
                 xv[q] = xn[size_t(in) * g.R + sl];
                 hv[q] = hn[size_t(in) * g.Pcap + p];

@@ -129,13 +129,14 @@ void destroy(hb_matrix *m)
 
 // staggered reset phases of MonoConvolve::setResetOffset (MonoConvolve.cpp:85-98); a negative
 // (random) request selects phase 0 so that runs are reproducible
+// The reference staggers its fixed parts by size / 8 samples (MonoConvolve.cpp:92-96) purely to spread the FFTs of the
+// parts over different audio callbacks of ONE CPU thread.  On the GPU a phase other than 0 only forces hop-unaligned calls
+// through the staging copies and rules out the multi-hop batches, and the output does not depend on the phase beyond
+// rounding (SURVEY B): every part takes the caller's offset as it is.
 void apply_reset_offset(hb_matrix *m, intptr_t offset)
 {
     if (offset < 0) offset = 0;
-    const size_t n = m->sizes.size(), fixed = m->parts.size() - 1;
-    for (size_t k = 0; k < fixed; k++)
-        hb_conv_set_reset_offset(m->parts[k], offset + intptr_t(m->sizes[n - 1 - fixed + k] >> 3));
-    hb_conv_set_reset_offset(m->parts.back(), offset);
+    for (hb_conv *p : m->parts) hb_conv_set_reset_offset(p, offset);
 }
 
 int grow_tail(hb_matrix *m, uintptr_t size)

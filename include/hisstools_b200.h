@@ -224,7 +224,9 @@ int hb_matrix_create(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, 
 int hb_matrix_create_latency(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
                              int latency_mode, int device);
 void hb_matrix_destroy(hb_matrix *m);
-/* MonoConvolve::setResetOffset: MonoConvolve.cpp:80-98 (staggered per part; negative selects phase 0) */
+/* MonoConvolve::setResetOffset: MonoConvolve.cpp:80-98 (negative selects phase 0).  The reference staggers its parts by
+ * size / 8 samples to spread CPU load over callbacks; here every part takes the offset as it is (the output does not depend
+ * on the phase beyond rounding, and hop-aligned calls are what the GPU path is fastest on). */
 int hb_matrix_set_reset_offset(hb_matrix *m, intptr_t offset);
 /* MonoConvolve::resize / set / reset for pair (group, in, out): MonoConvolve.cpp:100-152.  Return the
  * reference ConvolveError (0, 3, 4) or a negative hb_status.  set/resize block process (MemorySwap.h:174-178). */
