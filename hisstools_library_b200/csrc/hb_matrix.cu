@@ -64,6 +64,84 @@ __global__ void __launch_bounds__(TD_BLOCK) k_td(const T *__restrict__ h, const 
     }
 }
 
+// Register-blocked form for long calls: every thread produces TD_R consecutive output samples from a sliding register
+// window of the input, four taps per step (one broadcast LDS.128 of taps + one LDS.128 of new samples per 4 * TD_R FMAs), so
+// the loop is bound by the FMA pipe instead of shared-memory loads.  grid = (ceil(n / (TDB * TD_R)), groups * outs);
+// shared memory: taps + (taps + TDB * TD_R) samples; taps must be a multiple of 4 (it is A / 2 with A >= 32).
+// four consecutive values from a 16-byte aligned shared-memory address
+__device__ __forceinline__ void ld4(const float *p, float *v)
+{
+    const float4 q = *reinterpret_cast<const float4 *>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void ld4(const double *p, double *v)
+{
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+constexpr int TD_R = 8;
+constexpr int TDB = 128;            // threads of the blocked kernel: several small CTAs per SM overlap their staging and arithmetic
+template <class T>
+__global__ void __launch_bounds__(TDB) k_td_blocked(const T *__restrict__ h, const T *__restrict__ x, size_t x_ld,
+                                                         const T *__restrict__ hist, T *__restrict__ out, size_t out_ld,
+                                                         uint32_t ins, uint32_t outs, uint32_t taps, size_t n, int add)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sh = reinterpret_cast<T *>(smem_raw);
+    T *sx = sh + taps;
+    constexpr uint32_t SPAN = TDB * TD_R;
+    const uint32_t row = blockIdx.y;
+    const uint32_t grp = row / outs;
+    const size_t s0 = size_t(blockIdx.x) * SPAN;
+    T acc[TD_R];
+#pragma unroll
+    for (int r = 0; r < TD_R; r++) acc[r] = T(0);
+    const uint32_t p = taps + TD_R * threadIdx.x;          // sx index of x[s], s = first sample of this thread
+    for (uint32_t i = 0; i < ins; i++)
+    {
+        const T *hp = h + (size_t(row) * ins + i) * taps;
+        const size_t xrow = size_t(grp) * ins + i;
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < taps; k += TDB) sh[k] = hp[k];
+        for (uint32_t j = threadIdx.x; j < taps + SPAN; j += TDB)
+        {
+            const long long idx = (long long) s0 + (long long) j - (long long) taps;
+            T v = T(0);
+            if (idx < 0) v = hist[xrow * taps + size_t(idx + (long long) taps)];
+            else if (size_t(idx) < n) v = x[xrow * x_ld + size_t(idx)];
+            sx[j] = v;
+        }
+        __syncthreads();
+        // win[q] = sx[p - k - 4 + q] (q < 12; 16-byte aligned groups of four): tap k + t (t = 0..3) of output r reads win[4 - t + r]
+        T win[TD_R + 4], hv[4];
+        ld4(sx + p - 4, win); ld4(sx + p, win + 4); ld4(sx + p + 4, win + 8);
+        for (uint32_t k = 0; k < taps; k += 4)
+        {
+            ld4(sh + k, hv);
+#pragma unroll
+            for (int r = 0; r < TD_R; r++)
+            {
+                acc[r] = fma(hv[0], win[4 + r], acc[r]);
+                acc[r] = fma(hv[1], win[3 + r], acc[r]);
+                acc[r] = fma(hv[2], win[2 + r], acc[r]);
+                acc[r] = fma(hv[3], win[1 + r], acc[r]);
+            }
+            // slide the window four samples towards the past
+#pragma unroll
+            for (int q = TD_R + 3; q >= 4; q--) win[q] = win[q - 4];
+            if (k + 4 < taps) ld4(sx + p - k - 8, win);
+        }
+    }
+    const size_t s = s0 + size_t(TD_R) * threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < TD_R; r++)
+        if (s + r < n)
+        {
+            T *o = out + size_t(row) * out_ld + s + r;
+            *o = add ? *o + acc[r] : acc[r];
+        }
+}
+
 // new history = last `taps` samples of (old history ++ x[0..n))
 template <class T>
 __global__ void k_td_hist(const T *__restrict__ old_hist, const T *__restrict__ x, size_t x_ld, T *__restrict__ new_hist, uint32_t taps, size_t n)
@@ -214,10 +292,22 @@ int process_rows(hb_matrix *m, const T *d_in, size_t in_ld, T *d_out, size_t out
                 HB_CUDA(cudaMemsetAsync(m->d_hist[m->hist_cur], 0, rows_in * taps * sizeof(T), st));
                 m->head_reset = false;
             }
-            dim3 grid((unsigned) ((n + TD_BLOCK - 1) / TD_BLOCK), m->groups * m->outs);
-            const size_t smem = (size_t(2) * taps + TD_BLOCK) * sizeof(T);
-            k_td<T><<<grid, TD_BLOCK, smem, st>>>((const T *) m->d_head, d_in, in_ld, (const T *) m->d_hist[m->hist_cur], d_out, out_ld,
-                                                 m->ins, m->outs, taps, n, add ? 1 : 0);
+            if (n >= 4 * TD_BLOCK && taps % 4 == 0)
+            {
+                // long calls: register-blocked kernel (TD_R samples per thread)
+                const size_t span = size_t(TDB) * TD_R;
+                dim3 grid((unsigned) ((n + span - 1) / span), m->groups * m->outs);
+                const size_t smem = (size_t(2) * taps + span) * sizeof(T);
+                k_td_blocked<T><<<grid, TDB, smem, st>>>((const T *) m->d_head, d_in, in_ld, (const T *) m->d_hist[m->hist_cur], d_out, out_ld,
+                                                             m->ins, m->outs, taps, n, add ? 1 : 0);
+            }
+            else
+            {
+                dim3 grid((unsigned) ((n + TD_BLOCK - 1) / TD_BLOCK), m->groups * m->outs);
+                const size_t smem = (size_t(2) * taps + TD_BLOCK) * sizeof(T);
+                k_td<T><<<grid, TD_BLOCK, smem, st>>>((const T *) m->d_head, d_in, in_ld, (const T *) m->d_hist[m->hist_cur], d_out, out_ld,
+                                                     m->ins, m->outs, taps, n, add ? 1 : 0);
+            }
             HB_LAUNCH_CHECK();
             dim3 hgrid((taps + 255) / 256, (unsigned) rows_in);
             k_td_hist<T><<<hgrid, 256, 0, st>>>((const T *) m->d_hist[m->hist_cur], d_in, in_ld, (T *) m->d_hist[m->hist_cur ^ 1], taps, n);

@@ -550,7 +550,7 @@ def test_convolver_zero_latency_head(hb):
             assert cv.set(i, o, irs[o][i], L, False) == 0
     got = np.zeros((n_out, xs.shape[1]), np.float32)
     pos, k = 0, 0
-    sizes = [64, 1, 100, 128, 300, 4096, 17]
+    sizes = [64, 1, 100, 128, 300, 4096, 17, 1024, 2500]           # calls of 1024 samples and more take the register-blocked head
     while pos < xs.shape[1]:
         n = min(sizes[k % len(sizes)], xs.shape[1] - pos)
         yb = np.zeros((n_out, n), np.float32)
