@@ -36,6 +36,7 @@ def needs_build():
         return True
     t = os.path.getmtime(out)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".cu", ".h"))]       # every source and header in csrc/
     return any(os.path.getmtime(d) > t for d in deps)
 
 

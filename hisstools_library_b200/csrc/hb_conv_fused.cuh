@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
         }
     }
 
+    trace_mark(g, 1, 0);                                        // phase stamps (trace only): forward part done
     // ---- this rank's share of the (input, partition >= 1) products: spectra already in the delay line ----
     {
         const uint32_t q0 = (uint32_t) ((uint64_t(rank) * fa.tail_items) / cs), q1 = (uint32_t) ((uint64_t(rank + 1) * fa.tail_items) / cs);
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
         }
     }
 
+    trace_mark(g, 1, 1);                                        // products done
     // ---- publish the partial spectrum and Nyquist sum; rank 0 reduces over the cluster ----
 #pragma unroll
     for (int e = 0; e < EPT; e++)
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     const T nyq_sum = block_sum<T>(nyq, red);
     if (tid == 0) nyq_part = nyq_sum;
     cluster.sync();
+    trace_mark(g, 2, 0);                                        // first cluster barrier passed
     if (rank == 0)
     {
         T nyq_total = nyq_sum;
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
         }
     }
     cluster.sync();                                             // remote shared memory may go away from here on
+    trace_mark(g, 2, 1);                                        // reduction done
     if (rank != 0) { trace_mark(g, 0, 1); return; }
 
     // ---- inverse real FFT, scale, first B samples (k_inv's tail) ----
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     }
     __syncthreads();
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
+    trace_mark(g, 3, 0);                                        // inverse transform done
     const T scale = T(1) / T(size_t(4) << g.log2n);
     T *dst = yout + size_t(grp) * ld + off;
 #pragma unroll

@@ -58,7 +58,7 @@ def main():
                 t0 = int(ent[m].min())
             e, x_ = ent[m].astype(np.int64) - t0, ext[m].astype(np.int64) - t0
             print("hop %3d %-4s ctas %3d  first entry %9.1f us  last entry %9.1f us  first exit %9.1f us  last exit %9.1f us" %
-                  (h, KIND[k], int(m.sum()), e.min() / 1e3, e.max() / 1e3, x_.min() / 1e3, x_.max() / 1e3))
+                  (h, KIND[k], int(m.sum()), e.min() / 1e3, e.max() / 1e3, x_[x_ > -t0 // 2].min() / 1e3 if (x_ > -t0 // 2).any() else -1, x_.max() / 1e3))
     eng.close()
 
 
