@@ -431,6 +431,36 @@ def test_convolver_golden_latency_short(hb):
         assert ck.rel_rms(got[o], want[o]) <= TOL32
 
 
+@pytest.mark.parametrize("mode", ["kLatencyShort", "kLatencyZero"])
+def test_large_matrix_latency_modes_use_batches_and_match_truth(hb, mode):
+    """Convolver(64, 64, LatencyMode): with 4096 pairs the small FFT parts stream enough spectra for the multi-hop batches
+    (several parts accumulating into the same block, forward / inverse FFTs of a batch in one launch each, the
+    register-blocked direct-form head for kLatencyZero).  Three outputs against float64 direct convolution, blocks of 1024
+    samples plus a ragged call."""
+    n = 64
+    L = 2600
+    rng = np.random.default_rng(7)
+    irs = (rng.standard_normal((n, n, L)) * np.exp(-6.9 * np.arange(L) / L) * 0.1).astype(np.float32)
+    xs = np.stack([ck.synth_audio(1024 * 7 + 333, 900 + i) for i in range(n)])
+    cv = hb.Convolver(n, n, getattr(hb, mode))
+    cv.setResetOffset(0)
+    for o in range(n):
+        for i in range(n):
+            assert cv.set(i, o, irs[o, i], L, False) == 0
+    got = np.zeros((n, xs.shape[1]), np.float32)
+    pos = 0
+    for m in [1024, 1024, 333, 1024, 2048, 1024, 1024]:
+        yb = np.zeros((n, m), np.float32)
+        cv.process(np.ascontiguousarray(xs[:, pos:pos + m]), yb, n, n, m)
+        got[:, pos:pos + m] = yb
+        pos += m
+    assert pos == xs.shape[1]
+    delay = 0 if mode == "kLatencyZero" else 128
+    for o in (0, 17, 63):
+        truth = sum(ck.direct_convolve_delayed(irs[o, i], xs[i], delay) for i in range(n))
+        assert ck.rel_rms(got[o], truth) <= TOL32
+
+
 def test_n2m_config3_reduced(hb):
     """BASELINE config 3 geometry (8 -> 1, FFT 4096) with 16384-tap IRs, against direct convolution."""
     n_in, B, L = 8, 2048, 16384
