@@ -209,13 +209,14 @@ void plan_geometry(hb_conv *c)
     // automatic choice: below a few MiB of tail spectra a hop is bound by launch latency, and the extra launch and
     // the two stream hand-overs of the overlapped schedule cost more than they hide (measured: DESIGN.md 4)
     const uint64_t tail_bytes = uint64_t(c->pairs() + uint64_t(g.groups) * g.ins) * (g.P ? g.P - 1 : 0) * g.B * 2 * c->esize();
-    // fused single-launch hop (hb_conv_fused.cuh): single-output engines whose partition spectrum is one bin tile and
+    // fused single-launch hop (hb_conv_fused.cuh): engines of up to 8 outputs whose partition spectrum is one bin tile and
     // whose per-output share of the delay line is small enough for one cluster (<= 8 CTAs x 256 KiB of L2-resident reads)
     c->fused = false;
     c->fused_cs = 1;
-    if ((c->schedule == 2 || c->schedule == 3) && g.outs == 1 && g.n_bt == 1 && g.P >= 1 && log2m <= 12 && log2m >= 3)
+    if ((c->schedule == 2 || c->schedule == 3) && g.outs <= 8 && g.n_bt == 1 && g.P >= 1 && log2m <= 12 && log2m >= 3)
     {
-        const uint64_t per_output = tail_bytes / std::max<uint32_t>(g.groups, 1);
+        // spectra one output's cluster reads per hop: its IR partitions and the delay line of every input
+        const uint64_t per_output = uint64_t(g.ins) * (g.P - 1) * g.B * 4 * c->esize();
         uint32_t cs = 1;
         while (cs < 8 && per_output / cs > (uint64_t(96) << 10)) cs <<= 1;
         // measured (profiles/r1_small_hops.txt): config 1 15 us against 21, config 2 21 us against 27; an 8 -> 1 engine with
@@ -578,7 +579,7 @@ int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, siz
     fa.tail_items = g.ins * (g.P - 1);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(g.groups * cs);
+    cfg.gridDim = dim3(g.groups * g.outs * cs);
     cfg.blockDim = dim3(std::max<uint32_t>(std::min<uint32_t>(B / EPT, 512u), 128u));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;

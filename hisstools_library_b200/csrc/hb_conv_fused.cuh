@@ -1,9 +1,11 @@
-// hb_conv_fused.cuh -- one launch per hop for small single-output engines (PartitionedConvolve, MonoConvolve parts,
-// NToMonoConvolve: groups x ins x 1 output, spectrum of one partition <= 32 KiB so that bin tiles do not split).
+// hb_conv_fused.cuh -- one launch per hop for small engines (PartitionedConvolve, MonoConvolve parts, NToMonoConvolve,
+// small Convolver matrices: groups x ins x up to 8 outputs, one bin tile per spectrum).
 //
 // Such hops are bound by launch latency, not by HBM: the three-kernel hop (k_fwd -> k_cmac -> k_inv) spends ~7 us per
 // launch on a few hundred KiB of L2-resident data.  Here one thread-block CLUSTER per (group, output) does the whole
 // hop (PartitionedConvolve.cpp:352-377):
+//   (with several outputs every output's cluster transforms the inputs for itself -- a few microseconds of redundant
+//   arithmetic instead of a grid-wide dependency -- and only output 0's cluster stores the spectra into the delay line)
 //   every rank  forward FFT of the inputs it owns (rank = input mod cluster size) into the newest FDL slot, partition 0
 //               against that fresh spectrum, then its share of the (input, partition >= 1) products against spectra that
 //               are already in the delay line -- all accumulated in registers, one complex bin set per thread;
@@ -39,7 +41,11 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank(), cs = fa.cs;
-    const uint32_t grp = blockIdx.x / cs;                       // one cluster per (group, the single output)
+    const uint32_t cl = blockIdx.x / cs;                        // one cluster per (group, output)
+    const uint32_t grp = cl / g.outs, o = cl - grp * g.outs;
+    const uint32_t ot = o / g.OT, row = o - ot * g.OT;
+    const uint32_t tile = grp * g.n_ot + ot;                    // one bin tile: tile = (group, output tile)
+    const bool writer = o == 0;                                 // this cluster keeps the delay line
     const uint32_t B = g.B, P = g.P, R = g.R;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);             // FFT work array (padded)
@@ -61,8 +67,8 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     if (rank == 0 && carry_dst)
     {
         // hand the block computed by the previous hop to the caller (the output-ring read of PartitionedConvolve.cpp:307)
-        const T *cs_ = carry_src + size_t(grp) * carry_src_ld;
-        T *cd = carry_dst + size_t(grp) * carry_dst_ld;
+        const T *cs_ = carry_src + size_t(cl) * carry_src_ld;
+        T *cd = carry_dst + size_t(cl) * carry_dst_ld;
         for (uint32_t k = tid; k < B; k += nthr) cd[k] = add_carry ? cd[k] + cs_[k] : cs_[k];
     }
 
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     {
         const uint32_t ch = grp * g.ins + in;
         const T *pn = newest + size_t(ch) * new_ld, *pp = prev + size_t(ch) * prev_ld;
-        T *ps = save ? save + size_t(ch) * save_ld : nullptr;
+        T *ps = (save && writer) ? save + size_t(ch) * save_ld : nullptr;
         __syncthreads();                                        // s is free (previous input's spectrum consumed)
 #pragma unroll
         for (int e = 0; e < EPT; e++)
@@ -99,7 +105,9 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
         block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, twl, twl_log2);
         __syncthreads();
         Cx<T> *xrow = X + (size_t(ch) * R + g.slot) * B;
-        const Cx<T> *h0 = H + (size_t(ch) * g.Pcap) * B;       // unit (tile = grp, in, p = 0): OT = 1, one bin tile
+        // unit (tile, in, p) holds OT rows of B bins; this output is row `row` of it
+        const Cx<T> *h0 = H + ((size_t(tile) * g.ins + in) * g.Pcap * g.OT + row) * B;
+        const T *hnq = Hnyq + (size_t(cl) * g.ins + in) * g.Pcap;
 #pragma unroll
         for (int e = 0; e < EPT; e++)
         {
@@ -110,11 +118,11 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 if (k == 0)
                 {
                     const T xn = z.y;
-                    Xnyq[size_t(ch) * R + g.slot] = xn;
-                    nyq += xn * Hnyq[size_t(ch) * g.Pcap];      // outs = 1: Hnyq[(grp * 1 + 0) * ins + in][p]
+                    if (writer) Xnyq[size_t(ch) * R + g.slot] = xn;
+                    nyq += xn * hnq[0];
                     z.y = T(0);
                 }
-                xrow[k] = z;
+                if (writer) xrow[k] = z;
                 const Cx<T> h = h0[k];
                 acc[e].x = fma(z.x, h.x, acc[e].x); acc[e].x = fma(-z.y, h.y, acc[e].x);
                 acc[e].y = fma(z.x, h.y, acc[e].y); acc[e].y = fma(z.y, h.x, acc[e].y);
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
             const uint32_t ch = grp * g.ins + in;
             uint32_t sl = g.slot + p;
             if (sl >= R) sl -= R;
-            const Cx<T> *hp = H + (size_t(ch) * g.Pcap + p) * B;
+            const Cx<T> *hp = H + (((size_t(tile) * g.ins + in) * g.Pcap + p) * g.OT + row) * B;
             const Cx<T> *xp = X + (size_t(ch) * R + sl) * B;
             Cx<T> hv[EPT], xv[EPT];
 #pragma unroll
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                     acc[e].y = fma(xv[e].x, hv[e].y, acc[e].y); acc[e].y = fma(xv[e].y, hv[e].x, acc[e].y);
                 }
             }
-            if (tid == 0) nyq += Xnyq[size_t(ch) * R + sl] * Hnyq[size_t(ch) * g.Pcap + p];
+            if (tid == 0) nyq += Xnyq[size_t(ch) * R + sl] * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
         }
     }
 
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
     trace_mark(g, 3, 0);                                        // inverse transform done
     const T scale = T(1) / T(size_t(4) << g.log2n);
-    T *dst = yout + size_t(grp) * ld + off;
+    T *dst = yout + size_t(cl) * ld + off;
 #pragma unroll
     for (int e = 0; e < EPT / 2; e++)
     {

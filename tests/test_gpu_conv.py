@@ -123,49 +123,55 @@ def test_schedules_agree_and_survive_mid_stream_changes(hb, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("ins,groups,B,L", [(1, 1, 512, 4096), (1, 1, 1024, 65536), (8, 1, 2048, 30000), (3, 2, 256, 5000), (1, 3, 16, 100), (5, 1, 64, 64)])
-def test_fused_hop_against_serial_and_truth(hb, dtype, ins, groups, B, L):
-    """The fused single-launch hop (one thread-block cluster per output: hb_conv_fused.cuh) on single-output engines --
-    BASELINE configs 1 and 2, a config-3-like 8 -> 1 shape, several groups, tiny and one-partition sizes -- against the
-    serial three-kernel hop (summation order only) and float64 direct convolution, ragged calls included."""
+@pytest.mark.parametrize("ins,outs,groups,B,L,fused", [(1, 1, 1, 512, 4096, True), (1, 1, 1, 1024, 65536, True), (8, 1, 1, 2048, 30000, False),
+                                                       (3, 1, 2, 256, 5000, True), (1, 1, 3, 16, 100, True), (5, 1, 1, 64, 64, True),
+                                                       (2, 2, 1, 512, 3000, True), (3, 5, 1, 256, 2000, True), (2, 8, 2, 128, 1000, True)])
+def test_fused_hop_against_serial_and_truth(hb, dtype, ins, outs, groups, B, L, fused):
+    """The fused single-launch hop (one thread-block cluster per output: hb_conv_fused.cuh) on small engines -- BASELINE
+    configs 1 and 2, several groups, tiny and one-partition sizes, stereo and wider matrices (every output's cluster
+    transforms the inputs for itself) -- against the serial three-kernel hop (summation order only) and float64 direct
+    convolution, ragged calls included; an 8 -> 1 engine with 3.7 MB of spectra per output is not eligible."""
     from hisstools_library_b200.convolve import _Engine
     if dtype == np.float64 and B > 2048:
         pytest.skip("spectrum above one bin tile")
     tol = TOL32 if dtype == np.float32 else TOL64
-    irs = [[ck.synth_ir(L, 700 + 10 * g + i).astype(dtype) for i in range(ins)] for g in range(groups)]
+    irs = [[[ck.synth_ir(L, 700 + 100 * g + 10 * o + i).astype(dtype) for i in range(ins)] for o in range(outs)] for g in range(groups)]
     n = B * 12 + 37
     xs = np.stack([ck.synth_audio(n, 700 + r) for r in range(groups * ins)]).astype(dtype)
-    outs = {}
+    res = {}
     for mode in ("auto", "serial"):
-        e = _Engine(dtype, groups, ins, 1, 2 * B, L, 0, 0, 0)
+        e = _Engine(dtype, groups, ins, outs, 2 * B, L, 0, 0, 0)
         e.set_schedule(None if mode == "auto" else False)
         e.set_reset_offset(0)
         for g in range(groups):
-            for i in range(ins):
-                e.set_ir(g, i, 0, irs[g][i], L)
-        y = np.zeros((groups, n), dtype)
+            for o in range(outs):
+                for i in range(ins):
+                    e.set_ir(g, i, o, irs[g][o][i], L)
+        y = np.zeros((groups * outs, n), dtype)
         pos, k = 0, 0
         sizes = [B, B, B // 2 + 1, 3 * B, 5, B]
         while pos < n:
             m = min(sizes[k % len(sizes)], n - pos)
-            yo = [np.zeros(m, dtype) for _ in range(groups)]
+            yo = [np.zeros(m, dtype) for _ in range(groups * outs)]
             e.process([np.ascontiguousarray(xs[r, pos:pos + m]) for r in range(groups * ins)], yo, m)
-            for g in range(groups):
-                y[g, pos:pos + m] = yo[g]
+            for r in range(groups * outs):
+                y[r, pos:pos + m] = yo[r]
             pos += m
             k += 1
-        # eligible for the fused hop: at most 8 ranks x 256 KiB of spectra per output (plan_geometry)
-        eligible = ins * (-(-L // B) - 1) * B * 4 * np.dtype(dtype).itemsize <= 8 * 256 * 1024
-        if mode == "serial" or eligible:
-            assert e.schedule == ("fused" if mode == "auto" else "serial")
+        if mode == "serial":
+            assert e.schedule == "serial"
+        elif fused:
+            assert e.schedule == "fused"
         else:
             assert e.schedule in ("overlapped", "serial")
-        outs[mode] = y
+        res[mode] = y
         e.close()
     for g in range(groups):
-        assert ck.rel_rms(outs["auto"][g], outs["serial"][g]) <= tol / 5
-        truth = sum(ck.direct_convolve_delayed_fft(irs[g][i], xs[g * ins + i], B) for i in range(ins))
-        assert ck.rel_rms(outs["auto"][g], truth) <= tol * (1 if dtype == np.float32 else 10)
+        for o in range(outs):
+            r = g * outs + o
+            assert ck.rel_rms(res["auto"][r], res["serial"][r]) <= tol / 5
+            truth = sum(ck.direct_convolve_delayed_fft(irs[g][o][i], xs[g * ins + i], B) for i in range(ins))
+            assert ck.rel_rms(res["auto"][r], truth) <= tol * (1 if dtype == np.float32 else 10)
 
 
 @pytest.mark.parametrize("dtype,schedule", [(np.float32, None), (np.float32, False), (np.float64, None)])
