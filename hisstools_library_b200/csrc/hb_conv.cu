@@ -362,12 +362,7 @@ template <class K> int allow_smem(K kernel, size_t bytes)
 template <class T> size_t fft_smem(uint32_t log2m) { return size_t(padded_elems<HB_PADSH>(1u << log2m)) * sizeof(Cx<T>); }
 // shared-memory copy of the twiddles of a real transform of 2^(log2m+1) points: 2^log2m entries behind the data
 template <class T> size_t tw_smem(uint32_t log2m) { return (size_t(1) << log2m) * sizeof(Cx<T>); }
-// 1: the half circle fits behind the data, 2: only its first quarter does (tw_root derives the rest), 0: neither
-template <class T> int tw_fits(uint32_t log2m)
-{
-    if (fft_smem<T>(log2m) + tw_smem<T>(log2m) <= 200 * 1024) return 1;
-    return fft_smem<T>(log2m) + tw_smem<T>(log2m) / 2 <= 200 * 1024 ? 2 : 0;
-}
+template <class T> int tw_fits(uint32_t log2m) { return fft_smem<T>(log2m) + tw_smem<T>(log2m) <= 200 * 1024 ? 1 : 0; }
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
 template <class T, int XA, int OB>
@@ -449,7 +444,7 @@ int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
     const int stage_tw = tw_fits<T>(log2m);
-    const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) / stage_tw : 0);
+    const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) : 0);
     int rc = allow_smem(k_fwd<T, EPT>, smem);
     if (rc) return rc;
     k_fwd<T, EPT><<<dim3(g.groups * g.ins, nh), fft_threads(log2m, EPT), smem, st>>>(g, prev, prev_ld, newest, new_ld, save, save_ld, (Cx<T> *) c->d_X, (T *) c->d_Xnyq,
@@ -503,7 +498,7 @@ int launch_inv_ept(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStre
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
     const int stage_tw = tw_fits<T>(log2m);
-    const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) / stage_tw : 0);
+    const size_t smem = fft_smem<T>(log2m) + (stage_tw ? tw_smem<T>(log2m) : 0);
     int rc = allow_smem(k_inv<T, EPT>, smem);
     if (rc) return rc;
     k_inv<T, EPT><<<dim3(g.groups * g.outs, nh), fft_threads(log2m, EPT), smem, st>>>(g, sets, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off,

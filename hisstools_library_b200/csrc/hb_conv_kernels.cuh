@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
     // instead of one per pass); the loads are issued together with the input loads below
     Cx<T> *stw = s + padded_elems<HB_PADSH>(B);
     Cx<T> twr[EPT];
-    if (stage_tw) twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n, stage_tw == 2);
+    if (stage_tw) twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
     // rotated frame [newest B | previous B], de-interleaved on the way in: z[k] = frame[2k] + i frame[2k+1].
     // Every thread issues all of its loads before the first store, so their latencies overlap.
     const T *pn = newest + size_t(ch) * new_ld, *pp = prev + size_t(ch) * prev_ld;
@@ -643,9 +643,9 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
     }
     if (stage_tw)
     {
-        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n, stage_tw == 2);
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
         tw = stw;
-        tw_log2 = (int) g.log2n | (stage_tw == 2 ? TW_QUARTER : 0);
+        tw_log2 = (int) g.log2n;
     }
     __syncthreads();
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, tw, tw_log2);
@@ -759,10 +759,10 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
         // twiddles of this transform size into shared memory (published by the barriers of block_sum below)
         Cx<T> *stw = s + padded_elems<HB_PADSH>(B);
         Cx<T> twr[EPT];
-        twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n, stage_tw == 2);
-        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n, stage_tw == 2);
+        twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
         tw = stw;
-        tw_log2 = (int) g.log2n | (stage_tw == 2 ? TW_QUARTER : 0);
+        tw_log2 = (int) g.log2n;
     }
 
     if (carry_dst)

@@ -94,9 +94,9 @@ __device__ __forceinline__ void block_real_split(Cx<T> *s, uint32_t M, int log2N
 // transform) copied from the device table into shared memory, EPT per thread.  The loads are returned in
 // registers so that the caller can issue them together with its own input loads and store later.
 template <class T, int EPT>
-__device__ __forceinline__ void twiddle_stage_load(Cx<T> *r, const Cx<T> *__restrict__ tw, int tw_log2, int log2n, int quarter = 0)
+__device__ __forceinline__ void twiddle_stage_load(Cx<T> *r, const Cx<T> *__restrict__ tw, int tw_log2, int log2n)
 {
-    const uint32_t count = (1u << (log2n - 1)) >> (quarter ? 1 : 0);
+    const uint32_t count = 1u << (log2n - 1);
     const int sh = tw_log2 - log2n;
 #pragma unroll
     for (int e = 0; e < EPT; e++)
@@ -106,9 +106,9 @@ __device__ __forceinline__ void twiddle_stage_load(Cx<T> *r, const Cx<T> *__rest
     }
 }
 template <class T, int EPT>
-__device__ __forceinline__ void twiddle_stage_store(Cx<T> *stw, const Cx<T> *r, int log2n, int quarter = 0)
+__device__ __forceinline__ void twiddle_stage_store(Cx<T> *stw, const Cx<T> *r, int log2n)
 {
-    const uint32_t count = (1u << (log2n - 1)) >> (quarter ? 1 : 0);
+    const uint32_t count = 1u << (log2n - 1);
 #pragma unroll
     for (int e = 0; e < EPT; e++)
     {

@@ -39,33 +39,17 @@ template <class T> HB_HD Cx<T> mul_pi(Cx<T> a) { return cx<T>(-a.y, a.x); }
 // Twiddle table: tw[q] = exp(-2 pi i q / 2^tw_log2) for q in [0, 2^(tw_log2-1)) (half circle),
 // computed in double on the host and rounded to T like the reference's tables (Core:414-448).
 // root(a, l) = exp(-2 pi i a / 2^l), a < 2^l, l <= tw_log2.
-// The table holds the half circle of order 2^tw_log2.  With TW_QUARTER set in tw_log2 it holds only the first quarter
-// (2^(tw_log2 - 2) entries; a shared-memory copy where the half circle does not fit beside the data): the second
-// quarter follows from w(q + quarter) = -i w(q).
-constexpr int TW_QUARTER = 0x100;
 template <class T>
 HB_HD Cx<T> tw_root(const Cx<T> *tw, int tw_log2, uint32_t a, int l)
 {
-    const int L = tw_log2 & 0xFF;
-    uint32_t q = a << (L - l);
-    const uint32_t half = 1u << (L - 1);
-    const bool neg = q >= half;
-    if (neg) q -= half;
-    Cx<T> w;
-    if (tw_log2 & TW_QUARTER)
+    uint32_t q = a << (tw_log2 - l);
+    uint32_t half = 1u << (tw_log2 - 1);
+    if (q >= half)
     {
-        const uint32_t quarter = half >> 1;
-        if (q >= quarter)
-        {
-            const Cx<T> v = tw[q - quarter];
-            w = cx<T>(v.y, -v.x);
-        }
-        else
-            w = tw[q];
+        Cx<T> w = tw[q - half];
+        return cx<T>(-w.x, -w.y);
     }
-    else
-        w = tw[q];
-    return neg ? cx<T>(-w.x, -w.y) : w;
+    return tw[q];
 }
 
 // shared-memory index with optional padding (one extra slot every 2^PADSH elements)
