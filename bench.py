@@ -57,6 +57,11 @@ WORKLOADS = {
     "c3": (8, 1, 1, 131072, 2048, "f32", "NToMonoConvolve 8-in->1-out, 131072-tap IRs, 2048-sample blocks, float"),
     "c4": (64, 64, 1, 262144, 4096, "f32", "Convolver 64-in x 64-out, 262144-tap IRs, 4096-sample blocks, float"),
     "c5": (1, 1, 16, 1048576, 8192, "f64", "PartitionedConvolve double: 16ch, 1M-tap IR, 8192-sample blocks"),
+    # one rank's share of config 4 when its inputs are sharded over 2 / 4 / 8 GPUs, runnable on ONE GPU (ncu cannot wrap a
+    # multi-rank command): the source of profiles/traffic.json's c4_n2 / c4_n4 / c4_n8 entries
+    "c4r2": (32, 64, 1, 262144, 4096, "f32", "one rank of config 4 sharded over 2 GPUs: 32-in x 64-out, 262144-tap IRs, 4096-sample blocks"),
+    "c4r4": (16, 64, 1, 262144, 4096, "f32", "one rank of config 4 sharded over 4 GPUs: 16-in x 64-out, 262144-tap IRs, 4096-sample blocks"),
+    "c4r8": (8, 64, 1, 262144, 4096, "f32", "one rank of config 4 sharded over 8 GPUs: 8-in x 64-out, 262144-tap IRs, 4096-sample blocks"),
 }
 
 
