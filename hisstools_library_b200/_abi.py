@@ -83,6 +83,8 @@ SIGNATURES = {
     "hb_conv_set_profiling": (C.c_int, [V, C.c_int]),
     "hb_conv_get_profile": (C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "hb_conv_set_multi_hop": (C.c_int, [V, C.c_int]),
+    "hb_conv_set_fft_path": (C.c_int, [V, C.c_int]),
+    "hb_conv_fft_path": (C.c_int, [V]),
     "hb_conv_set_trace": (C.c_int, [V, C.c_int]),
     "hb_conv_get_trace": (C.c_int, [V, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_conv_set_schedule": (C.c_int, [V, C.c_int]),

@@ -140,6 +140,14 @@ class _Engine:
         _abi.check(_abi.lib().hb_conv_get_profile(self._h, ms, C.byref(h)))
         return dict(zip(("forward", "cmac", "wait", "inverse", "tail"), [float(v) for v in ms])), int(h.value)
 
+    def set_fft_path(self, path=0):
+        """0 automatic, 1 one CTA per transform, 2 cluster of 8 CTAs, 3 four-step (hb_conv_set_fft_path)."""
+        return _abi.check(_abi.lib().hb_conv_set_fft_path(self._h, int(path)))
+
+    @property
+    def fft_path(self):
+        return _abi.lib().hb_conv_fft_path(self._h)
+
     def set_multi_hop(self, enable=True):
         return _abi.check(_abi.lib().hb_conv_set_multi_hop(self._h, 1 if enable else 0))
 

@@ -11,6 +11,7 @@
 #include "hb_common.cuh"
 #include "hb_conv_kernels.cuh"
 #include "hb_conv_big.cuh"
+#include "hb_conv_cluster.cuh"
 #include "hb_conv_fused.cuh"
 
 #include <algorithm>
@@ -114,6 +115,7 @@ struct hb_conv
     int multi_hop = 1;              // hb_conv_set_multi_hop: batch the hops of one call over a single pass of the IR spectra
     bool mh_ok = false;             // eligible for the current geometry (plan_geometry)
     int mh_stages = 3;
+    int fft_path = 0;               // hb_conv_set_fft_path: 0 automatic, 1 one CTA per transform, 2 cluster of 8 CTAs, 3 four-step
     BigScratch big;                 // four-step scratch for FFT sizes above the single-CTA limit (hb_conv_big.cuh)
     DevBuf d_nyq;
 
@@ -154,6 +156,29 @@ struct hb_conv
 
 namespace
 {
+
+// largest half-length transform (log2 of complex points) run as one CTA in shared memory; above it the four-step
+// chains of hb_conv_big.cuh take over.  HB_BIG_FROM (experiments only) lowers the switch-over, down to 2^12 points.
+int single_cta_max_log2m(const hb_conv *c)
+{
+    const int lim = c->dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m;
+    static const char *env = getenv("HB_BIG_FROM");
+    if (env && atoi(env) >= 12) return std::min(lim, atoi(env) - 1);
+    if (c->fft_path == 3) return std::min(lim, 11);
+    return lim;
+}
+
+// transforms spread over clusters of 8 CTAs (hb_conv_cluster.cuh).  Automatic choice: double precision with fewer
+// transforms than two per SM -- there the one-CTA kernels are bound by the FP64 pipe of the few SMs they occupy
+// (config 5: 38 us forward, 60-86 us inverse on 16 SMs; profiles/r1_c5_cluster_fft.txt).
+bool use_cluster_fft(const hb_conv *c)
+{
+    const int m = (int) c->g.log2n - 1;
+    if (c->fft_path == 1 || c->fft_path == 3 || c->fused) return false;
+    if (m < CL_MIN_LOG2M || m > single_cta_max_log2m(c) || c->g.n_bt > (uint32_t) CL_MAX_SEG_TILES) return false;
+    if (c->fft_path == 2) return true;
+    return c->dtype == HB_F64 && uint64_t(c->groups) * std::max(c->ins, c->outs) <= 2 * (uint64_t) c->sm_count;
+}
 
 // ---- geometry -------------------------------------------------------------------------------------
 uint32_t choose_ot(uint32_t outs)
@@ -243,8 +268,11 @@ void plan_geometry(hb_conv *c)
         const size_t budget = 227 * 1024 > fft_total + 2048 ? 227 * 1024 - fft_total - 2048 : 0;
         const int st_co = (int) (budget / stage);
         const uint64_t fft_ctas = uint64_t(g.groups) * std::max(g.ins, g.outs);
-        if (c->variant == 1 && !(log2m <= 12 && st_co >= st)) reserve = std::min<uint64_t>(fft_ctas, sms / 4);
+        // (the four-step and the cluster kernels are small CTAs: they fit beside the ring)
+        if (c->variant == 1 && !(log2m <= 12 && st_co >= st) && (int) log2m <= single_cta_max_log2m(c) && !use_cluster_fft(c)) reserve = std::min<uint64_t>(fft_ctas, sms / 4);
     }
+    // cluster FFT CTAs (up to 42 KiB) are placed beside the resident tail CTA: leave them room
+    if (c->split && c->variant == 1 && use_cluster_fft(c)) st = std::min<int>(st, (int) ((227 * 1024 - 48 * 1024) / stage));
     static const char *env_st = getenv("HB_STAGES"), *env_rs = getenv("HB_RESERVE");          // experiments only
     if (env_st && atoi(env_st) >= 2) st = std::min<int>(atoi(env_st), (int) ((220 * 1024) / stage));
     if (env_rs && c->split) reserve = std::min<uint64_t>((uint64_t) atoi(env_rs), sms - 1);
@@ -256,7 +284,7 @@ void plan_geometry(hb_conv *c)
         const size_t stage_mh = size_t(g.Q + MH_MAX * g.TBV) * 16;
         c->mh_stages = (int) std::min<size_t>(3, (200 * 1024) / stage_mh);
         c->mh_ok = c->multi_hop && c->variant == 1 && !c->fused && tail_bytes >= (uint64_t(4) << 20) && g.OT >= 8 &&
-                   ((g.XA == 1 && g.OB == 8) || (g.XA == 2 && g.OB == 4)) && (int) log2m <= (c->dtype == HB_F64 ? SmemFftLimit<double>::max_log2m : SmemFftLimit<float>::max_log2m) &&
+                   ((g.XA == 1 && g.OB == 8) || (g.XA == 2 && g.OB == 4)) && (int) log2m <= single_cta_max_log2m(c) &&
                    c->mh_stages >= 2;
     }
     c->r_full = make_range(0, g.P, sms * per_sm);
@@ -453,7 +481,7 @@ int launch_fwd_ept(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     return HB_OK;
 }
 
-template <class T> bool is_big(const hb_conv *c) { return (int) c->g.log2n - 1 > SmemFftLimit<T>::max_log2m; }
+template <class T> bool is_big(const hb_conv *c) { return (int) c->g.log2n - 1 > single_cta_max_log2m(c); }
 inline dim3 bigc_grid(uint32_t B, size_t batch) { return dim3((unsigned) std::min<size_t>((B + 255) / 256, 256), (unsigned) batch); }
 
 // forward transform of every input channel at sizes above the single-CTA limit (hb_conv_big.cuh)
@@ -476,12 +504,28 @@ int launch_fwd_big(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     return HB_OK;
 }
 
+// forward transform of every input channel on clusters of 8 CTAs (hb_conv_cluster.cuh)
+template <class T>
+int launch_fwd_cl(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const int m = (int) g.log2n - 1;
+    const size_t smem = cl_fwd_smem<T>(m);
+    int rc = allow_smem(k_fwd_cl<T>, smem);
+    if (rc) return rc;
+    k_fwd_cl<T><<<g.groups * g.ins * CL_CS, (1u << m) / (CL_CS * CL_EPT), smem, st>>>(g, prev, prev_ld, newest, new_ld, save, save_ld, (Cx<T> *) c->d_X, (T *) c->d_Xnyq,
+                                                                                    (const Cx<T> *) c->d_tw, c->tw_log2);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
 // nh > 1: the forward transforms of nh consecutive hops in one launch (hop j from block j of the caller's rows into slot
 // c->g.slot - j; single-CTA transforms only)
 template <class T>
 int launch_fwd(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, cudaStream_t st, uint32_t nh = 1)
 {
     if (is_big<T>(c)) return launch_fwd_big<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st);
+    if (nh == 1 && use_cluster_fft(c)) return launch_fwd_cl<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, st);
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_fwd_ept<T, EPT>(c, prev, prev_ld, newest, new_ld, save, save_ld, st, nh));
 }
 
@@ -532,6 +576,22 @@ int launch_inv_big(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStre
     return HB_OK;
 }
 
+// inverse transform of every output channel on clusters of 8 CTAs (hb_conv_cluster.cuh)
+template <class T>
+int launch_inv_cl(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const int m = (int) g.log2n - 1;
+    const size_t smem = cl_inv_smem<T>(m, g.n_bt);
+    int rc = allow_smem(k_inv_cl<T>, smem);
+    if (rc) return rc;
+    k_inv_cl<T><<<g.groups * g.outs * CL_CS, (1u << m) / (CL_CS * CL_EPT), smem, st>>>(g, sets, (const T *) c->d_Xnyq, (const T *) c->d_Hnyq, io.yout, io.ld, io.off, io.add_result,
+                                                                                     io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry,
+                                                                                     (const Cx<T> *) c->d_tw, c->tw_log2);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
 inline InvBatch no_batch() { InvBatch ib; memset(&ib, 0, sizeof(ib)); ib.last_j = -1; return ib; }
 
 // nh > 1: the inverse transforms of nh consecutive hops in one launch (hop j: segment sets ib.set_stride apart, block j of the
@@ -545,6 +605,7 @@ int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t
         if (peer.world) { set_error("the fused multi-GPU exchange is not implemented for FFT sizes above the single-CTA limit"); return HB_ERR_UNSUPPORTED; }
         return launch_inv_big<T>(c, sets, io, st);
     }
+    if (nh == 1 && ib.last_j < 0 && !peer.world && use_cluster_fft(c)) return launch_inv_cl<T>(c, sets, io, st);
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer, nh, ib));
 }
 
@@ -1592,6 +1653,24 @@ extern "C" int hb_conv_set_schedule(hb_conv *c, int overlapped)
     c->schedule = overlapped;
     c->need_reset = true;           // the partial-segment sets depend on the schedule
     return HB_OK;
+}
+
+extern "C" int hb_conv_set_fft_path(hb_conv *c, int path)
+{
+    if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    if (path < 0 || path > 3) { set_error("fft path must be 0 (automatic), 1 (one CTA per transform), 2 (cluster of 8 CTAs) or 3 (four-step)"); return HB_ERR_BAD_ARG; }
+    c->fft_path = path;
+    c->need_reset = true;           // the tail grid depends on where the FFT CTAs run
+    return HB_OK;
+}
+
+extern "C" int hb_conv_fft_path(const hb_conv *c)
+{
+    if (!c) return -1;
+    const int m = (int) c->g.log2n - 1;
+    if (m > single_cta_max_log2m(c)) return 3;
+    return use_cluster_fft(c) ? 2 : 1;
 }
 
 extern "C" int hb_conv_set_multi_hop(hb_conv *c, int enable)

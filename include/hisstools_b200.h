@@ -189,6 +189,15 @@ uint64_t hb_conv_bytes_per_launch(const hb_conv *c);
  * spectrum ONCE for up to four hops (k_cmac_tma_mh) instead of once per hop.  Same result up to summation order;
  * enable = 0 processes such calls hop by hop.  Takes effect with a reset. */
 int hb_conv_set_multi_hop(hb_conv *c, int enable);
+/* Where the forward / inverse transforms of a hop run.  0 (default, automatic), 1: one CTA per channel (k_fwd / k_inv);
+ * 2: every transform spread over a thread-block cluster of 8 CTAs exchanging through distributed shared memory
+ * (hb_conv_cluster.cuh; transforms of 2^11 points up to the one-CTA limit, single hops, not the fused multi-GPU exchange --
+ * otherwise the one-CTA kernels run); 3: the four-step chains over global memory (hb_conv_big.cuh) from 2^12 points.
+ * Automatic = 2 for double-precision engines with fewer transforms than two per SM, whose one-CTA transforms are bound
+ * by the FP64 pipe of the few SMs they occupy; sizes above the one-CTA limit always take the four-step chains.
+ * Results differ by rounding only.  Takes effect with a reset.  hb_conv_fft_path: the path in effect (1, 2 or 3). */
+int hb_conv_set_fft_path(hb_conv *c, int path);
+int hb_conv_fft_path(const hb_conv *c);
 /* Kernel timeline (debug): while enabled, thread 0 of every CTA of the hop kernels stamps %globaltimer at entry
  * and exit.  hb_conv_get_trace synchronises the device and copies the HB_TRACE_WORDS stamps out:
  * out[(((hop % 16) * 5 + kind) * 2 + exit) * 256 + cta], kind 0 forward FFT, 1 head, 2 tail / whole

@@ -310,6 +310,53 @@ def test_pconv_semantics(hb):
     assert ck.rel_rms(a, ck.direct_convolve_delayed(ir, x, 128)) <= TOL32
 
 
+@pytest.mark.parametrize("schedule", ["overlapped", "serial"])
+@pytest.mark.parametrize("dtype,B", [(np.float32, 2048), (np.float32, 8192), (np.float32, 16384), (np.float64, 2048), (np.float64, 4096), (np.float64, 8192)])
+def test_fft_paths_agree(hb, dtype, B, schedule):
+    """hb_conv_set_fft_path: transforms on clusters of 8 CTAs (distributed shared memory, hb_conv_cluster.cuh) and the
+    four-step chains against one CTA per transform, on a 2-group 2-in x 3-out matrix with ragged call sizes (hand-over of
+    the previous block, accumulation into the caller's rows), and against float64 direct convolution."""
+    from hisstools_library_b200.convolve import _Engine
+    groups, n_in, n_out = 2, 2, 3
+    L = 3 * B + 100
+    tol = TOL32 if dtype == np.float32 else TOL64
+    irs = {(g, o, i): ck.synth_ir(L, 700 + 100 * g + 10 * o + i).astype(dtype) for g in range(groups) for o in range(n_out) for i in range(n_in)}
+    xs = np.stack([ck.synth_audio(B * 6 + 77, 700 + i) for i in range(groups * n_in)]).astype(dtype)
+    sizes = [B, B, 100, 2 * B, 1, B + 5, B]
+    outs = {}
+    for path in (1, 2, 3):
+        if path == 3 and B < 4096:
+            continue
+        e = _Engine(dtype, groups, n_in, n_out, 2 * B, L, 0, 0, 0)
+        e.set_schedule(schedule == "overlapped")
+        e.set_multi_hop(False)
+        e.set_fft_path(path)
+        e.set_reset_offset(0)
+        for (g, o, i), ir in irs.items():
+            e.set_ir(g, i, o, ir, L)
+        y = np.zeros((groups * n_out, xs.shape[1]), dtype)
+        pos, k = 0, 0
+        while pos < xs.shape[1]:
+            n = min(sizes[k % len(sizes)], xs.shape[1] - pos)
+            xi = [np.ascontiguousarray(xs[r, pos:pos + n]) for r in range(groups * n_in)]
+            yo = [np.zeros(n, dtype) for _ in range(groups * n_out)]
+            e.process(xi, yo, n)
+            for r in range(groups * n_out):
+                y[r, pos:pos + n] = yo[r]
+            pos += n
+            k += 1
+        assert e.fft_path == path
+        outs[path] = y
+        e.close()
+    for path in outs:
+        for r in range(groups * n_out):
+            assert ck.rel_rms(outs[path][r], outs[1][r]) <= (2e-6 if dtype == np.float32 else 1e-14), (path, r)
+    for g in range(groups):
+        for o in range(n_out):
+            truth = sum(ck.direct_convolve_delayed_fft(irs[(g, o, i)], xs[g * n_in + i], B) for i in range(n_in))
+            assert ck.rel_rms(outs[2][g * n_out + o], truth) <= tol * (1 if dtype == np.float32 else 10)
+
+
 def test_pconv_double_engine(hb):
     """double engine against the restated double loop on the reference's own double FFT (golden) and
     against float64 direct convolution; BASELINE config 5 tolerance 1e-12."""

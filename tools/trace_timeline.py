@@ -59,6 +59,14 @@ def main():
             e, x_ = ent[m].astype(np.int64) - t0, ext[m].astype(np.int64) - t0
             print("hop %3d %-4s ctas %3d  first entry %9.1f us  last entry %9.1f us  first exit %9.1f us  last exit %9.1f us" %
                   (h, KIND[k], int(m.sum()), e.min() / 1e3, e.max() / 1e3, x_[x_ > -t0 // 2].min() / 1e3 if (x_ > -t0 // 2).any() else -1, x_.max() / 1e3))
+    if os.environ.get("HB_TRACE_DETAIL"):
+        # per-CTA entry / exit of one kind in the last complete hop (e.g. HB_TRACE_DETAIL=inv)
+        k = KIND.index(os.environ["HB_TRACE_DETAIL"])
+        h = hop - 2
+        ent, ext = tr[h % 16, k, 0].astype(np.int64), tr[h % 16, k, 1].astype(np.int64)
+        idx = np.nonzero(ent > 0)[0]
+        print("hop %d %s, per CTA (entry, exit) in us:" % (h, KIND[k]))
+        print(" ".join("%d:(%.1f,%.1f)" % (i, (ent[i] - t0) / 1e3, (ext[i] - t0) / 1e3) for i in idx))
     eng.close()
 
 
