@@ -290,6 +290,21 @@ void plan_geometry(hb_conv *c)
     c->r_full = make_range(0, g.P, sms * per_sm);
     c->r_head = make_range(0, g.P ? 1 : 0, sms);
     c->r_tail = make_range(1, g.P ? g.P - 1 : 0, (sms - reserve) * per_sm);
+    {
+        // L2 policy of the streamed copies.  IR units: evict_first (read once per hop, gigabytes).  FDL tiles: evict_last while
+        // the whole delay line (re-read every hop) can stay in the 126 MB L2; a delay line larger than that cannot be kept, and
+        // marking it evict_last only costs bandwidth (config 5, 256 MiB: 95.0 -> 88.7 us per hop with evict_first).  Keeping a
+        // SUBSET of the IR or of a large FDL resident with evict_last was measured too and is slower than plain streaming
+        // (profiles/r1_l2_policy.txt).  HB_PIN_P / HB_PIN_S: experiments only.
+        static const char *env_pp = getenv("HB_PIN_P"), *env_ps = getenv("HB_PIN_S");
+        const uint64_t fdl_bytes = uint64_t(g.groups) * g.ins * g.n_bt * g.R * g.TBV * 16;
+        Range *rs[3] = {&c->r_full, &c->r_head, &c->r_tail};
+        for (Range *r : rs)
+        {
+            r->pin_p = env_pp ? (uint32_t) atoi(env_pp) : 0u;
+            r->pin_s = env_ps ? (uint32_t) atoi(env_ps) : (fdl_bytes <= (uint64_t(64) << 20) ? g.R : 0u);
+        }
+    }
     g.G = c->r_full.G;
 }
 

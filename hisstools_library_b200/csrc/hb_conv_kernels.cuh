@@ -81,6 +81,8 @@ struct Range
     uint32_t G;            // CTAs of this launch
     uint32_t slot;         // FDL slot of the spectrum that meets partition 0
     uint32_t kind;         // trace only: 1 head, 2 tail / whole
+    uint32_t pin_p;        // L2 residency (k_cmac_tma): IR units of partitions p < pin_p are loaded evict_last, the others evict_first
+    uint32_t pin_s;        // FDL tiles of ring slots s < pin_s are loaded evict_last, the others evict_first
     uint64_t U;            // units of this launch = tiles*upt
 };
 
@@ -195,6 +197,13 @@ struct Cursor
     {
         return ((uint64_t(tile) * g.ins + in) * g.Pcap + p) * g.Q;
     }
+    // ring slot of the matching FDL tile
+    __device__ __forceinline__ uint32_t x_slot(const Geom &g, const Range &r) const
+    {
+        uint32_t s = r.slot + p;
+        if (s >= g.R) s -= g.R;
+        return s;
+    }
     // vector offset of the matching FDL tile
     __device__ __forceinline__ uint64_t x_off(const Geom &g, const Range &r) const
     {
@@ -246,20 +255,20 @@ __global__ void HB_CMAC_BOUNDS k_cmac_tma(const Geom g, const Range rg, const ty
     __syncthreads();
 
     Cursor prod;
-    uint64_t pol_h = 0, pol_x = 0;
+    uint64_t pol_first = 0, pol_last = 0;
     uint32_t issued = 0;
     const uint32_t h_bytes = g.Q * (uint32_t) sizeof(V), x_bytes = g.TBV * (uint32_t) sizeof(V);
     if (tid == 0)
     {
-        pol_h = l2_policy_evict_first();
-        pol_x = l2_policy_evict_last();
+        pol_first = l2_policy_evict_first();
+        pol_last = l2_policy_evict_last();
         prod.seek(rg, u0);
         for (; issued < n && issued + 1 < (uint32_t) nstages; issued++)
         {
             V *dst = ring + size_t(issued) * stage_vecs;
             mbar_expect_tx(&full[issued], h_bytes + x_bytes);
-            bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[issued], pol_h);
-            bulk_g2s(dst + g.Q, X + prod.x_off(g, rg), x_bytes, &full[issued], pol_x);
+            bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[issued], prod.p < rg.pin_p ? pol_last : pol_first);
+            bulk_g2s(dst + g.Q, X + prod.x_off(g, rg), x_bytes, &full[issued], prod.x_slot(g, rg) < rg.pin_s ? pol_last : pol_first);
             prod.advance(g, rg);
         }
     }
@@ -279,8 +288,8 @@ __global__ void HB_CMAC_BOUNDS k_cmac_tma(const Geom g, const Range rg, const ty
             uint32_t ps = stage ? stage - 1 : nstages - 1;
             V *dst = ring + size_t(ps) * stage_vecs;
             mbar_expect_tx(&full[ps], h_bytes + x_bytes);
-            bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[ps], pol_h);
-            bulk_g2s(dst + g.Q, X + prod.x_off(g, rg), x_bytes, &full[ps], pol_x);
+            bulk_g2s(dst, H + prod.h_off(g), h_bytes, &full[ps], prod.p < rg.pin_p ? pol_last : pol_first);
+            bulk_g2s(dst + g.Q, X + prod.x_off(g, rg), x_bytes, &full[ps], prod.x_slot(g, rg) < rg.pin_s ? pol_last : pol_first);
             prod.advance(g, rg);
             issued++;
         }
