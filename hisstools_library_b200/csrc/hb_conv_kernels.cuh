@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(288, 1) k_cmac_tma_mh(const Geom g, const Rang
     if (tid == 256)
     {
         pol_h = l2_policy_evict_first();
-        pol_x = l2_policy_evict_last();
+        pol_x = rg.pin_s ? l2_policy_evict_last() : l2_policy_evict_first();     // delay line kept in L2 only while it fits (plan_geometry)
         prod.seek(rg, u0);
         while (issued < n && issued + 1 < (uint32_t) nstages) issue(issued);
     }
