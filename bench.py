@@ -412,6 +412,8 @@ def run_ours(args):
         yh = torch.zeros(y_shard.shape, dtype=tdt).pin_memory()
         xd = torch.empty_like(x_pool[0])
 
+        got = torch.cuda.Event()
+
         def e2e_step(k):
             xd.copy_(xh[k % n_pool], non_blocking=True)
             if sharded is not None:
@@ -419,13 +421,18 @@ def run_ours(args):
             else:
                 eng.process_device(xd.data_ptr(), n, y_part.data_ptr(), n, n, False, stream.cuda_stream)
             yh.copy_(y_shard, non_blocking=True)
-            torch.cuda.synchronize()
+            # the step is over when its result is in host memory; the tail of the NEXT hop, launched ahead on the engine's
+            # second stream, keeps running behind this wait as it does in the device-resident loop (the final barrier +
+            # synchronize below puts what is left of it inside the timed region)
+            got.record(stream)
+            got.synchronize()
         for k in range(e2e_warm):
             e2e_step(k)
         barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
             e2e_step(k)
+        torch.cuda.synchronize()
         barrier()
         e2e_s = time.perf_counter() - t0
         d2h = y_shard.numel() * es
