@@ -276,6 +276,8 @@ def run_ours(args):
         eng.set_tuning(args.ctas_per_sm, args.variant)
     if args.schedule is not None:
         eng.set_schedule(args.schedule == "overlapped")
+    if args.fft_path:
+        eng.set_fft_path(args.fft_path)
     gen = torch.Generator(device=dev)
     decay = torch.exp(-6.9 * torch.arange(taps, device=dev, dtype=torch.float64) / taps).to(tdt)
     for g in range(l_groups):
@@ -469,6 +471,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": desc, "hops_per_step": args.hops, "samples_per_step_per_channel": n, "partitions": P,
                            "sharding": mode, "local_inputs": l_ins, "outputs": outs, "groups": l_groups, "schedule": eng.schedule,
+                           "transforms": {1: "one CTA each", 2: "cluster of 8 CTAs each (DSMEM)", 3: "four-step chains"}.get(eng.fft_path, "?"),
                            "l2": "inputs larger than L2: %.2f GiB of IR spectra per rank streamed every step" % (bytes_per_hop / 2 ** 30)
                                  if bytes_per_hop > 256e6 else "working set %.1f MiB is L2-resident (not an HBM-roofline case)" % (bytes_per_hop / 2 ** 20),
                            "collective": ("peer stores fused into the inverse-FFT epilogue (NVLink), owner-side sum" if sharded is not None and sharded.exchange == "fused"
@@ -500,6 +503,8 @@ def main():
     ap.add_argument("--variant", type=int, default=None, help="multiply-accumulate kernel: 1 = TMA ring, 0 = direct loads")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--schedule", default=None, choices=["overlapped", "serial"], help="hop schedule (default: the library's automatic choice)")
+    ap.add_argument("--fft-path", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="transforms: 0 automatic, 1 one CTA each, 2 cluster of 8 CTAs each, 3 four-step chains (hb_conv_set_fft_path)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"], help="multi-GPU sum of partial outputs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-multi-hop", action="store_true", help="skip the multi-hop reuse leg")
