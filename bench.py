@@ -477,7 +477,10 @@ def run_ours(args):
                            "collective": ("peer stores fused into the inverse-FFT epilogue (NVLink), owner-side sum" if sharded is not None and sharded.exchange == "fused"
                                           else "nccl reduce_scatter of partial output blocks") if mode == "inputs" else "none"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "api": "hb_conv_process (host pointers)" if world == 1 else "pinned H2D + ShardedConvolver.process_device (hb_matrix_process_dev + NCCL reduce_scatter) + D2H"},
+                        "api": "hb_conv_process (host pointers)" if world == 1 else
+                               "pinned H2D + ShardedConvolver.process_device (%s) + D2H of this rank's output rows, waiting on the result event" %
+                               ("hb_conv_process_shard_dev: peer stores from the inverse-FFT epilogue" if sharded is not None and sharded.exchange == "fused"
+                                else "hb_matrix_process_dev + NCCL reduce_scatter")},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
