@@ -169,7 +169,7 @@ int single_cta_max_log2m(const hb_conv *c)
 }
 
 // transforms spread over clusters of 8 CTAs (hb_conv_cluster.cuh).  Automatic choice: double precision with fewer
-// transforms than two per SM -- there the one-CTA kernels are bound by the FP64 pipe of the few SMs they occupy
+// transforms than two per SM -- there the one-CTA kernels are latency-bound on the few SMs they occupy and set the hop period
 // (config 5: 38 us forward, 60-86 us inverse on 16 SMs; profiles/r1_c5_cluster_fft.txt).
 bool use_cluster_fft(const hb_conv *c)
 {

@@ -2,9 +2,10 @@
 // thread-block CLUSTER of 8 CTAs (distributed shared memory), for engines whose transforms are few and expensive.
 //
 // Why: one CTA per channel (k_fwd / k_inv) leaves a 16-channel double-precision engine (BASELINE config 5: 16 x 8192
-// complex points) on 16 SMs, where the transforms are bound by the FP64 pipe of their SM (ncu: pipe_fp64 92 % active,
-// 38 us forward, 60-86 us inverse beside the streaming multiply-accumulate -- profiles/r1_c5_cluster_fft.txt); the
-// FFT kernels, not HBM, then set the hop period.  Eight CTAs per transform put the same arithmetic on 128 SMs.
+// complex points) on 16 SMs, where each transform is a chain of dependent shared-memory passes and global round trips on
+// 16 warps (ncu: 25 % issue slots busy, 16 cycles per issued instruction; 38 us forward, 60-86 us inverse beside the
+// streaming multiply-accumulate -- profiles/r1_c5_cluster_fft.txt); the FFT kernels, not HBM, then set the hop period.
+// Eight CTAs per transform put the same work on 128 SMs with an eighth of the passes' length each.
 //
 // Decomposition of the M-point complex transform (M = 8 L), decimation in time over the cluster rank r:
 //   rank r      local L-point Stockham transform (hb_fft_block.cuh) of the decimated sequence z[8 n + r]  ->  Y_r[k2]

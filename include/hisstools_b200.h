@@ -193,8 +193,8 @@ int hb_conv_set_multi_hop(hb_conv *c, int enable);
  * 2: every transform spread over a thread-block cluster of 8 CTAs exchanging through distributed shared memory
  * (hb_conv_cluster.cuh; transforms of 2^11 points up to the one-CTA limit, single hops, not the fused multi-GPU exchange --
  * otherwise the one-CTA kernels run); 3: the four-step chains over global memory (hb_conv_big.cuh) from 2^12 points.
- * Automatic = 2 for double-precision engines with fewer transforms than two per SM, whose one-CTA transforms are bound
- * by the FP64 pipe of the few SMs they occupy; sizes above the one-CTA limit always take the four-step chains.
+ * Automatic = 2 for double-precision engines with fewer transforms than two per SM, whose one-CTA transforms (long,
+ * latency-bound, on a few SMs) would otherwise set the hop period; sizes above the one-CTA limit always take the four-step chains.
  * Results differ by rounding only.  Takes effect with a reset.  hb_conv_fft_path: the path in effect (1, 2 or 3). */
 int hb_conv_set_fft_path(hb_conv *c, int path);
 int hb_conv_fft_path(const hb_conv *c);
