@@ -50,6 +50,8 @@ SIGNATURES = {
     "hb_conv_shard_export": (C.c_int, [V, U32, U32, V]),
     "hb_conv_shard_attach": (C.c_int, [V, V]),
     "hb_conv_process_shard_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
+    "hb_conv_shard_status": (C.c_int, [V, C.POINTER(U32)]),
+    "hb_conv_join": (C.c_int, [V, V]),
     "hb_conv_set_tuning": (C.c_int, [V, C.c_int, C.c_int]),
     "hb_conv_set_host_pipeline": (C.c_int, [V, C.c_int]),
     "hb_conv_bytes_per_hop": (C.c_uint64, [V]),

@@ -130,6 +130,16 @@ class _Engine:
         return _abi.check(_abi.lib().hb_conv_process_shard_dev(self._h, C.c_void_p(in_ptr), int(in_ld), C.c_void_p(out_ptr), int(out_ld),
                                                                int(n), 1 if accumulate else 0, C.c_void_p(stream)))
 
+    def shard_status(self):
+        """bit mask of the ranks whose blocks the owner-side sum stopped waiting for (0 = none was ever late)"""
+        late = C.c_uint32()
+        _abi.check(_abi.lib().hb_conv_shard_status(self._h, C.byref(late)))
+        return int(late.value)
+
+    def join(self, stream=0):
+        """make `stream` wait for the tail the overlapped schedule launched ahead (hb_conv_join)"""
+        return _abi.check(_abi.lib().hb_conv_join(self._h, C.c_void_p(stream)))
+
     def set_profiling(self, enable=True):
         return _abi.check(_abi.lib().hb_conv_set_profiling(self._h, 1 if enable else 0))
 

@@ -25,6 +25,7 @@ namespace
 {
 constexpr uintptr_t MIN_FFT_LOG2 = 5;       // PartitionedConvolve.h:18
 constexpr uintptr_t MAX_FFT_LOG2 = 20;      // PartitionedConvolve.h:19
+constexpr size_t INBOX_LATE_OFF = 192;     // inbox tail: arrival counters [2][world] (<= 128 bytes), then the late-peer flag word
 constexpr uint32_t MH_MAX = 4;              // hops one multi-hop multiply-accumulate launch covers at most
 constexpr uint32_t MH_EXTRA = MH_MAX - 1;   // extra delay-line slots that needs
 
@@ -351,6 +352,13 @@ void free_device(hb_conv *c)
     c->blk_valid = false;
 }
 
+// Nyquist side arrays are sized for the smallest hop the object may be switched to
+size_t nyq_capacity(const hb_conv *c)
+{
+    const size_t minB = size_t(1) << (MIN_FFT_LOG2 - 1);
+    return c->max_length / minB + MH_EXTRA;
+}
+
 // allocate everything whose size depends on max_length (ctor and resize)
 int alloc_capacity(hb_conv *c)
 {
@@ -359,9 +367,7 @@ int alloc_capacity(hb_conv *c)
     const size_t hbytes = h_vectors(c) * 16;
     const size_t maxB_ = (size_t(1) << c->max_fft_log2) >> 1;
     const size_t xbytes = size_t(c->groups) * c->ins * (c->max_length + MH_EXTRA * maxB_) * 2 * c->esize();
-    // Nyquist side arrays are sized for the smallest hop the object may be switched to
-    const size_t minB = size_t(1) << (MIN_FFT_LOG2 - 1);
-    const size_t pmax = c->max_length / minB + MH_EXTRA;
+    const size_t pmax = nyq_capacity(c);
     if (cudaMalloc(&c->d_H, std::max<size_t>(hbytes, 16)) != cudaSuccess ||
         cudaMalloc(&c->d_X, std::max<size_t>(xbytes, 16)) != cudaSuccess ||
         cudaMalloc(&c->d_Hnyq, std::max<size_t>(c->pairs() * pmax * c->esize(), 16)) != cudaSuccess ||
@@ -750,6 +756,14 @@ int apply_fft_size(hb_conv *c, uintptr_t fft_size)
     if (fft_size != (uintptr_t(1) << l2)) error = ERR_FFT_SIZE_NON_POWER_OF_TWO;
     if (l2 != c->fft_log2)
     {
+        // every loaded IR is dropped (PartitionedConvolve.cpp:145-149).  The spectra are tiled per FFT size and the
+        // multiply-accumulate kernels have no per-pair mask, so what is left in the arrays from the old size must read as
+        // silence for the pairs that are not set again (or set shorter than the longest pair)
+        if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));
+        HB_CUDA(cudaMemsetAsync(c->d_H, 0, std::max<size_t>(h_vectors(c) * 16, 16), c->stream));
+        HB_CUDA(cudaMemsetAsync(c->d_Hnyq, 0, std::max<size_t>(c->pairs() * nyq_capacity(c) * c->esize(), 16), c->stream));
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        c->tail_valid = false;
         std::fill(c->nparts.begin(), c->nparts.end(), 0u);
         c->P = 0;
         c->fft_log2 = l2;
@@ -1137,13 +1151,23 @@ int core_dispatch(hb_conv *c, const void *d_in, size_t in_ld, void *d_out, size_
                               : process_core<float>(c, (const float *) d_in, in_ld, (float *) d_out, out_ld, n, accumulate, st);
 }
 
+// how long k_gather waits for a peer's blocks before it raises the late flag (HB_PEER_TIMEOUT_MS, default 30 s: a peer may
+// still be loading impulse responses)
+unsigned long long peer_timeout_ns()
+{
+    static const char *env = getenv("HB_PEER_TIMEOUT_MS");
+    const double ms = env && atof(env) > 0 ? atof(env) : 30000.0;
+    return (unsigned long long) (ms * 1e6);
+}
+
 // Hop-aligned call of a rank of the fused multi-GPU exchange: as the aligned path of process_core, but the
 // inverse kernel delivers every partial block into its owner's inbox and k_gather sums what arrived here.
 // d_out holds this rank's outs/world output rows.
 template <class T>
 int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
 {
-    if (!c->P) return HB_ERR_NO_IR;
+    // a rank without an impulse response still takes part (k_shard_silence): its peers wait for its blocks
+    const bool silent = c->P == 0;
     if (!n) return HB_OK;
     int rc;
     if ((rc = ensure_ready<T>(c, n, st))) return rc;
@@ -1172,13 +1196,19 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
         peer.slot = c->inbox_slot;
         const uint32_t expected = (++c->parity_uses[peer.parity]) * o_loc;
         InvIO<T> io = {nullptr, 0, 0, 0, nullptr, 0, nullptr, 0, 0};
-        if ((rc = launch_hop<T>(c, st, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
-                                last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, io, peer))) return rc;
+        if (silent)
+        {
+            k_shard_silence<T><<<c->outs, 256, 0, st>>>(peer, (uint32_t) B);
+            HB_LAUNCH_CHECK();
+        }
+        else if ((rc = launch_hop<T>(c, st, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                     last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, io, peer))) return rc;
         k_gather<T><<<o_loc, 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
                                           peer.parity, peer.slot, expected, (uint32_t) B,
                                           last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
                                           first ? y_keep : nullptr, c->yout_ld, first ? d_out : nullptr, out_ld, accumulate,
-                                          (unsigned long long *) c->d_trace.p, c->g.hop);
+                                          (unsigned long long *) c->d_trace.p, c->g.hop, peer_timeout_ns(),
+                                          (uint32_t *) ((char *) c->d_inbox + c->inbox_data_bytes + INBOX_LATE_OFF));
         HB_LAUNCH_CHECK();
     }
     c->cur = nxt;
@@ -1291,7 +1321,8 @@ extern "C" void hb_conv_destroy(hb_conv *c)
 
 extern "C" int hb_conv_set_fft_size(hb_conv *c, uintptr_t fft_size)
 {
-    if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    int rc = check_handle(c);
+    if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
     return apply_fft_size(c, fft_size);
 }
@@ -1366,8 +1397,12 @@ extern "C" int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint3
     std::lock_guard<std::mutex> g(c->lock);
     uintptr_t len = (!d_ir || length <= c->offset) ? 0 : length - c->offset;
     const char *p = (const char *) d_ir + (len ? c->offset * c->esize() : 0);
-    return c->dtype == HB_F64 ? set_ir_core<double>(c, group, in, out, (const double *) p, len, c->stream)
-                              : set_ir_core<float>(c, group, in, out, (const float *) p, len, c->stream);
+    rc = c->dtype == HB_F64 ? set_ir_core<double>(c, group, in, out, (const double *) p, len, c->stream)
+                            : set_ir_core<float>(c, group, in, out, (const float *) p, len, c->stream);
+    if (rc < 0) return rc;
+    // as hb_conv_set_ir: d_ir may be reused and any stream may process once this returns
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
 }
 
 extern "C" int hb_conv_resize(hb_conv *c, uintptr_t max_length)
@@ -1634,6 +1669,17 @@ extern "C" int hb_conv_shard_attach(hb_conv *c, const void *handles)
     return HB_OK;
 }
 
+extern "C" int hb_conv_shard_status(hb_conv *c, uint32_t *late_ranks)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    if (!c->d_inbox || !late_ranks) { set_error("hb_conv_shard_status: not a sharded engine"); return HB_ERR_BAD_ARG; }
+    HB_CUDA(cudaDeviceSynchronize());
+    HB_CUDA(cudaMemcpy(late_ranks, (const char *) c->d_inbox + c->inbox_data_bytes + INBOX_LATE_OFF, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
 extern "C" int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out_shard, uintptr_t out_ld,
                                          uintptr_t num_samples, int accumulate, void *stream)
 {
@@ -1647,6 +1693,17 @@ extern "C" int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t
     c->blk_valid = false;
     return c->dtype == HB_F64 ? process_shard<double>(c, (const double *) d_in, in_ld, (double *) d_out_shard, out_ld, num_samples, accumulate, st)
                               : process_shard<float>(c, (const float *) d_in, in_ld, (float *) d_out_shard, out_ld, num_samples, accumulate, st);
+}
+
+extern "C" int hb_conv_join(hb_conv *c, void *stream)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+    // the only work an engine keeps in flight outside the caller's stream: the tail launched ahead for the next hop
+    if (c->split && c->tail_valid) HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
+    return HB_OK;
 }
 
 extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)

@@ -970,17 +970,45 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
 
 // ---------------------------------------------------------------------------------------------
 // k_gather: the owner's half of the fused exchange.  One CTA per owned output: wait until every source
-// rank has delivered this hop's blocks (arrival counter >= expected; bounded wait, a lost peer traps
-// instead of hanging the device), hand the previously finished block to the caller (carry), then sum the
+// rank has delivered this hop's blocks (arrival counter >= expected; bounded wait, a lost peer raises a flag
+// instead of hanging or trapping the device), hand the previously finished block to the caller (carry), then sum the
 // sources in rank order into `yout` (the caller's rows or the staging rows kept for the next call).
 // ---------------------------------------------------------------------------------------------
+// A rank with no impulse response loaded still takes part in every hop of the fused exchange: it delivers silence to every
+// owner and bumps the arrival counters, so that the peers' k_gather never waits for it and the hop sequence stays in step
+// (the NCCL exchange contributes silence in the same state).  One CTA per output channel.
+template <class T>
+__global__ void __launch_bounds__(256) k_shard_silence(const PeerOut peer, uint32_t B)
+{
+    const uint32_t ch = blockIdx.x;
+    const uint32_t owner = ch / peer.outs_local, o_loc = ch - owner * peer.outs_local;
+    T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(peer.parity) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
+    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) pd[k] = T(0);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        atomicAdd_system(peer.count[owner] + peer.parity * peer.world + peer.rank, 1u);
+    }
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// `timeout_ns`: how long the owner waits for a peer's blocks; a peer that is later than that (stopped, crashed) raises
+// *late (read by hb_conv_shard_status) and the hop is summed from what has arrived -- the device is never trapped.
 template <class T>
 __global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, const uint32_t *count, uint32_t world, uint32_t outs_local,
                                                 uint32_t parity, uint64_t slot, uint32_t expected, uint32_t B,
                                                 T *__restrict__ yout, size_t ld, size_t off, int add_result,
                                                 const T *__restrict__ carry_src, size_t carry_src_ld,
                                                 T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
-                                                unsigned long long *trace, uint32_t hop)
+                                                unsigned long long *trace, uint32_t hop, unsigned long long timeout_ns, uint32_t *late)
 {
     const uint32_t o = blockIdx.x;
     trace_mark(trace, hop, 4, 0);
@@ -993,9 +1021,9 @@ __global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, con
     if (threadIdx.x < world)
     {
         const volatile uint32_t *cnt = count + parity * world + threadIdx.x;
-        const long long t0 = clock64();
-        while (int32_t(*cnt - expected) < 0)
-            if (clock64() - t0 > (4ll << 30)) __trap();            // ~2 s at 2 GHz
+        const unsigned long long t0 = global_ns();
+        for (uint32_t spins = 0; int32_t(*cnt - expected) < 0; spins++)
+            if ((spins & 1023u) == 1023u && global_ns() - t0 > timeout_ns) { atomicOr(late, 1u << threadIdx.x); break; }
         __threadfence_system();
     }
     __syncthreads();

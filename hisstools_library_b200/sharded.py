@@ -159,6 +159,11 @@ class ShardedConvolver:
         """One block: local partial outputs for every output channel, then the sum over ranks.
         Returns True when y_shard was written (some rank had an IR loaded)."""
         dist = self.dist
+        if not stream and hasattr(x_local, "is_cuda") and x_local.is_cuda:
+            # 0 would mean "the engine's own stream" to the C ABI; the collective and the copies below run on torch's
+            # current stream, so the engine's kernels must be enqueued there as well
+            import torch
+            stream = torch.cuda.current_stream(x_local.device).cuda_stream
         if self.exchange == "fused":
             return self.engine.process_shard_tensor(x_local, y_shard, n, stream)
         part = self._partial_like(y_shard, n)

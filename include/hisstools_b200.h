@@ -158,6 +158,17 @@ int hb_conv_shard_attach(hb_conv *c, const void *handles);
 int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out_shard, uintptr_t out_ld,
                               uintptr_t num_samples, int accumulate, void *stream);
 
+/* late_ranks: bit r set = the owner-side sum on this rank gave up waiting for rank r's blocks at least once (longer than
+ * HB_PEER_TIMEOUT_MS, default 30 s) and summed that hop without them.  Synchronises the device.  A rank that has no
+ * impulse response loaded still takes part in every hop (it delivers silence), so only a stopped peer raises this. */
+int hb_conv_shard_status(hb_conv *c, uint32_t *late_ranks);
+
+/* Make `stream` (NULL = the handle's own) wait for the work the engine keeps in flight on its internal streams -- the
+ * share of the NEXT hop that the overlapped schedule launches ahead (hb_conv_set_schedule).  Callers that time a run of
+ * process_dev calls with events on their stream call this before the closing event, so that the timed window holds as
+ * many tail launches as hops. */
+int hb_conv_join(hb_conv *c, void *stream);
+
 /* tuning / introspection used by bench.py and the tests */
 /* CTAs per SM for the multiply-accumulate kernel (0 = library default) */
 int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant);

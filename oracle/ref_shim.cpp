@@ -203,6 +203,36 @@ SHIM int ref_matrix_set(void *p, uint32_t in, uint32_t out, const float *ir, uin
     m->pairs[idx]->setResetOffset(0);
     return err;
 }
+// Load every pair of the matrix from a pool of `npool` impulse responses of `len` taps (pair (in, out) takes pool entry
+// (in + out) % npool), the rows dealt to `threads` host threads: set-up of the full-size timing runs, where 4096 pairs
+// set one after the other take longer than the timed steps.
+SHIM int ref_matrix_set_pool_mt(void *p, const float *const *pool_irs, uint32_t npool, uintptr_t len, int threads)
+{
+    auto *m = static_cast<RefMatrix *>(p);
+    if (threads < 1) threads = 1;
+    if (uint32_t(threads) > m->nOut) threads = int(m->nOut);
+    std::vector<int> errs(threads, 0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+    {
+        uint32_t r0 = uint32_t(uint64_t(m->nOut) * t / threads), r1 = uint32_t(uint64_t(m->nOut) * (t + 1) / threads);
+        pool.emplace_back([=, &errs]()
+        {
+            for (uint32_t o = r0; o < r1; o++)
+                for (uint32_t i = 0; i < (m->parallel ? 1u : m->nIn); i++)
+                {
+                    size_t idx = m->parallel ? o : size_t(o) * m->nIn + i;
+                    int e = m->pairs[idx]->set(pool_irs[(i + o) % npool], len, true);
+                    m->pairs[idx]->setResetOffset(0);
+                    if (e) errs[t] = e;
+                }
+        });
+    }
+    for (auto &th : pool) th.join();
+    for (int e : errs) if (e) return e;
+    return 0;
+}
+
 // ins: nIn planar pointers, outs: nOut planar pointers; rows [row0,row1) only (for threading)
 static void matrix_rows(RefMatrix *m, const float *const *ins, float *const *outs, size_t n, uint32_t row0, uint32_t row1, float *temp)
 {
@@ -227,6 +257,29 @@ SHIM void ref_matrix_process(void *p, const float *const *ins, float *const *out
 #if defined(__SSE__)
     _mm_setcsr(old);
 #endif
+}
+
+// The same call with the output rows dealt to `threads` host threads (rows are independent objects, inputs are read-only):
+// used by the full-size parity checks, where one thread would take minutes.  Results do not depend on the thread count.
+SHIM void ref_matrix_process_mt(void *p, const float *const *ins, float *const *outs, size_t n, int threads)
+{
+    auto *m = static_cast<RefMatrix *>(p);
+    if (threads < 1) threads = 1;
+    if (uint32_t(threads) > m->nOut) threads = int(m->nOut);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+    {
+        uint32_t r0 = uint32_t(uint64_t(m->nOut) * t / threads), r1 = uint32_t(uint64_t(m->nOut) * (t + 1) / threads);
+        pool.emplace_back([=]()
+        {
+#if defined(__SSE__)
+            _mm_setcsr(_mm_getcsr() | 0x8040);
+#endif
+            std::vector<float> temp(n);
+            matrix_rows(m, ins, outs, n, r0, r1, temp.data());
+        });
+    }
+    for (auto &th : pool) th.join();
 }
 
 // Time `hops` calls of `block` samples on all rows with `threads` host threads (one thread per

@@ -174,6 +174,8 @@ def ref():
         sig("ref_matrix_destroy", None, V)
         sig("ref_matrix_set", C.c_int, V, C.c_uint32, C.c_uint32, c_f32p, UP)
         sig("ref_matrix_process", None, V, PP32, PP32, SZ)
+        sig("ref_matrix_set_pool_mt", C.c_int, V, PP32, C.c_uint32, UP, C.c_int)
+        sig("ref_matrix_process_mt", None, V, PP32, PP32, SZ, C.c_int)
         sig("ref_matrix_time", C.c_double, V, PP32, PP32, SZ, C.c_int, C.c_int, C.c_int)
         sig("ref_hardware_threads", C.c_int)
         sig("ref_restated_time_f64", C.c_double, C.POINTER(V), C.c_int, PP64, PP64, SZ, C.c_int, C.c_int, C.c_int)
@@ -318,3 +320,49 @@ def synth_ir(length, pair=0):
     rng = np.random.default_rng(2000 + pair)
     k = np.arange(length, dtype=np.float64)
     return (rng.standard_normal(length) * np.exp(-6.9 * k / max(length, 1))).astype(np.float32)
+
+
+def ref_matrix_run(irs, xs, fft_size, block=None, threads=None):
+    """The reference's uniform-partition matrix (rows of MonoConvolve(maxLen, false, fft) summed as
+    NToMonoConvolve.cpp:35-43 does) on irs[rows][ins][taps] and xs[ins][n], streamed in `block`-sample calls
+    (default: one hop) with the rows dealt to host threads.  Returns y[rows][n] (float32)."""
+    lib = ref()
+    irs = np.ascontiguousarray(irs, np.float32)
+    xs = np.ascontiguousarray(xs, np.float32)
+    rows, ins, taps = irs.shape
+    n = xs.shape[1]
+    block = block or fft_size // 2
+    m = lib.ref_matrix_create(ins, rows, taps, fft_size, 0)
+    if not m:
+        raise MemoryError("reference matrix allocation failed")
+    try:
+        for o in range(rows):
+            for i in range(ins):
+                lib.ref_matrix_set(m, i, o, fptr(irs[o, i]), taps)
+        y = np.zeros((rows, n), np.float32)
+        use = threads or min(rows, os.cpu_count() or 1)
+        P32 = c_f32p
+        for pos in range(0, n, block):
+            nb = min(block, n - pos)
+            xp = (P32 * ins)(*[xs[i, pos:].ctypes.data_as(P32) for i in range(ins)])
+            yp = (P32 * rows)(*[y[o, pos:].ctypes.data_as(P32) for o in range(rows)])
+            lib.ref_matrix_process_mt(m, xp, yp, nb, use)
+    finally:
+        lib.ref_matrix_destroy(m)
+    return y
+
+
+def ref_restated_run_f64(ir, x, fft_size, block=None):
+    """The double-precision oracle of SURVEY 8c (PartitionedConvolve.cpp:173-426 restated over the reference's own
+    FFT_SETUP_D transforms, oracle/ref_shim.cpp PConvRestated<double>) on one channel."""
+    lib = ref()
+    ir = np.ascontiguousarray(ir, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    block = block or fft_size // 2
+    h = lib.ref_restated_create_f64(fft_size)
+    lib.ref_restated_set_f64(h, fptr(ir), len(ir))
+    y = np.zeros_like(x)
+    for pos in range(0, len(x), block):
+        lib.ref_restated_process_f64(h, fptr(x[pos:]), fptr(y[pos:]), min(block, len(x) - pos))
+    lib.ref_restated_destroy_f64(h)
+    return y

@@ -675,3 +675,102 @@ def test_mono_zero_latency_against_oracle(hb):
         n = min(96, len(x) - pos)
         mc.process(x[pos:pos + n], np.zeros(n, np.float32), got[pos:pos + n], n)
     assert ck.rel_rms(got, want) <= TOL32
+
+
+# ---- contracts ---------------------------------------------------------------------------------------
+
+def test_fft_size_change_drops_every_pair(hb):
+    """setFFTSize with a new size drops every loaded IR (PartitionedConvolve.cpp:145-149).  On a multi-pair engine the
+    spectra left over from the old size's tiling must read as silence for the pairs that are not set again, and for the
+    partitions beyond the length of a pair that is set shorter than the longest one."""
+    from hisstools_library_b200.convolve import _Engine
+    n_in, n_out, L = 2, 2, 4096
+    e = _Engine(np.float32, 1, n_in, n_out, 1024, L, 0, 0, 0)
+    e.set_reset_offset(0)
+    for o in range(n_out):
+        for i in range(n_in):
+            e.set_ir(0, i, o, ck.synth_ir(L, 40 + 2 * o + i), L)
+    xs = np.stack([ck.synth_audio(128 * 40, 40 + i) for i in range(n_in)])
+
+    def run():
+        ys = [np.zeros(xs.shape[1], np.float32) for _ in range(n_out)]
+        e.process([xs[i] for i in range(n_in)], ys, xs.shape[1])
+        return ys
+
+    run()
+    assert e.set_fft_size(256) == 0
+    long_ir, short_ir = ck.synth_ir(128 * 5, 50), ck.synth_ir(100, 51)
+    e.set_ir(0, 0, 0, long_ir, len(long_ir))                 # pair (in 0, out 0): 5 partitions
+    e.set_ir(0, 1, 1, short_ir, len(short_ir))               # pair (in 1, out 1): 1 partition; the other two pairs stay dropped
+    ys = run()
+    assert ck.rel_rms(ys[0], ck.direct_convolve_delayed(long_ir, xs[0], 128)) <= TOL32
+    assert ck.rel_rms(ys[1], ck.direct_convolve_delayed(short_ir, xs[1], 128)) <= TOL32
+    e.close()
+
+
+def test_process_skips_the_block_while_set_holds_the_object(hb):
+    """The audio thread never waits for set / resize: while another thread replaces an impulse response, process returns
+    HB_ERR_BUSY and leaves the outputs untouched -- the try-lock of MonoConvolve.cpp:181-183 / MemorySwap.h:182-185."""
+    import ctypes as C
+    import threading
+    from hisstools_library_b200 import _abi
+    lib = _abi.lib()
+    mc = hb.MonoConvolve(1 << 16, hb.kLatencyShort)
+    mc.setResetOffset(0)
+    ir = ck.synth_ir(1 << 21, 60)
+    assert mc.set(ir[:4096], 4096, False) == 0
+    h = mc.matrix._h
+    n = 64
+    x = ck.synth_audio(n, 60)
+    stop = threading.Event()
+    seen = {"busy": 0, "ok": 0, "bad": 0}
+
+    def audio_thread():
+        ip = (C.c_void_p * 1)(x.ctypes.data)
+        while not stop.is_set():
+            y = np.full(n, 9.0, np.float32)
+            op = (C.c_void_p * 1)(y.ctypes.data)
+            rc = lib.hb_matrix_process(h, ip, op, n, 0)
+            if rc == _abi.HB_ERR_BUSY:
+                seen["busy"] += 1
+                if not np.all(y == 9.0):
+                    seen["bad"] += 1
+            elif rc == _abi.HB_OK:
+                seen["ok"] += 1
+            else:
+                seen["bad"] += 1
+
+    t = threading.Thread(target=audio_thread)
+    t.start()
+    try:
+        for k in range(6):
+            # a 2M-tap IR with a resize request: allocation, upload and 100+ transforms under the object's lock
+            assert mc.set(ir, len(ir) - k, True) == 0
+    finally:
+        stop.set()
+        t.join()
+    assert seen["bad"] == 0 and seen["ok"] > 0
+    assert seen["busy"] > 0
+
+
+def test_reset_of_one_pair_restarts_the_whole_matrix_documented_difference(hb):
+    """Convolver::reset(in, out) restarts ONE MonoConvolve in the reference (Convolver.cpp:88-97).  Here the delay line of an
+    input is shared by all outputs, so the whole matrix restarts from silence: pinned, so that a change of
+    this behaviour is a decision and not an accident."""
+    n_in, n_out, B, L = 2, 2, 128, 1000
+    cv = hb.Convolver(n_in, n_out, False, 2 * B, maxLength=L)
+    cv.setResetOffset(0)
+    irs = [[ck.synth_ir(L, 70 + 2 * o + i) for i in range(n_in)] for o in range(n_out)]
+    for o in range(n_out):
+        for i in range(n_in):
+            assert cv.set(i, o, irs[o][i], L, False) == 0
+    xs = np.stack([ck.synth_audio(B * 24, 70 + i) for i in range(n_in)])
+    half = B * 12
+    y = np.zeros((n_out, B * 24), np.float32)
+    cv.process(xs[:, :half], y[:, :half], n_in, n_out, half)
+    assert cv.reset(1, 0) is not None
+    ya = np.zeros((n_out, half), np.float32)
+    cv.process(np.ascontiguousarray(xs[:, half:]), ya, n_in, n_out, half)
+    for o in range(n_out):
+        fresh = sum(ck.direct_convolve_delayed(irs[o][i], xs[i][half:], B) for i in range(n_in))
+        assert ck.rel_rms(ya[o], fresh) <= TOL32              # every pair restarted, also those of output 1
