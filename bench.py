@@ -308,9 +308,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # host-side barriers for the legs in which rank 0 alone drives every GPU (an NCCL barrier would park a spinning kernel on them)
+        cpu_group = dist.new_group(backend="gloo")
     if world != args.gpus and rank == 0:
         sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE\n" % (args.gpus, world))
 
@@ -345,6 +348,8 @@ def run_ours(args):
         eng.set_schedule(args.schedule == "overlapped")
     if args.fft_path:
         eng.set_fft_path(args.fft_path)
+    if args.tail_streams:
+        eng.set_tail_streams(args.tail_streams)
     gen = torch.Generator(device=dev)
     decay = torch.exp(-6.9 * torch.arange(taps, device=dev, dtype=torch.float64) / taps).to(tdt)
     for g in range(l_groups):
@@ -545,11 +550,32 @@ def run_ours(args):
             ("hb_conv_process_shard_dev: peer stores from the inverse-FFT epilogue" if sharded is not None and sharded.exchange == "fused"
              else "hb_matrix_process_dev + NCCL reduce_scatter")
     e2e_value = job_rows * n * e2e_blocks / e2e_s / 1e6
+    e2e_ms_per_block = e2e_s / e2e_blocks * 1e3
 
     # ---- parity against the compiled reference, outside every timed region ---------------------------
-    parity = None
+    parity, ref_pack = None, None
     if not args.no_parity:
-        parity = parity_leg(args, torch, dist, ck, eng, sharded, gen, decay, stream, dev, mode, world, rank, l_ins, l_groups, tdt, ndt, n_pool)
+        parity, ref_pack = parity_leg(args, torch, dist, ck, eng, sharded, gen, decay, stream, dev, mode, world, rank, l_ins, l_groups, tdt, ndt, n_pool)
+
+    # ---- N > 1: end to end through ONE object in ONE process -- the reference's Convolver::process(ins, outs, ...) with host
+    # pointers over all N GPUs (hb_matrix_create_multi); rank 0 drives every GPU, the other ranks wait on the host
+    per_rank_e2e = None
+    if world > 1 and mode in ("inputs", "groups") and not args.no_front:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        front = None
+        if rank == 0:
+            front = front_leg(args, torch, ck, world, local, e2e_blocks, max(3, args.warmup) * min(R, 8), n_pool, tdt, ndt, ref_pack)
+        dist.barrier(group=cpu_group)
+        torch.cuda.set_device(local)
+        if rank == 0 and front is not None:
+            per_rank_e2e = {"value": e2e_value, "ms_per_block": e2e_ms_per_block, "api": e2e_api}
+            e2e_value, e2e_ms_per_block, e2e_api = front["value"], front["ms_per_block"], front["api"]
+            h2d, d2h = front["h2d"] * R, front["d2h"] * R
+            if parity is not None and front.get("rel_rms") is not None:
+                parity["rel_rms_host_pointer_path"] = front["rel_rms"]
+                parity["host_pointer_path"] = front["api"]
+                parity["ok"] = bool(parity["ok"] and front["rel_rms"] <= TOL[dtype])
 
     # ---- roofline of the dominant kernel (multiply-accumulate), per rank ---------------------------
     peak, peak_src = measured_peak()
@@ -589,8 +615,10 @@ def run_ours(args):
                            "collective": ("peer stores fused into the inverse-FFT epilogue (NVLink), owner-side sum" if sharded is not None and sharded.exchange == "fused"
                                           else "nccl reduce_scatter of partial output blocks") if mode == "inputs" else "none"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "blocks": e2e_blocks,
-                        "ms_per_block": e2e_s / e2e_blocks * 1e3, "api": e2e_api},
+                        "ms_per_block": e2e_ms_per_block, "api": e2e_api},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        if per_rank_e2e is not None:
+            line["e2e"]["per_rank_processes"] = per_rank_e2e
         if parity is not None:
             line["parity"] = parity
         if cpu is not None:
@@ -616,7 +644,7 @@ def parity_leg(args, torch, dist, ck, eng, sharded, gen, decay, stream, dev, mod
     n = B
     rows_in = l_groups * l_ins
     if ck.ref() is None:
-        return {"rel_rms": None, "oracle": "unavailable: oracle/_ref/libhisstools_ref.so is missing"}
+        return {"rel_rms": None, "oracle": "unavailable: oracle/_ref/libhisstools_ref.so is missing"}, None
     # the rows of this rank's output that are checked: first and last it owns
     if mode == "inputs":
         own = outs // world
@@ -659,9 +687,10 @@ def parity_leg(args, torch, dist, ck, eng, sharded, gen, decay, stream, dev, mod
     if world > 1:
         dist.barrier()
     if rank != 0:
-        return None
+        return None, None
     # the reference's inputs on rank 0: every rank's pool regenerated from its seed, the checked rows' IRs from theirs
-    if mode == "inputs":
+    if mode in ("inputs", "groups"):
+        # the whole job's rows, rank after rank (rank 0's come first)
         pools = [input_pool(gen, r, rows_in, n, n_pool, tdt, dev) for r in range(world)]
         x_full = np.concatenate([np.concatenate([pools[r][k % n_pool].cpu().numpy() for k in range(hops)], axis=1) for r in range(world)], axis=0)
         del pools
@@ -686,6 +715,76 @@ def parity_leg(args, torch, dist, ck, eng, sharded, gen, decay, stream, dev, mod
     if got_host is not None:
         res["rel_rms_host_pointer_path"] = max(ck.rel_rms(got_host[q], want[q]) for q in range(len(check_local)))
         res["ok"] = bool(res["ok"] and res["rel_rms_host_pointer_path"] <= TOL[dtype])
+    # what the single-process multi-GPU leg needs to repeat the check: the whole job's input stream, the checked rows, the reference
+    x_job = x_full
+    return res, {"x": x_job, "rows": check_global, "want": want, "hops": hops}
+
+
+def front_leg(args, torch, ck, world, local, blocks, warm, n_pool, tdt, ndt, ref_pack):
+    """Rank 0 only: the whole workload behind ONE hb_matrix handle dealt to all `world` GPUs of this process, driven through
+    the host-pointer C-ABI call (what HISSTools::Convolver::process forwards to), one call per block: H2D, the kernels of every
+    device, the exchange, D2H inside the timed region.  Also streams the parity input through it when the reference rows exist."""
+    from hisstools_library_b200 import _abi
+    from hisstools_library_b200.convolve import _Matrix
+    ins, outs, groups, taps, B, dtype, _ = WORKLOADS[args.workload]
+    es = 8 if dtype == "f64" else 4
+    n = B
+    devices = list(range(world))
+    m = _Matrix(groups, ins, outs, taps, (False, 2 * B, 0, 0, 0), ndt, 0, devices)
+    m.setResetOffset(0)
+    engines = m.shard_engines()
+    by_inputs = groups == 1
+    l_ins, l_groups = (ins // world, 1) if by_inputs else (ins, groups // world)
+    for d in devices:
+        dd = torch.device("cuda", d)
+        with torch.cuda.device(dd):
+            gen = torch.Generator(device=dd)
+            decay = torch.exp(-6.9 * torch.arange(taps, device=dd, dtype=torch.float64) / taps).to(tdt)
+            for g in range(l_groups):
+                for o in range(outs):
+                    for i in range(l_ins):
+                        gi = d * l_ins + i if by_inputs else i
+                        gg = g if by_inputs else d * l_groups + g
+                        ir = device_ir(gen, ir_seed(ins, outs, gg, o, gi), taps, decay, tdt)
+                        engines[d].set_ir_device(g, i, o, ir.data_ptr(), taps)
+            torch.cuda.synchronize()
+    torch.cuda.set_device(local)
+    rows_in, rows_out = groups * ins, groups * outs
+    rng = np.random.default_rng(11)
+    xin = [rng.uniform(-1, 1, (rows_in, n)).astype(ndt) for _ in range(n_pool)]
+    yout = np.zeros((rows_out, n), ndt)
+    lib = _abi.lib()
+    VP = C.c_void_p
+    ips = [(VP * rows_in)(*[x[r].ctypes.data for r in range(rows_in)]) for x in xin]
+    ops = (VP * rows_out)(*[yout[r].ctypes.data for r in range(rows_out)])
+    h = m._h
+    for q in range(warm):
+        _abi.check(lib.hb_matrix_process(h, ips[q % n_pool], ops, n, 0))
+    for d in devices:
+        torch.cuda.synchronize(d)
+    t0 = time.perf_counter()
+    for q in range(blocks):
+        _abi.check(lib.hb_matrix_process(h, ips[q % n_pool], ops, n, 0))
+    for d in devices:
+        torch.cuda.synchronize(d)                                       # the last call's device work is inside the timed region
+    secs = time.perf_counter() - t0
+    res = {"value": rows_out * n * blocks / secs / 1e6, "ms_per_block": secs / blocks * 1e3, "h2d": rows_in * n * es, "d2h": rows_out * n * es,
+           "api": "hb_matrix_process (host pointers) on ONE multi-device matrix (hb_matrix_create_multi, %d GPUs, exchange: %s), one call per block "
+                  "from one process" % (world, m.exchange), "rel_rms": None}
+    if ref_pack is not None:
+        m.reset()
+        x = ref_pack["x"]
+        hops = ref_pack["hops"]
+        got = np.zeros((len(ref_pack["rows"]), hops * n), ndt)
+        xb = np.zeros((rows_in, n), ndt)
+        ip = (VP * rows_in)(*[xb[r].ctypes.data for r in range(rows_in)])
+        for k in range(hops):
+            xb[:] = x[:, k * n:(k + 1) * n]
+            _abi.check(lib.hb_matrix_process(h, ip, ops, n, 0))
+            for q, r in enumerate(ref_pack["rows"]):
+                got[q, k * n:(k + 1) * n] = yout[r]
+        res["rel_rms"] = max(ck.rel_rms(got[q], ref_pack["want"][q]) for q in range(len(ref_pack["rows"])))
+    m.close()
     return res
 
 
@@ -703,10 +802,12 @@ def main():
     ap.add_argument("--schedule", default=None, choices=["overlapped", "serial"], help="hop schedule (default: the library's automatic choice)")
     ap.add_argument("--fft-path", type=int, default=0, choices=[0, 1, 2, 3],
                     help="transforms: 0 automatic, 1 one CTA each, 2 cluster of 8 CTAs each, 3 four-step chains (hb_conv_set_fft_path)")
+    ap.add_argument("--tail-streams", type=int, default=0, choices=[0, 1, 2], help="overlapped schedule: streams the tail launches alternate between (0: library default)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"], help="multi-GPU sum of partial outputs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-multi-hop", action="store_true", help="skip the multi-hop reuse leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity leg")
+    ap.add_argument("--no-front", action="store_true", help="N > 1: skip the single-process multi-GPU end-to-end leg (report the per-rank one)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":

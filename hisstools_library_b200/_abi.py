@@ -50,6 +50,7 @@ SIGNATURES = {
     "hb_conv_shard_export": (C.c_int, [V, U32, U32, V]),
     "hb_conv_shard_attach": (C.c_int, [V, V]),
     "hb_conv_process_shard_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
+    "hb_conv_shard_attach_local": (C.c_int, [V, C.POINTER(V)]),
     "hb_conv_shard_status": (C.c_int, [V, C.POINTER(U32)]),
     "hb_conv_join": (C.c_int, [V, V]),
     "hb_conv_set_tuning": (C.c_int, [V, C.c_int, C.c_int]),
@@ -57,6 +58,11 @@ SIGNATURES = {
     "hb_conv_bytes_per_hop": (C.c_uint64, [V]),
     "hb_matrix_create": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, U32, U32, U32, U32, C.c_int]),
     "hb_matrix_create_latency": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, C.c_int]),
+    "hb_matrix_create_multi": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, U32, U32, U32, U32, C.POINTER(C.c_int), U32]),
+    "hb_matrix_create_latency_multi": (C.c_int, [C.POINTER(V), C.c_int, U32, U32, U32, UP, C.c_int, C.POINTER(C.c_int), U32]),
+    "hb_matrix_shards": (U32, [V]),
+    "hb_matrix_shard": (V, [V, U32]),
+    "hb_matrix_exchange": (C.c_int, [V]),
     "hb_matrix_destroy": (None, [V]),
     "hb_matrix_set_reset_offset": (C.c_int, [V, IP]),
     "hb_matrix_resize": (C.c_int, [V, U32, U32, U32, UP]),
@@ -90,6 +96,7 @@ SIGNATURES = {
     "hb_conv_set_trace": (C.c_int, [V, C.c_int]),
     "hb_conv_get_trace": (C.c_int, [V, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_conv_set_schedule": (C.c_int, [V, C.c_int]),
+    "hb_conv_set_tail_streams": (C.c_int, [V, C.c_int]),
     "hb_conv_schedule": (C.c_int, [V]),
     "hb_conv_bytes_per_launch": (C.c_uint64, [V]),
 }

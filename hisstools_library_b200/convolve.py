@@ -175,6 +175,10 @@ class _Engine:
         (the fused single-launch hop where it applies, else overlapped / serial by size)."""
         return _abi.check(_abi.lib().hb_conv_set_schedule(self._h, 2 if overlapped is None else (1 if overlapped else 0)))
 
+    def set_tail_streams(self, streams=1):
+        """overlapped schedule: 2 = tails of consecutive hops on alternating streams (hb_conv_set_tail_streams)"""
+        return _abi.check(_abi.lib().hb_conv_set_tail_streams(self._h, int(streams)))
+
     @property
     def schedule(self):
         return ("serial", "overlapped", "fused")[_abi.lib().hb_conv_schedule(self._h)]
@@ -305,20 +309,43 @@ class _Matrix:
     """groups x (ins x outs) convolution matrix with one partition scheme: one hb_matrix handle, the
     shared machinery behind MonoConvolve, NToMonoConvolve and Convolver (host logic in csrc/hb_matrix.cu)."""
 
-    def __init__(self, groups, ins, outs, maxLength, scheme, dtype, device):
+    def __init__(self, groups, ins, outs, maxLength, scheme, dtype, device, devices=None):
         zero, A, B, C_, D = scheme
         self.dtype = np.dtype(dtype)
         self.groups, self.ins, self.outs = groups, ins, outs
         self.sizes, _, _, _ = partition_scheme(zero, A, B, C_, D)       # raises RuntimeError like the reference
         self._h = C.c_void_p()
-        code = _abi.lib().hb_matrix_create(C.byref(self._h), _hb_dtype(dtype), groups, ins, outs, int(maxLength),
-                                           1 if zero else 0, int(A), int(B), int(C_), int(D), int(device))
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if self.devices is not None:
+            # one matrix dealt to several GPUs of this process (hb_matrix_create_multi)
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            code = _abi.lib().hb_matrix_create_multi(C.byref(self._h), _hb_dtype(dtype), groups, ins, outs, int(maxLength),
+                                                     1 if zero else 0, int(A), int(B), int(C_), int(D), arr, len(self.devices))
+        else:
+            code = _abi.lib().hb_matrix_create(C.byref(self._h), _hb_dtype(dtype), groups, ins, outs, int(maxLength),
+                                               1 if zero else 0, int(A), int(B), int(C_), int(D), int(device))
         _abi.check(code)
         lib = _abi.lib()
         self.head_taps = int(lib.hb_matrix_head_taps(self._h))
         self.engines = [_Engine(dtype, groups, ins, outs, 0, 0, 0, 0, device, borrowed=lib.hb_matrix_part(self._h, k))
                         for k in range(lib.hb_matrix_parts(self._h))]
         self.tail = self.engines[-1]
+
+    @property
+    def exchange(self):
+        """how the sum over inputs crosses devices: none, peer-reads (owner-side kernel) or fused (inverse-FFT epilogue)"""
+        return ("none", "peer-reads", "fused")[_abi.lib().hb_matrix_exchange(self._h)]
+
+    def shard_engines(self, part=-1):
+        """one borrowed _Engine per device: part `part` (default: the tail) of every shard of a multi-device matrix"""
+        lib = _abi.lib()
+        out = []
+        for d in range(lib.hb_matrix_shards(self._h)):
+            sh = C.c_void_p(lib.hb_matrix_shard(self._h, d))
+            k = lib.hb_matrix_parts(sh) - 1 if part < 0 else part
+            dev = self.devices[d] if self.devices is not None else 0
+            out.append(_Engine(self.dtype, 1, 1, 1, 0, 0, 0, 0, dev, borrowed=lib.hb_matrix_part(sh, k)))
+        return out
 
     def setResetOffset(self, offset=-1):
         _abi.check(_abi.lib().hb_matrix_set_reset_offset(self._h, int(offset)))
@@ -473,19 +500,21 @@ class Convolver:
     The reference constructs every pair with room for 16384 taps (Convolver.cpp:18,35); use
     set(..., resize=True) for longer IRs, or the maxLength keyword to pre-allocate."""
 
-    def __init__(self, *args, dtype=np.float32, device=0, maxLength=16384):
+    def __init__(self, *args, dtype=np.float32, device=0, maxLength=16384, devices=None):
+        """devices=[...]: the matrix is dealt to these GPUs of this process (input channels of an N x M matrix, banks of a
+        parallel convolver); everything else -- set, resize, process with all rows -- stays as on one device."""
         args = list(args)
         if len(args) >= 2 and isinstance(args[1], (int, np.integer)) and not isinstance(args[1], (LatencyMode, bool)):
             self.mN2M = True
             self.mNumIns = max(int(args[0]), 1)
             self.mNumOuts = int(args[1])
             scheme = args[2:]
-            self._m = _Matrix(1, self.mNumIns, self.mNumOuts, maxLength, _scheme(scheme), dtype, device)
+            self._m = _Matrix(1, self.mNumIns, self.mNumOuts, maxLength, _scheme(scheme), dtype, device, devices)
         else:
             self.mN2M = False
             self.mNumIns = self.mNumOuts = max(int(args[0]), 1)
             scheme = args[1:]
-            self._m = _Matrix(self.mNumIns, 1, 1, maxLength, _scheme(scheme), dtype, device)
+            self._m = _Matrix(self.mNumIns, 1, 1, maxLength, _scheme(scheme), dtype, device, devices)
         self.dtype = self._m.dtype
 
     def _pair(self, inChan, outChan):

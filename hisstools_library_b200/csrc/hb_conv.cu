@@ -13,6 +13,7 @@
 #include "hb_conv_big.cuh"
 #include "hb_conv_cluster.cuh"
 #include "hb_conv_fused.cuh"
+#include "hb_conv_mh.h"
 
 #include <algorithm>
 #include <map>
@@ -26,7 +27,7 @@ namespace
 constexpr uintptr_t MIN_FFT_LOG2 = 5;       // PartitionedConvolve.h:18
 constexpr uintptr_t MAX_FFT_LOG2 = 20;      // PartitionedConvolve.h:19
 constexpr size_t INBOX_LATE_OFF = 192;     // inbox tail: arrival counters [2][world] (<= 128 bytes), then the late-peer flag word
-constexpr uint32_t MH_MAX = 4;              // hops one multi-hop multiply-accumulate launch covers at most
+constexpr uint32_t MH_MAX = 8;              // hops one multi-hop multiply-accumulate launch covers at most
 constexpr uint32_t MH_EXTRA = MH_MAX - 1;   // extra delay-line slots that needs
 
 // reference error codes (ConvolveErrors.h:4-19)
@@ -106,7 +107,9 @@ struct hb_conv
     uint32_t fused_cs = 1;          // its cluster size
     Range r_full{}, r_head{}, r_tail{};
     DevBuf d_St[2];                 // tail partial segments, double-buffered over hops
-    cudaStream_t s_tail = nullptr;
+    cudaStream_t s_tail = nullptr, s_tail_b = nullptr;
+    int tail_streams = 1;           // hb_conv_set_tail_streams: 2 = the tails of consecutive hops alternate between two streams, so that the
+                                    // CTAs of the next tail take over the SMs one by one as the CTAs of the running one exit
     cudaEvent_t ev_fwd = nullptr, ev_tail[2] = {nullptr, nullptr};
     bool tail_valid = false;        // d_St[tail_par] holds the tail of the upcoming hop
     bool tail_missing = false;      // a multi-hop batch ran last: nothing was computed ahead for the upcoming hop
@@ -115,6 +118,8 @@ struct hb_conv
     DevBuf d_Smh;                   // partial segments of a multi-hop launch: [hop][cta + tile][row][TBV]
     int multi_hop = 1;              // hb_conv_set_multi_hop: batch the hops of one call over a single pass of the IR spectra
     bool mh_ok = false;             // eligible for the current geometry (plan_geometry)
+    int mh_max = 1;                 // hops one multi-hop launch covers at most for the current geometry
+    bool mh_packed = false;         // float engines: the packed-FFMA2 kernel (hb_conv_mh.cuh), up to 8 hops per pass
     int mh_stages = 3;
     int fft_path = 0;               // hb_conv_set_fft_path: 0 automatic, 1 one CTA per transform, 2 cluster of 8 CTAs, 3 four-step
     BigScratch big;                 // four-step scratch for FFT sizes above the single-CTA limit (hb_conv_big.cuh)
@@ -139,6 +144,7 @@ struct hb_conv
     size_t inbox_data_bytes = 0, inbox_slot = 0;
     void *peer_base[HB_MAX_WORLD] = {};
     bool peers_attached = false;
+    bool peers_local = false;       // peers of the same process (plain pointers, nothing to close)
     uint32_t hop_seq = 0, parity_uses[2] = {0, 0};
 
     // optional per-kernel timing (hb_conv_set_profiling): PROF_EV events per hop, five on the launching stream
@@ -282,11 +288,15 @@ void plan_geometry(hb_conv *c)
     // multi-hop reuse (k_cmac_tma_mh): HBM-bound engines with full-height tiles (the FDL tile is 1/OT of the IR unit, so the
     // extra hops add little traffic), TMA variant, single-CTA transforms
     {
-        const size_t stage_mh = size_t(g.Q + MH_MAX * g.TBV) * 16;
+        const size_t stage_mh = size_t(g.Q + 4 * g.TBV) * 16;              // scalar kernel (double): at most 4 hops per pass
         c->mh_stages = (int) std::min<size_t>(3, (200 * 1024) / stage_mh);
         c->mh_ok = c->multi_hop && c->variant == 1 && !c->fused && tail_bytes >= (uint64_t(4) << 20) && g.OT >= 8 &&
                    ((g.XA == 1 && g.OB == 8) || (g.XA == 2 && g.OB == 4)) && (int) log2m <= single_cta_max_log2m(c) &&
                    c->mh_stages >= 2;
+        static const char *env_scalar = getenv("HB_MH_SCALAR");              // experiments only: the scalar kernel on float engines
+        c->mh_packed = c->mh_ok && c->dtype == HB_F32 && mh2_supported(g, 2) && !(env_scalar && atoi(env_scalar));
+        // hops one pass carries at most: 8 (half units) where the prepared delay-line tiles stay small beside the IR unit
+        c->mh_max = !c->mh_ok ? 1 : (!c->mh_packed ? 4 : (mh2_supported(g, 8) ? 8 : (mh2_supported(g, 4) ? 4 : 2)));
     }
     c->r_full = make_range(0, g.P, sms * per_sm);
     c->r_head = make_range(0, g.P ? 1 : 0, sms);
@@ -326,6 +336,8 @@ void free_device(hb_conv *c)
     c->d_St[0].release(); c->d_St[1].release(); c->d_trace.release();
     c->big.release(); c->d_nyq.release(); c->d_Smh.release();
     if (c->s_tail) cudaStreamDestroy(c->s_tail);
+    if (c->s_tail_b) cudaStreamDestroy(c->s_tail_b);
+    c->s_tail_b = nullptr;
     if (c->ev_fwd) cudaEventDestroy(c->ev_fwd);
     for (int k = 0; k < 2; k++) if (c->ev_tail[k]) cudaEventDestroy(c->ev_tail[k]);
     c->s_tail = nullptr; c->ev_fwd = nullptr; c->ev_tail[0] = c->ev_tail[1] = nullptr;
@@ -334,9 +346,9 @@ void free_device(hb_conv *c)
     c->d_io_in.release(); c->d_io_out.release(); c->d_ir.release();
     c->h_in.release(); c->h_out.release(); c->h_ir.release();
     for (uint32_t r = 0; r < c->shard_world; r++)
-        if (c->peers_attached && r != c->shard_rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+        if (c->peers_attached && !c->peers_local && r != c->shard_rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     cudaFree(c->d_inbox);
-    c->d_inbox = nullptr; c->peers_attached = false; c->shard_world = 0;
+    c->d_inbox = nullptr; c->peers_attached = false; c->peers_local = false; c->shard_world = 0;
     for (int k = 0; k < 2; k++)
     {
         c->h_blk[k].release(); c->h_inq[k].release(); c->d_inq[k].release();
@@ -421,9 +433,12 @@ int launch_cmac_inst(hb_conv *c, const Range &r, void *S, int variant, cudaStrea
     const Geom &g = c->g;
     if (variant == 1)
     {
-        int rc = allow_smem(k_cmac_tma<T, XA, OB>, c->cmac_smem);
+        // two tail streams: more than half an SM's shared memory per CTA, so that a CTA of the next tail is placed when one of the
+        // running tail leaves and never beside it (two resident tails would leave no room for the FFT kernels of the critical path)
+        const size_t smem = (c->tail_streams == 2 && r.kind == 2 && c->split) ? std::max<size_t>(c->cmac_smem, 116 * 1024) : c->cmac_smem;
+        int rc = allow_smem(k_cmac_tma<T, XA, OB>, smem);
         if (rc) return rc;
-        k_cmac_tma<T, XA, OB><<<r.G, 256, c->cmac_smem, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, c->nstages);
+        k_cmac_tma<T, XA, OB><<<r.G, 256, smem, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, c->nstages);
     }
     else
     {
@@ -471,10 +486,14 @@ int launch_cmac_mh_inst(hb_conv *c, const Range &r, void *S, uint64_t set_stride
     return HB_OK;
 }
 
-// NH (2 or 4) hops over one pass of the IR spectra; S holds NH partial-segment sets set_stride vectors apart
+// rows of an IR unit one CTA of a multi-hop launch works on: all of them, or half (8 hops: hb_conv_mh.cuh)
+inline uint32_t mh_split(const hb_conv *c, int nh) { return c->mh_packed && nh == 8 ? 2u : 1u; }
+
+// NH (2, 4 or 8) hops over one pass of the IR spectra; S holds NH partial-segment sets set_stride vectors apart
 template <class T>
 int launch_cmac_mh(hb_conv *c, const Range &r, void *S, int nh, uint64_t set_stride, cudaStream_t st)
 {
+    if (c->mh_packed) return launch_cmac_mh2(c->g, r, c->d_H, c->d_X, S, nh, set_stride, st);
     const uint32_t key = (c->g.XA * 16 + c->g.OB) * 8 + (uint32_t) nh;
     switch (key)
     {
@@ -760,6 +779,7 @@ int apply_fft_size(hb_conv *c, uintptr_t fft_size)
         // multiply-accumulate kernels have no per-pair mask, so what is left in the arrays from the old size must read as
         // silence for the pairs that are not set again (or set shorter than the longest pair)
         if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));
+        if (c->s_tail_b) HB_CUDA(cudaStreamSynchronize(c->s_tail_b));
         HB_CUDA(cudaMemsetAsync(c->d_H, 0, std::max<size_t>(h_vectors(c) * 16, 16), c->stream));
         HB_CUDA(cudaMemsetAsync(c->d_Hnyq, 0, std::max<size_t>(c->pairs() * nyq_capacity(c) * c->esize(), 16), c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
@@ -828,6 +848,7 @@ int do_reset(hb_conv *c, cudaStream_t st)
 {
     // a tail launched ahead for a hop that will not come any more may still be running on its stream
     if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));
+    if (c->s_tail_b) HB_CUDA(cudaStreamSynchronize(c->s_tail_b));
     c->tail_valid = false;
     c->tail_missing = false;
     plan_geometry(c);
@@ -839,6 +860,7 @@ int do_reset(hb_conv *c, cudaStream_t st)
         for (int k = 0; k < 2; k++)
             if ((rc = c->d_St[k].ensure(std::max<size_t>((size_t(c->r_tail.G) + g.tiles) * g.Q * 16, 16)))) return rc;
         if (!c->s_tail) HB_CUDA(cudaStreamCreateWithFlags(&c->s_tail, cudaStreamNonBlocking));
+        if (!c->s_tail_b) HB_CUDA(cudaStreamCreateWithFlags(&c->s_tail_b, cudaStreamNonBlocking));
         if (!c->ev_fwd) HB_CUDA(cudaEventCreateWithFlags(&c->ev_fwd, cudaEventDisableTiming));
         for (int k = 0; k < 2; k++)
             if (!c->ev_tail[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[k], cudaEventDisableTiming));
@@ -931,11 +953,14 @@ int launch_tail_ahead(hb_conv *c, cudaStream_t st, cudaEvent_t *pe)
     Range rt = c->r_tail;
     rt.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
     rt.kind = 2;
-    HB_CUDA(cudaStreamWaitEvent(c->s_tail, c->ev_fwd, 0));
-    if (pe) { HB_CUDA(cudaEventRecord(pe[5], c->s_tail)); c->ev_has_tail[c->ev_used - 1] = 1; }
-    if ((r = launch_cmac<T>(c, rt, c->d_St[np].p, c->variant, c->s_tail))) return r;
-    if (pe) HB_CUDA(cudaEventRecord(pe[6], c->s_tail));
-    HB_CUDA(cudaEventRecord(c->ev_tail[np], c->s_tail));
+    // (two tail streams: this launch waits for the forward FFTs only, not for the tail that is still running on the other
+    // stream; its segment set np was last read by the inverse FFTs two hops back, which precede ev_fwd on st)
+    cudaStream_t ts = (c->tail_streams == 2 && np) ? c->s_tail_b : c->s_tail;
+    HB_CUDA(cudaStreamWaitEvent(ts, c->ev_fwd, 0));
+    if (pe) { HB_CUDA(cudaEventRecord(pe[5], ts)); c->ev_has_tail[c->ev_used - 1] = 1; }
+    if ((r = launch_cmac<T>(c, rt, c->d_St[np].p, c->variant, ts))) return r;
+    if (pe) HB_CUDA(cudaEventRecord(pe[6], ts));
+    HB_CUDA(cudaEventRecord(c->ev_tail[np], ts));
     c->tail_par = np;
     c->tail_valid = true;
     return HB_OK;
@@ -1062,7 +1087,8 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
         while (h < nh)
         {
             const size_t left = nh - h;
-            const int nb = (c->mh_ok && left >= 4) ? 4 : ((c->mh_ok && left >= 2) ? 2 : 1);
+            int nb = 1;
+            while (nb * 2 <= c->mh_max && size_t(nb) * 2 <= left) nb *= 2;
             if (nb == 1)
             {
                 const bool first = h == 0, last = h + 1 == nh;
@@ -1086,8 +1112,9 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
                                     last_in_batch ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st, (uint32_t) nb))) return rc;
             Range rf = c->r_full;
             rf.slot = slot0; rf.kind = 2;
-            const uint64_t set_stride = uint64_t(rf.G + c->g.tiles) * c->g.Q;
-            if ((rc = c->d_Smh.ensure(size_t(MH_MAX) * set_stride * 16))) return rc;
+            const uint32_t split = mh_split(c, nb);
+            const uint64_t set_stride = uint64_t(rf.G + c->g.tiles * split) * (c->g.Q / split);
+            if ((rc = c->d_Smh.ensure(size_t(MH_MAX) * uint64_t(rf.G + c->g.tiles) * c->g.Q * 16))) return rc;
             if ((rc = launch_cmac_mh<T>(c, rf, c->d_Smh.p, nb, set_stride, st))) return rc;
             // inverse transforms of the nb hops in one launch: hop j sums set j, runs its Nyquist products from slot0 - j and
             // leaves its block B samples further on; the last hop of the call stays behind in the staging row
@@ -1095,7 +1122,7 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
                 SegSets sets;
                 memset(&sets, 0, sizeof(sets));
                 sets.n = 1;
-                sets.s[0].S = c->d_Smh.p; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
+                sets.s[0].S = c->d_Smh.p; sets.s[0].U = rf.U * split; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G; sets.s[0].split = split;
                 InvIO<T> io;
                 io.yout = d_out; io.ld = out_ld; io.off = (h + 1) * B; io.add_result = accumulate;
                 io.carry_src = first ? y_keep : nullptr; io.carry_src_ld = c->yout_ld;
@@ -1160,9 +1187,10 @@ unsigned long long peer_timeout_ns()
     return (unsigned long long) (ms * 1e6);
 }
 
-// Hop-aligned call of a rank of the fused multi-GPU exchange: as the aligned path of process_core, but the
-// inverse kernel delivers every partial block into its owner's inbox and k_gather sums what arrived here.
-// d_out holds this rank's outs/world output rows.
+// A call of a rank of the fused multi-GPU exchange: as process_core, but the inverse kernel of every hop delivers each
+// partial block into its owner's inbox and k_gather sums what arrived here.  d_out holds this rank's outs/world output
+// rows (nullptr: the caller fetches the finished block itself -- deferred host path, at most one hop).  Any numSamples:
+// hop-aligned calls run straight from / into the caller's rows, the others through the staging rows.
 template <class T>
 int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
 {
@@ -1172,19 +1200,16 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
     int rc;
     if ((rc = ensure_ready<T>(c, n, st))) return rc;
     const size_t B = c->g.B;
-    if (c->rw != 0 || n % B != 0 || c->xin_ld < B || c->yout_ld < B)
-    {
-        set_error("the fused multi-GPU exchange takes hop-aligned calls only (reset offset 0, numSamples a multiple of %zu)", B);
-        return HB_ERR_UNSUPPORTED;
-    }
-    const size_t nh = n / B;
     const uint32_t world = c->shard_world, o_loc = c->outs / world;
-    const int cur = c->cur, nxt = cur ^ 1;
-    const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
-    const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
-    for (size_t h = 0; h < nh; h++)
+    const size_t rows_in = c->ins, rows_out = o_loc;
+    const size_t rw = c->rw;
+    const size_t nh = (rw + n) / B;
+
+    // one hop: this rank's partial blocks to their owners, then the owner-side sum of the blocks that arrived here into
+    // row set `yout` at offset `off`; carry_dst (optional) first receives the block at carry_src (the output-ring read)
+    auto shard_hop = [&](const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld,
+                         T *yout, size_t ld, size_t off, int add_result, const T *carry_src, T *carry_dst, size_t carry_dst_ld) -> int
     {
-        const bool first = h == 0, last = h + 1 == nh;
         PeerOut peer;
         for (uint32_t r = 0; r < world; r++)
         {
@@ -1196,24 +1221,78 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
         peer.slot = c->inbox_slot;
         const uint32_t expected = (++c->parity_uses[peer.parity]) * o_loc;
         InvIO<T> io = {nullptr, 0, 0, 0, nullptr, 0, nullptr, 0, 0};
+        int r;
         if (silent)
         {
             k_shard_silence<T><<<c->outs, 256, 0, st>>>(peer, (uint32_t) B);
             HB_LAUNCH_CHECK();
         }
-        else if ((rc = launch_hop<T>(c, st, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
-                                     last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, io, peer))) return rc;
+        else if ((r = launch_hop<T>(c, st, prev, prev_ld, newest, new_ld, save, save_ld, io, peer))) return r;
         k_gather<T><<<o_loc, 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
-                                          peer.parity, peer.slot, expected, (uint32_t) B,
-                                          last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
-                                          first ? y_keep : nullptr, c->yout_ld, first ? d_out : nullptr, out_ld, accumulate,
+                                          peer.parity, peer.slot, expected, (uint32_t) B, yout, ld, off, add_result,
+                                          carry_src, c->yout_ld, carry_dst, carry_dst_ld, accumulate,
                                           (unsigned long long *) c->d_trace.p, c->g.hop, peer_timeout_ns(),
                                           (uint32_t *) ((char *) c->d_inbox + c->inbox_data_bytes + INBOX_LATE_OFF));
         HB_LAUNCH_CHECK();
+        return HB_OK;
+    };
+
+    const char *ib = (const char *) d_in, *ie = (const char *) (d_in + (rows_in - 1) * in_ld + n);
+    const char *ob = (const char *) d_out, *oe = (const char *) (d_out + (rows_out - 1) * out_ld + n);
+    const bool disjoint = !d_out || ie <= ob || oe <= ib;
+    if (rw == 0 && nh * B == n && disjoint && (d_out || nh <= 1) && c->xin_ld >= B && c->yout_ld >= B)
+    {
+        const int cur = c->cur, nxt = cur ^ 1;
+        const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
+        const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
+        for (size_t h = 0; h < nh; h++)
+        {
+            const bool first = h == 0, last = h + 1 == nh;
+            if ((rc = shard_hop(first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld,
+                                last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
+                                first ? y_keep : nullptr, (first && d_out) ? d_out : nullptr, out_ld))) return rc;
+        }
+        c->cur = nxt;
+        c->x_tail = c->y_tail = 0;
+        return HB_OK;
     }
-    c->cur = nxt;
-    c->x_tail = c->y_tail = 0;
+
+    if ((rc = ensure_staging<T>(c, B + rw + n, (nh + 1) * B, true, st))) return rc;
+    if (c->x_tail || c->y_tail)
+    {
+        const int nxt = c->cur ^ 1;
+        if ((rc = launch_rows<T>((T *) c->d_xin[nxt].p, c->xin_ld, (const T *) c->d_xin[c->cur].p + c->x_tail, c->xin_ld, B + rw, rows_in, 0, st))) return rc;
+        if ((rc = launch_rows<T>((T *) c->d_yout[nxt].p, c->yout_ld, (const T *) c->d_yout[c->cur].p + c->y_tail, c->yout_ld, B, rows_out, 0, st))) return rc;
+        c->cur = nxt;
+        c->x_tail = c->y_tail = 0;
+    }
+    T *xin = (T *) c->d_xin[c->cur].p;
+    T *yout = (T *) c->d_yout[c->cur].p;
+    if ((rc = launch_rows<T>(xin + B + rw, c->xin_ld, d_in, in_ld, n, rows_in, 0, st))) return rc;
+    for (size_t h = 0; h < nh; h++)
+        if ((rc = shard_hop(xin + h * B, c->xin_ld, xin + (h + 1) * B, c->xin_ld, nullptr, 0, yout, c->yout_ld, (h + 1) * B, 0, nullptr, nullptr, 0))) return rc;
+    if (d_out && (rc = launch_rows<T>(d_out, out_ld, yout + rw, c->yout_ld, n, rows_out, accumulate, st))) return rc;
+    c->rw = (rw + n) - nh * B;
+    c->x_tail = nh * B;
+    c->y_tail = nh * B;
     return HB_OK;
+}
+
+int shard_dispatch(hb_conv *c, const void *d_in, size_t in_ld, void *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
+{
+    return c->dtype == HB_F64 ? process_shard<double>(c, (const double *) d_in, in_ld, (double *) d_out, out_ld, n, accumulate, st)
+                              : process_shard<float>(c, (const float *) d_in, in_ld, (float *) d_out, out_ld, n, accumulate, st);
+}
+
+// rows a host-pointer call brings and takes: a rank of the fused exchange returns only the outputs it owns
+inline size_t host_rows_in(const hb_conv *c) { return size_t(c->groups) * c->ins; }
+inline size_t host_rows_out(const hb_conv *c) { return c->peers_attached ? c->outs / c->shard_world : size_t(c->groups) * c->outs; }
+// the engine behind a host-pointer call: the local matrix, or this rank's share of the fused exchange
+inline int host_dispatch(hb_conv *c, const void *d_in, size_t in_ld, void *d_out, size_t out_ld, size_t n, int accumulate, cudaStream_t st)
+{
+    return c->peers_attached ? shard_dispatch(c, d_in, in_ld, d_out, out_ld, n, accumulate, st)
+                             : core_dispatch(c, d_in, in_ld, d_out, out_ld, n, accumulate, st);
 }
 
 // wait for the copy streams of the deferred host path (before anything else touches the staging rows)
@@ -1293,6 +1372,8 @@ extern "C" int hb_conv_create(hb_conv **out, int dtype, uint32_t groups, uint32_
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete c; return HB_ERR_CUDA; }
+    static const char *env_ts = getenv("HB_TAIL_STREAMS");           // experiments: default number of tail streams
+    if (env_ts && atoi(env_ts) == 2) c->tail_streams = 2;
     c->tw_log2 = (int) l2;
     rc = make_twiddles(dtype, c->tw_log2, &c->d_tw);
     if (rc == HB_OK) rc = alloc_capacity(c);
@@ -1395,6 +1476,9 @@ extern "C" int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint3
     if (rc) return rc;
     if (group >= c->groups || in >= c->ins || out >= c->outs) { set_error("hb_conv_set_ir_dev: bad argument"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    // d_ir may have been produced on any stream of the caller (the transforms run on the engine's own non-blocking
+    // stream, which is not ordered after any of them): wait for everything enqueued on the device so far
+    HB_CUDA(cudaDeviceSynchronize());
     uintptr_t len = (!d_ir || length <= c->offset) ? 0 : length - c->offset;
     const char *p = (const char *) d_ir + (len ? c->offset * c->esize() : 0);
     rc = c->dtype == HB_F64 ? set_ir_core<double>(c, group, in, out, (const double *) p, len, c->stream)
@@ -1412,6 +1496,7 @@ extern "C" int hb_conv_resize(hb_conv *c, uintptr_t max_length)
     std::lock_guard<std::mutex> g(c->lock);
     HB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));       // a tail launched ahead reads the spectra freed below
+    if (c->s_tail_b) HB_CUDA(cudaStreamSynchronize(c->s_tail_b));
     const uintptr_t maxB = (uintptr_t(1) << c->max_fft_log2) >> 1;
     uintptr_t ml = max_length ? max_length : maxB;
     if (ml % maxB) ml = (ml / maxB + 1) * maxB;
@@ -1480,7 +1565,7 @@ namespace
 {
 void scatter_rows(hb_conv *c, void *const *outs, const char *src, size_t src_ld, size_t src_off, size_t n, int accumulate)
 {
-    const size_t es = c->esize(), rows_out = size_t(c->groups) * c->outs;
+    const size_t es = c->esize(), rows_out = host_rows_out(c);
     for (size_t r = 0; r < rows_out; r++)
     {
         if (!outs[r]) continue;
@@ -1503,7 +1588,7 @@ void scatter_rows(hb_conv *c, void *const *outs, const char *src, size_t src_ld,
 
 void gather_rows(hb_conv *c, const void *const *ins, char *dst, size_t n)
 {
-    const size_t es = c->esize(), rows_in = size_t(c->groups) * c->ins;
+    const size_t es = c->esize(), rows_in = host_rows_in(c);
     for (size_t r = 0; r < rows_in; r++)
     {
         // a null input row is an inactive channel: silence (NToMonoConvolve.cpp:41 stops at activeInChans)
@@ -1519,7 +1604,7 @@ void gather_rows(hb_conv *c, const void *const *ins, char *dst, size_t n)
 int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size_t n, int accumulate)
 {
     const size_t es = c->esize(), B = c->g.B, rw = c->rw;
-    const size_t rows_in = size_t(c->groups) * c->ins, rows_out = size_t(c->groups) * c->outs;
+    const size_t rows_in = host_rows_in(c), rows_out = host_rows_out(c);
     int rc;
     for (int k = 0; k < 2; k++)
     {
@@ -1562,7 +1647,7 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
     c->inq_pending[q] = true;
     c->inq_cur = q ^ 1;
     HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_inq[q], 0));
-    if ((rc = core_dispatch(c, c->d_inq[q].p, n, nullptr, 0, n, 0, c->stream))) return rc;
+    if ((rc = host_dispatch(c, c->d_inq[q].p, n, nullptr, 0, n, 0, c->stream))) return rc;
     HB_CUDA(cudaEventRecord(c->ev_done[q], c->stream));
     c->done_pending[q] = true;
     c->blk_valid = true;                    // process_core ran no reset here: ensure_ready was called by the caller
@@ -1593,7 +1678,8 @@ extern "C" int hb_conv_process(hb_conv *c, const void *const *ins, void *const *
     if (rc) return rc;
     if ((!ins || !outs) && n) { set_error("hb_conv_process: null buffer"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
-    if (!c->P) return HB_ERR_NO_IR;
+    // (a rank of the fused multi-GPU exchange takes part in every hop, loaded or not: its peers wait for its blocks)
+    if (!c->P && !c->peers_attached) return HB_ERR_NO_IR;
     if (!n) return HB_OK;
     rc = c->dtype == HB_F64 ? ensure_ready<double>(c, n, c->stream) : ensure_ready<float>(c, n, c->stream);
     if (rc) return rc;
@@ -1601,14 +1687,14 @@ extern "C" int hb_conv_process(hb_conv *c, const void *const *ins, void *const *
 
     // a call that crosses a hop boundary needs that hop's result before it returns: synchronous round trip
     const size_t es = c->esize();
-    const size_t rows_in = size_t(c->groups) * c->ins, rows_out = size_t(c->groups) * c->outs;
+    const size_t rows_in = host_rows_in(c), rows_out = host_rows_out(c);
     if ((rc = c->h_in.ensure(rows_in * n * es)) || (rc = c->h_out.ensure(rows_out * n * es)) ||
         (rc = c->d_io_in.ensure(rows_in * n * es)) || (rc = c->d_io_out.ensure(rows_out * n * es))) return rc;
     HB_CUDA(cudaStreamSynchronize(c->stream));                 // deferred work may still be reading the staging buffers
     if ((rc = drain_deferred(c))) return rc;
     gather_rows(c, ins, (char *) c->h_in.p, n);
     HB_CUDA(cudaMemcpyAsync(c->d_io_in.p, c->h_in.p, rows_in * n * es, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = core_dispatch(c, c->d_io_in.p, n, c->d_io_out.p, n, n, 0, c->stream))) return rc;
+    if ((rc = host_dispatch(c, c->d_io_in.p, n, c->d_io_out.p, n, n, 0, c->stream))) return rc;
     HB_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_io_out.p, rows_out * n * es, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
     c->blk_valid = false;
@@ -1620,7 +1706,7 @@ extern "C" int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, v
 {
     int rc = check_handle(c);
     if (rc) return rc;
-    if (!handle_out || world < 1 || world > HB_MAX_WORLD || rank >= world || c->groups != 1 || c->outs % world)
+    if (world < 1 || world > HB_MAX_WORLD || rank >= world || c->groups != 1 || c->outs % world)
     {
         set_error("hb_conv_shard_export: needs 1 <= world <= %d, rank < world, one group and outs a multiple of world", HB_MAX_WORLD);
         return HB_ERR_BAD_ARG;
@@ -1633,9 +1719,12 @@ extern "C" int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, v
     HB_CUDA(cudaMalloc(&c->d_inbox, data + 256));
     HB_CUDA(cudaMemset(c->d_inbox, 0, data + 256));
     HB_CUDA(cudaDeviceSynchronize());
-    cudaIpcMemHandle_t h;
-    HB_CUDA(cudaIpcGetMemHandle(&h, c->d_inbox));
-    memcpy(handle_out, &h, sizeof(h));
+    if (handle_out)                 // NULL: the peers live in this process (hb_conv_shard_attach_local)
+    {
+        cudaIpcMemHandle_t h;
+        HB_CUDA(cudaIpcGetMemHandle(&h, c->d_inbox));
+        memcpy(handle_out, &h, sizeof(h));
+    }
     c->shard_world = world; c->shard_rank = rank;
     c->inbox_data_bytes = data; c->inbox_slot = slot;
     c->hop_seq = 0; c->parity_uses[0] = c->parity_uses[1] = 0;
@@ -1669,6 +1758,37 @@ extern "C" int hb_conv_shard_attach(hb_conv *c, const void *handles)
     return HB_OK;
 }
 
+extern "C" int hb_conv_shard_attach_local(hb_conv *c, hb_conv *const *peers)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c->lock);
+    if (!peers || !c->d_inbox || c->peers_attached) { set_error("hb_conv_shard_attach_local: export first, attach once"); return HB_ERR_BAD_ARG; }
+    for (uint32_t r = 0; r < c->shard_world; r++)
+    {
+        if (r == c->shard_rank) { c->peer_base[r] = c->d_inbox; continue; }
+        const hb_conv *p = peers[r];
+        if (!p || !p->d_inbox || p->shard_world != c->shard_world || p->shard_rank != r || p->inbox_data_bytes != c->inbox_data_bytes)
+        {
+            set_error("hb_conv_shard_attach_local: peer %u is not an exported engine of the same exchange", r);
+            return HB_ERR_BAD_ARG;
+        }
+        if (p->device != c->device)
+        {
+            int can = 0;
+            HB_CUDA(cudaDeviceCanAccessPeer(&can, c->device, p->device));
+            if (!can) { set_error("device %d cannot map the memory of device %d (peer access over NVLink / PCIe is required)", c->device, p->device); return HB_ERR_UNSUPPORTED; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d) -> %s", p->device, cudaGetErrorString(e)); cudaGetLastError(); return HB_ERR_CUDA; }
+        }
+        c->peer_base[r] = p->d_inbox;
+    }
+    c->peers_attached = true;
+    c->peers_local = true;
+    return HB_OK;
+}
+
 extern "C" int hb_conv_shard_status(hb_conv *c, uint32_t *late_ranks)
 {
     int rc = check_handle(c);
@@ -1691,8 +1811,7 @@ extern "C" int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t
     cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
     if (c->blk_valid && (rc = drain_deferred(c))) return rc;
     c->blk_valid = false;
-    return c->dtype == HB_F64 ? process_shard<double>(c, (const double *) d_in, in_ld, (double *) d_out_shard, out_ld, num_samples, accumulate, st)
-                              : process_shard<float>(c, (const float *) d_in, in_ld, (float *) d_out_shard, out_ld, num_samples, accumulate, st);
+    return shard_dispatch(c, d_in, in_ld, d_out_shard, out_ld, num_samples, accumulate, st);
 }
 
 extern "C" int hb_conv_join(hb_conv *c, void *stream)
@@ -1714,6 +1833,16 @@ extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)
     c->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : (variant == 1 ? 1 : 2);
     c->variant = variant;
     c->need_reset = true;           // partial-segment geometry depends on the grid
+    return HB_OK;
+}
+
+extern "C" int hb_conv_set_tail_streams(hb_conv *c, int streams)
+{
+    if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    if (streams != 1 && streams != 2) { set_error("tail streams must be 1 or 2"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    c->tail_streams = streams;
+    c->need_reset = true;
     return HB_OK;
 }
 

@@ -717,8 +717,10 @@ struct InvBatch
 struct SegSet
 {
     const void *S;         // [cta + tile][row][TBV] of that launch
-    uint64_t U;            // its unit count, units per tile and grid (Range)
+    uint64_t U;            // its work-item count, items per (virtual) tile and grid (Range)
     uint32_t upt, G;
+    uint32_t split;        // 0 / 1: one segment holds all OT rows of a tile; 2: a launch that worked on half units (hb_conv_mh.cuh):
+    uint32_t pad;          //        virtual tile = tile * 2 + (row >= OT / 2), segments of Q / 2 vectors
 };
 struct SegSets
 {
@@ -819,6 +821,9 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
             const V *__restrict__ S = reinterpret_cast<const V *>(sets.s[q].S) + seg_shift;
             const uint64_t sU = sets.s[q].U;
             const uint32_t sG = sets.s[q].G, supt = sets.s[q].upt;
+            const uint32_t split = sets.s[q].split > 1 ? sets.s[q].split : 1u;
+            const uint32_t rh = g.OT / split, Qs = g.Q / split;      // rows and vectors per segment
+            const uint32_t vhalf = row / rh, vrow = row - vhalf * rh;
             uint32_t seg_lo[GV], seg_hi[GV];
             uint64_t base[GV];
             uint32_t rounds = 0;
@@ -830,11 +835,11 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
                 if (v < B / CPV)
                 {
                     const uint32_t bt = v / g.TBV, xa = v - bt * g.TBV;
-                    const uint32_t tile = (grp * g.n_ot + ot) * g.n_bt + bt;
+                    const uint32_t tile = ((grp * g.n_ot + ot) * g.n_bt + bt) * split + vhalf;
                     const uint64_t ulo = uint64_t(tile) * supt, uhi = ulo + supt - 1;
                     seg_lo[e] = (uint32_t) unit_owner(ulo, sU, sG);
                     seg_hi[e] = (uint32_t) unit_owner(uhi, sU, sG);
-                    base[e] = uint64_t(tile) * g.Q + row * g.TBV + xa;
+                    base[e] = uint64_t(tile) * Qs + vrow * g.TBV + xa;
                     const uint32_t need = seg_hi[e] - seg_lo[e] + 1;
                     rounds = need > rounds ? need : rounds;
                 }
@@ -848,7 +853,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
                     for (int k = 0; k < 4; k++)
                     {
                         const uint32_t c = seg_lo[e] + r + k;
-                        if (c <= seg_hi[e]) part[e][k] = S[uint64_t(c) * g.Q + base[e]];
+                        if (c <= seg_hi[e]) part[e][k] = S[uint64_t(c) * Qs + base[e]];
                         else vzero(part[e][k]);
                     }
 #pragma unroll

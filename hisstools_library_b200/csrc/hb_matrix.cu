@@ -10,7 +10,13 @@
 #include "hb_common.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 using namespace hb;
@@ -156,8 +162,11 @@ __global__ void k_td_hist(const T *__restrict__ old_hist, const T *__restrict__ 
 
 } // namespace
 
+struct MultiFront;
+
 struct hb_matrix
 {
+    MultiFront *multi = nullptr;             // non-null: this handle is the front of a matrix dealt to several GPUs (below)
     int dtype = HB_F32, device = 0;
     uint32_t groups = 1, ins = 1, outs = 1;
     bool zero_latency = false;
@@ -192,9 +201,12 @@ int check(hb_matrix *m)
     return use_device(m->device);
 }
 
+void destroy_front(hb_matrix *m);
+
 void destroy(hb_matrix *m)
 {
     if (!m) return;
+    if (m->multi) { destroy_front(m); return; }
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (hb_conv *p : m->parts) hb_conv_destroy(p);
@@ -337,6 +349,383 @@ bool valid_sizes(const uint32_t in[4], std::vector<uint32_t> &sizes)
 }
 } // namespace
 
+// =====================================================================================================
+// One matrix on several GPUs of this process (hb_matrix_create_multi).
+//
+// The front handle owns one ordinary single-device hb_matrix per device ("shard") and a host worker thread per
+// device; every hb_matrix_* entry point on the front fans out to them.
+//   N x M matrix (groups == 1): the INPUT channels are dealt to the devices -- shard d holds inputs
+//     [d * ins / n, (d + 1) * ins / n) against all outputs (1 / n of the spectra and of the HBM traffic) and owns the
+//     sums of outputs [d * outs / n, ...).  The sum over inputs of NToMonoConvolve.cpp:39-42 then crosses devices:
+//       fused   (one uniform FFT size, no head): the engines of the shards form a fused exchange (hb_conv_shard_*):
+//               every inverse-FFT kernel stores its partial blocks straight into the owner's memory over NVLink and
+//               the host call is hb_conv_process on every engine, pipelined as on one device;
+//       generic (any partition scheme, any call size): every shard adds its parts into a local block of partial
+//               outputs, and each owner sums its rows out of all shards' blocks with one kernel that reads peer memory.
+//   parallel banks (groups > 1): the banks are dealt to the devices; nothing crosses.
+// =====================================================================================================
+namespace
+{
+// calls on a multi-device front visit several devices: the caller's current device is put back on return
+struct DeviceRestore
+{
+    int dev = -1;
+    DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+    ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
+// one worker thread per device: run(fn) calls fn(d) on every worker and returns the first failure
+class DevicePool
+{
+public:
+    void start(const std::vector<int> &devices)
+    {
+        n_ = (uint32_t) devices.size();
+        rc_.assign(n_, 0);
+        err_.assign(n_, std::string());
+        for (uint32_t d = 0; d < n_; d++)
+            threads_.emplace_back([this, d, dev = devices[d]]() { cudaSetDevice(dev); loop(d); });
+    }
+    void stop()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            quit_.store(true, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (std::thread &t : threads_) t.join();
+        threads_.clear();
+    }
+    int run(const std::function<int(uint32_t)> &fn)
+    {
+        job_ = &fn;
+        pending_.store(n_, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> l(m_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (uint32_t spins = 0; pending_.load(std::memory_order_acquire) != 0; spins++)
+            if (spins < 200000) cpu_relax(); else std::this_thread::yield();
+        for (uint32_t d = 0; d < n_; d++)
+            if (rc_[d] < 0 && rc_[d] != HB_ERR_NO_IR && rc_[d] != HB_ERR_BUSY) { set_error("device %u: %s", d, err_[d].c_str()); return rc_[d]; }
+        return HB_OK;
+    }
+    int code(uint32_t d) const { return rc_[d]; }
+
+private:
+    void loop(uint32_t d)
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            // a streaming caller comes back within microseconds: spin first, sleep only when it stays away
+            uint32_t spins = 0;
+            while (gen_.load(std::memory_order_acquire) == seen && !quit_.load(std::memory_order_acquire))
+            {
+                if (++spins < 100000) { cpu_relax(); continue; }
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait_for(l, std::chrono::milliseconds(50), [&]() { return gen_.load(std::memory_order_acquire) != seen || quit_.load(std::memory_order_acquire); });
+            }
+            if (quit_.load(std::memory_order_acquire)) return;
+            seen = gen_.load(std::memory_order_acquire);
+            const int r = (*job_)(d);
+            rc_[d] = r;
+            if (r < 0) err_[d] = hb_last_error();
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    uint32_t n_ = 0;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<uint32_t> pending_{0};
+    std::atomic<bool> quit_{false};
+    const std::function<int(uint32_t)> *job_ = nullptr;
+    std::vector<int> rc_;
+    std::vector<std::string> err_;
+};
+
+constexpr int MULTI_MAX = 16;
+struct PeerParts { const void *p[MULTI_MAX]; };
+
+// owner-side sum of the generic path: out[r][s] = sum over shards of part_e[row0 + r][s]; the blocks of the other shards are
+// read straight out of their memory (peer access over NVLink)
+template <class T>
+__global__ void k_peer_sum(PeerParts parts, uint32_t world, size_t ld, uint32_t row0, size_t n, T *__restrict__ out, size_t out_ld)
+{
+    const size_t r = blockIdx.y;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    {
+        T sum = T(0);
+        for (uint32_t e = 0; e < world; e++) sum += reinterpret_cast<const T *>(parts.p[e])[(row0 + r) * ld + i];
+        out[r * out_ld + i] = sum;
+    }
+}
+} // namespace
+
+struct MultiShard
+{
+    hb_matrix *m = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_part = nullptr;
+    DevBuf d_in, d_part, d_sum;
+    PinnedBuf h_in, h_out;
+    int loaded = 0;                          // result of the last local process: did this shard have anything loaded
+};
+
+struct MultiFront
+{
+    std::vector<MultiShard> sh;
+    bool by_inputs = true;                   // N x M matrix dealt by input channel; false: parallel banks dealt by bank
+    bool fused = false;                      // the shards' engines form a fused exchange
+    uint32_t l_ins = 0, l_outs = 0, l_groups = 0;
+    DevicePool pool;
+};
+
+namespace
+{
+void destroy_front(hb_matrix *m)
+{
+    DeviceRestore keep;
+    MultiFront *f = m->multi;
+    f->pool.stop();
+    // the engines write into each other's memory: every device must be idle before any shard goes
+    for (MultiShard &s : f->sh)
+        if (cudaSetDevice(s.device) == cudaSuccess) cudaDeviceSynchronize();
+    for (MultiShard &s : f->sh)
+    {
+        cudaSetDevice(s.device);
+        s.d_in.release(); s.d_part.release(); s.d_sum.release(); s.h_in.release(); s.h_out.release();
+        if (s.ev_part) cudaEventDestroy(s.ev_part);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        destroy(s.m);
+    }
+    delete f;
+    delete m;
+}
+
+// which shard holds pair (group, in, out) and under which local indices
+uint32_t front_locate(const hb_matrix *m, uint32_t &group, uint32_t &in)
+{
+    const MultiFront *f = m->multi;
+    if (f->by_inputs) { const uint32_t d = in / f->l_ins; in -= d * f->l_ins; return d; }
+    const uint32_t d = group / f->l_groups;
+    group -= d * f->l_groups;
+    return d;
+}
+
+int front_process(hb_matrix *m, const void *const *ins, void *const *outs, size_t n, int accumulate)
+{
+    MultiFront *f = m->multi;
+    const uint32_t nd = (uint32_t) f->sh.size();
+    const size_t es = m->esize();
+    if (f->fused)
+    {
+        // every engine takes its inputs and returns the outputs it owns: hb_conv_process pipelines the call as on one device
+        bool any = false;
+        for (MultiShard &s : f->sh) any = any || hb_conv_partitions(s.m->parts[0]) != 0;
+        if (!any) return HB_ERR_NO_IR;
+        return f->pool.run([&](uint32_t d) -> int
+        {
+            return hb_conv_process(f->sh[d].m->parts[0], ins + size_t(d) * f->l_ins, outs + size_t(d) * f->l_outs, n, accumulate);
+        });
+    }
+    // generic path, phase A: every shard adds its parts into a zeroed local block (all outputs of its banks)
+    const size_t rows_in = size_t(f->l_groups) * f->l_ins;                       // per shard
+    const size_t rows_part = size_t(f->l_groups) * m->outs;
+    int rc = f->pool.run([&](uint32_t d) -> int
+    {
+        MultiShard &s = f->sh[d];
+        int r;
+        if ((r = use_device(s.device))) return r;
+        if ((r = s.h_in.ensure(rows_in * n * es)) || (r = s.d_in.ensure(rows_in * n * es)) || (r = s.d_part.ensure(rows_part * n * es))) return r;
+        const void *const *my = ins + size_t(d) * rows_in;                      // inputs (or banks) are dealt in contiguous runs
+        for (size_t q = 0; q < rows_in; q++)
+        {
+            if (my[q]) memcpy((char *) s.h_in.p + q * n * es, my[q], n * es);
+            else memset((char *) s.h_in.p + q * n * es, 0, n * es);
+        }
+        HB_CUDA(cudaMemcpyAsync(s.d_in.p, s.h_in.p, rows_in * n * es, cudaMemcpyHostToDevice, s.stream));
+        HB_CUDA(cudaMemsetAsync(s.d_part.p, 0, rows_part * n * es, s.stream));
+        r = hb_matrix_process_dev(s.m, s.d_in.p, n, s.d_part.p, n, n, accumulate, s.stream);
+        s.loaded = r == HB_OK;
+        if (r != HB_OK && r != HB_ERR_NO_IR) return r;
+        HB_CUDA(cudaEventRecord(s.ev_part, s.stream));
+        return HB_OK;
+    });
+    if (rc) return rc;
+    bool any = false;
+    for (MultiShard &s : f->sh) any = any || s.loaded;
+    // phase B: every owner sums its rows out of all shards' blocks (or, for banks, just takes its own) and hands them over
+    const size_t rows_own = f->by_inputs ? f->l_outs : rows_part;
+    rc = f->pool.run([&](uint32_t d) -> int
+    {
+        MultiShard &s = f->sh[d];
+        int r;
+        if ((r = use_device(s.device))) return r;
+        const void *src = s.d_part.p;
+        if (f->by_inputs)
+        {
+            if ((r = s.d_sum.ensure(rows_own * n * es))) return r;
+            PeerParts parts;
+            for (uint32_t e = 0; e < nd; e++)
+            {
+                parts.p[e] = f->sh[e].d_part.p;
+                if (e != d) HB_CUDA(cudaStreamWaitEvent(s.stream, f->sh[e].ev_part, 0));
+            }
+            dim3 grid((unsigned) std::min<size_t>((n + 255) / 256, 64), (unsigned) rows_own);
+            if (m->dtype == HB_F64) k_peer_sum<double><<<grid, 256, 0, s.stream>>>(parts, nd, n, d * f->l_outs, n, (double *) s.d_sum.p, n);
+            else k_peer_sum<float><<<grid, 256, 0, s.stream>>>(parts, nd, n, d * f->l_outs, n, (float *) s.d_sum.p, n);
+            HB_LAUNCH_CHECK();
+            src = s.d_sum.p;
+        }
+        if (any)
+        {
+            if ((r = s.h_out.ensure(rows_own * n * es))) return r;
+            HB_CUDA(cudaMemcpyAsync(s.h_out.p, src, rows_own * n * es, cudaMemcpyDeviceToHost, s.stream));
+        }
+        HB_CUDA(cudaStreamSynchronize(s.stream));                               // also: the peers may overwrite their blocks again
+        if (!any) return HB_OK;
+        void *const *mine = outs + size_t(d) * rows_own;
+        for (size_t q = 0; q < rows_own; q++)
+        {
+            if (!mine[q]) continue;
+            const char *sp = (const char *) s.h_out.p + q * n * es;
+            if (!accumulate) memcpy(mine[q], sp, n * es);
+            else if (m->dtype == HB_F64) { double *dd = (double *) mine[q]; const double *ss = (const double *) sp; for (size_t k = 0; k < n; k++) dd[k] += ss[k]; }
+            else { float *dd = (float *) mine[q]; const float *ss = (const float *) sp; for (size_t k = 0; k < n; k++) dd[k] += ss[k]; }
+        }
+        return HB_OK;
+    });
+    if (rc) return rc;
+    return any ? HB_OK : HB_ERR_NO_IR;
+}
+
+int create_front(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                 const std::function<int(hb_matrix **, uint32_t, uint32_t, int)> &make_shard, const int *devices, uint32_t n_devices)
+{
+    if (!out || !devices || n_devices < 1 || n_devices > (uint32_t) MULTI_MAX) { set_error("hb_matrix_create_multi: 1 to %d devices", MULTI_MAX); return HB_ERR_BAD_ARG; }
+    *out = nullptr;
+    DeviceRestore keep;
+    for (uint32_t a = 0; a < n_devices; a++)
+        for (uint32_t b = a + 1; b < n_devices; b++)
+            if (devices[a] == devices[b]) { set_error("hb_matrix_create_multi: device %d listed twice", devices[a]); return HB_ERR_BAD_ARG; }
+    const bool by_inputs = groups == 1;
+    if (by_inputs ? (ins % n_devices || outs % n_devices) : (groups % n_devices) != 0)
+    {
+        set_error("hb_matrix_create_multi: %s must be a multiple of the device count %u", by_inputs ? "inputs and outputs" : "the bank count", n_devices);
+        return HB_ERR_BAD_ARG;
+    }
+    hb_matrix *m = new hb_matrix;
+    MultiFront *f = new MultiFront;
+    m->multi = f;
+    m->dtype = dtype; m->device = devices[0]; m->groups = groups; m->ins = ins; m->outs = outs;
+    f->by_inputs = by_inputs;
+    f->l_ins = by_inputs ? ins / n_devices : ins;
+    f->l_outs = by_inputs ? outs / n_devices : outs;
+    f->l_groups = by_inputs ? 1 : groups / n_devices;
+    f->sh.resize(n_devices);
+    int rc = HB_OK;
+    for (uint32_t d = 0; d < n_devices && rc >= 0; d++)
+    {
+        MultiShard &s = f->sh[d];
+        s.device = devices[d];
+        if ((rc = use_device(s.device))) break;
+        rc = make_shard(&s.m, f->l_groups, f->l_ins, s.device);
+        if (rc < 0) break;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s.ev_part, cudaEventDisableTiming) != cudaSuccess)
+        {
+            set_error("stream / event creation failed on device %d", s.device);
+            rc = HB_ERR_CUDA;
+        }
+    }
+    // every owner reads (generic) or writes (fused) the other shards' memory
+    for (uint32_t a = 0; a < n_devices && rc >= 0 && by_inputs; a++)
+        for (uint32_t b = 0; b < n_devices && rc >= 0; b++)
+        {
+            if (a == b) continue;
+            int can = 0;
+            cudaSetDevice(devices[a]);
+            if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) != cudaSuccess || !can)
+            {
+                set_error("device %d cannot map the memory of device %d (peer access over NVLink / PCIe is required)", devices[a], devices[b]);
+                rc = HB_ERR_UNSUPPORTED;
+                break;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d) -> %s", devices[b], cudaGetErrorString(e)); cudaGetLastError(); rc = HB_ERR_CUDA; }
+        }
+    // one uniform part and no head: the engines exchange inside their inverse-FFT kernels
+    if (rc >= 0 && by_inputs && n_devices > 1 && f->sh[0].m->parts.size() == 1 && !f->sh[0].m->head_taps)
+    {
+        static const char *env = getenv("HB_MULTI_GENERIC");                  // experiments only: force the generic path
+        if (!(env && atoi(env)))
+        {
+            std::vector<hb_conv *> engines;
+            for (MultiShard &s : f->sh) engines.push_back(s.m->parts[0]);
+            for (uint32_t d = 0; d < n_devices && rc >= 0; d++) rc = hb_conv_shard_export(engines[d], n_devices, d, nullptr);
+            for (uint32_t d = 0; d < n_devices && rc >= 0; d++) rc = hb_conv_shard_attach_local(engines[d], engines.data());
+            f->fused = rc >= 0;
+        }
+    }
+    if (rc < 0)
+    {
+        const std::string keep = hb_last_error();
+        f->sh.erase(std::remove_if(f->sh.begin(), f->sh.end(), [](const MultiShard &s) { return s.m == nullptr && s.stream == nullptr; }), f->sh.end());
+        destroy_front(m);
+        set_error("%s", keep.c_str());
+        return rc;
+    }
+    (void) max_length;
+    std::vector<int> devs(devices, devices + n_devices);
+    f->pool.start(devs);
+    *out = m;
+    return HB_OK;
+}
+} // namespace
+
+extern "C" int hb_matrix_create_multi(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                                      int zero_latency, uint32_t A, uint32_t B, uint32_t C, uint32_t D, const int *devices, uint32_t n_devices)
+{
+    if ((dtype != HB_F32 && dtype != HB_F64) || !groups || !ins || !outs) { set_error("hb_matrix_create_multi: bad argument"); return HB_ERR_BAD_ARG; }
+    return create_front(out, dtype, groups, ins, outs, max_length, [&](hb_matrix **shard, uint32_t l_groups, uint32_t l_ins, int device)
+    {
+        return hb_matrix_create(shard, dtype, l_groups, l_ins, outs, max_length, zero_latency, A, B, C, D, device);
+    }, devices, n_devices);
+}
+
+extern "C" int hb_matrix_create_latency_multi(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                                              int latency_mode, const int *devices, uint32_t n_devices)
+{
+    if ((dtype != HB_F32 && dtype != HB_F64) || !groups || !ins || !outs) { set_error("hb_matrix_create_latency_multi: bad argument"); return HB_ERR_BAD_ARG; }
+    return create_front(out, dtype, groups, ins, outs, max_length, [&](hb_matrix **shard, uint32_t l_groups, uint32_t l_ins, int device)
+    {
+        return hb_matrix_create_latency(shard, dtype, l_groups, l_ins, outs, max_length, latency_mode, device);
+    }, devices, n_devices);
+}
+
+extern "C" uint32_t hb_matrix_shards(const hb_matrix *m) { return !m ? 0 : (m->multi ? (uint32_t) m->multi->sh.size() : 1u); }
+extern "C" hb_matrix *hb_matrix_shard(hb_matrix *m, uint32_t index)
+{
+    if (!m) return nullptr;
+    if (!m->multi) return index == 0 ? m : nullptr;
+    return index < m->multi->sh.size() ? m->multi->sh[index].m : nullptr;
+}
+extern "C" int hb_matrix_exchange(const hb_matrix *m) { return !m || !m->multi ? 0 : (!m->multi->by_inputs ? 0 : (m->multi->fused ? 2 : 1)); }
+
 extern "C" int hb_matrix_create(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
                                 int zero_latency, uint32_t A, uint32_t B, uint32_t C, uint32_t D, int device)
 {
@@ -421,6 +810,12 @@ extern "C" int hb_matrix_set_reset_offset(hb_matrix *m, intptr_t offset)
 {
     if (!m) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(m->lock);
+    if (m->multi)
+    {
+        DeviceRestore keep;
+        for (MultiShard &s : m->multi->sh) hb_matrix_set_reset_offset(s.m, offset);
+        return HB_OK;
+    }
     apply_reset_offset(m, offset);
     return HB_OK;
 }
@@ -431,6 +826,14 @@ extern "C" int hb_matrix_resize(hb_matrix *m, uint32_t group, uint32_t in, uint3
     if (rc) return rc;
     if (group >= m->groups || in >= m->ins || out >= m->outs) { set_error("hb_matrix_resize: pair out of range"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(m->lock);                  // blocking, as MemorySwap::equal (MonoConvolve.cpp:100-110)
+    if (m->multi)
+    {
+        DeviceRestore keep;
+        const uint32_t d = front_locate(m, group, in);
+        rc = hb_matrix_resize(m->multi->sh[d].m, group, in, out, length);
+        for (MultiShard &s : m->multi->sh) hb_matrix_reset(s.m);          // a changed pair restarts the whole matrix
+        return rc;
+    }
     const size_t pair = m->pair_index(group, in, out);
     m->pair_len[pair] = 0;
     const int grown = grow_tail(m, length);
@@ -447,6 +850,14 @@ extern "C" int hb_matrix_set(hb_matrix *m, uint32_t group, uint32_t in, uint32_t
     if (rc) return rc;
     if (group >= m->groups || in >= m->ins || out >= m->outs || (ir_dtype != HB_F32 && ir_dtype != HB_F64)) { set_error("hb_matrix_set: bad argument"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(m->lock);                  // MonoConvolve::set (MonoConvolve.cpp:118-140)
+    if (m->multi)
+    {
+        DeviceRestore keep;
+        const uint32_t d = front_locate(m, group, in);
+        rc = hb_matrix_set(m->multi->sh[d].m, group, in, out, ir, ir_dtype, length, request_resize);
+        for (MultiShard &s : m->multi->sh) hb_matrix_reset(s.m);          // a changed pair restarts the whole matrix
+        return rc;
+    }
     if (!ir) length = 0;
     const size_t pair = m->pair_index(group, in, out);
     m->pair_len[pair] = 0;
@@ -473,14 +884,24 @@ extern "C" int hb_matrix_reset(hb_matrix *m)
 {
     if (!m) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(m->lock);
+    if (m->multi)
+    {
+        for (MultiShard &s : m->multi->sh) hb_matrix_reset(s.m);
+        return 0;
+    }
     for (hb_conv *p : m->parts) hb_conv_reset(p);
     m->head_reset = true;
     return 0;
 }
 
-extern "C" uint32_t hb_matrix_parts(const hb_matrix *m) { return m ? (uint32_t) m->parts.size() : 0; }
-extern "C" hb_conv *hb_matrix_part(hb_matrix *m, uint32_t index) { return (m && index < m->parts.size()) ? m->parts[index] : nullptr; }
-extern "C" uint32_t hb_matrix_head_taps(const hb_matrix *m) { return m ? m->head_taps : 0; }
+// (on a multi-device front: those of the first shard -- every shard has the same scheme)
+extern "C" uint32_t hb_matrix_parts(const hb_matrix *m) { return !m ? 0 : (m->multi ? hb_matrix_parts(m->multi->sh[0].m) : (uint32_t) m->parts.size()); }
+extern "C" hb_conv *hb_matrix_part(hb_matrix *m, uint32_t index)
+{
+    if (m && m->multi) return hb_matrix_part(m->multi->sh[0].m, index);
+    return (m && index < m->parts.size()) ? m->parts[index] : nullptr;
+}
+extern "C" uint32_t hb_matrix_head_taps(const hb_matrix *m) { return !m ? 0 : (m->multi ? m->multi->sh[0].m->head_taps : m->head_taps); }
 
 extern "C" int hb_matrix_process_dev(hb_matrix *m, const void *d_in, uintptr_t in_ld, void *d_out, uintptr_t out_ld, uintptr_t n,
                                      int accumulate, void *stream)
@@ -488,6 +909,7 @@ extern "C" int hb_matrix_process_dev(hb_matrix *m, const void *d_in, uintptr_t i
     int rc = check(m);
     if (rc) return rc;
     if ((!d_in || !d_out) && n) { set_error("hb_matrix_process_dev: null buffer"); return HB_ERR_BAD_ARG; }
+    if (m->multi) { set_error("hb_matrix_process_dev: a multi-device matrix takes host pointers (hb_matrix_process); its shards (hb_matrix_shard) take device pointers"); return HB_ERR_UNSUPPORTED; }
     // the audio thread never waits for set / resize: the block is skipped (MonoConvolve.cpp:181-183, MemorySwap.h:182-185)
     std::unique_lock<std::mutex> g(m->lock, std::try_to_lock);
     if (!g.owns_lock()) return HB_ERR_BUSY;
@@ -505,6 +927,7 @@ extern "C" int hb_matrix_process(hb_matrix *m, const void *const *ins, void *con
     std::unique_lock<std::mutex> g(m->lock, std::try_to_lock);
     if (!g.owns_lock()) return HB_ERR_BUSY;
     if (!n) return HB_OK;
+    if (m->multi) return front_process(m, ins, outs, n, accumulate);
     // a single uniform part (no head, one FFT size) is exactly one engine: its host path defers the device
     // work of hop-aligned calls behind the API's own one-hop latency (hb_conv_process)
     if (!m->head_taps && m->parts.size() == 1) return hb_conv_process(m->parts[0], ins, outs, n, accumulate);

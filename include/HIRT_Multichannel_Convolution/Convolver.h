@@ -27,6 +27,16 @@ namespace HISSTools
         Convolver(uint32_t numIns, uint32_t numOuts, uintptr_t maxLength, bool zeroLatency, uint32_t A, uint32_t B = 0, uint32_t C = 0, uint32_t D = 0)
         : mNumIns(std::max(numIns, 1u)), mNumOuts(numOuts), mN2M(true), mMatrix(1, std::max(numIns, 1u), numOuts, maxLength, zeroLatency, A, B, C, D) {}
 
+        // Superset: the same object dealt to several GPUs of this process -- `devices` lists CUDA device ordinals.  The input channels
+        // of an N x M matrix (numIns and numOuts multiples of the device count) or the channels of a parallel convolver are shared
+        // out; set / resize / process keep their reference signatures and take all channels, as on one device.
+        Convolver(uint32_t numIns, uint32_t numOuts, LatencyMode latency, const std::vector<int>& devices)
+        : mNumIns(std::max(numIns, 1u)), mNumOuts(numOuts), mN2M(true), mMatrix(1, std::max(numIns, 1u), numOuts, 16384, latency, devices) {}
+        Convolver(uint32_t numIO, LatencyMode latency, const std::vector<int>& devices)
+        : mNumIns(std::max(numIO, 1u)), mNumOuts(std::max(numIO, 1u)), mN2M(false), mMatrix(std::max(numIO, 1u), 1, 1, 16384, latency, devices) {}
+        Convolver(uint32_t numIns, uint32_t numOuts, uintptr_t maxLength, const std::vector<int>& devices, bool zeroLatency, uint32_t A, uint32_t B = 0, uint32_t C = 0, uint32_t D = 0)
+        : mNumIns(std::max(numIns, 1u)), mNumOuts(numOuts), mN2M(true), mMatrix(1, std::max(numIns, 1u), numOuts, maxLength, zeroLatency, A, B, C, D, devices) {}
+
         virtual ~Convolver() throw() {}
 
         // Clear IRs (Convolver.cpp:51-71)

@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <stdexcept>
+#include <vector>
 
 enum LatencyMode
 {
@@ -35,6 +36,20 @@ namespace HISSTools
                    int dtype = HB_F32, int device = 0) : mHandle(nullptr)
             {
                 create(groups, ins, outs, maxLength, zeroLatency, A, B, C, D, dtype, device);
+            }
+            // the same matrix dealt to several GPUs of this process (hb_matrix_create_multi / _latency_multi)
+            Matrix(uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t maxLength, LatencyMode latency, const std::vector<int>& devices, int dtype = HB_F32) : mHandle(nullptr)
+            {
+                hisstools_b200_detail::check(hb_matrix_create_latency_multi(&mHandle, dtype, groups, ins, outs, maxLength, static_cast<int>(latency),
+                                                                            devices.data(), static_cast<uint32_t>(devices.size())));
+            }
+            Matrix(uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t maxLength, bool zeroLatency, uint32_t A, uint32_t B, uint32_t C, uint32_t D,
+                   const std::vector<int>& devices, int dtype = HB_F32) : mHandle(nullptr)
+            {
+                const int code = hb_matrix_create_multi(&mHandle, dtype, groups, ins, outs, maxLength, zeroLatency ? 1 : 0, A, B, C, D,
+                                                        devices.data(), static_cast<uint32_t>(devices.size()));
+                if (code == HB_ERR_BAD_ARG) throw std::runtime_error(hb_last_error());
+                hisstools_b200_detail::check(code);
             }
             ~Matrix() { hb_matrix_destroy(mHandle); }
 

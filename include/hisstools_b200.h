@@ -118,7 +118,9 @@ int hb_conv_set_reset_offset(hb_conv *c, intptr_t offset);
  * element type of `ir` (HB_F32 or HB_F64; converted to the engine's type as Convolver.cpp:126-134
  * does for double IRs).  ir == NULL or length <= offset clears the pair.  Triggers reset(). */
 int hb_conv_set_ir(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length);
-/* same, `d_ir` in device memory in the engine's dtype */
+/* same, `d_ir` in device memory in the engine's dtype.  Synchronises: work enqueued earlier on ANY stream of the device
+ * (whatever produced d_ir) is waited for before the transforms start, and the call returns when the spectra are in place
+ * (d_ir may be reused at once). */
 int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *d_ir, uintptr_t length);
 /* grow / shrink the allocation to hold max_length taps per pair (the MemorySwap::equal step of
  * MonoConvolve.cpp:100-110).  Loaded IRs are kept (cut to the new capacity when it shrinks); the
@@ -158,6 +160,10 @@ int hb_conv_shard_attach(hb_conv *c, const void *handles);
 int hb_conv_process_shard_dev(hb_conv *c, const void *d_in, uintptr_t in_ld, void *d_out_shard, uintptr_t out_ld,
                               uintptr_t num_samples, int accumulate, void *stream);
 
+/* The same exchange between engines that live in ONE process (one per GPU): hb_conv_shard_export with handle_out = NULL on every
+ * engine, then attach_local on every engine with the array of all `world` engine handles in rank order.  Peer access between the
+ * devices is enabled here (cudaDeviceEnablePeerAccess).  hb_matrix_create_multi does this for a whole matrix. */
+int hb_conv_shard_attach_local(hb_conv *c, hb_conv *const *peers);
 /* late_ranks: bit r set = the owner-side sum on this rank gave up waiting for rank r's blocks at least once (longer than
  * HB_PEER_TIMEOUT_MS, default 30 s) and summed that hop without them.  Synchronises the device.  A rank that has no
  * impulse response loaded still takes part in every hop (it delivers silence), so only a stopped peer raises this. */
@@ -190,6 +196,10 @@ uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
  * cluster transform the inputs, split the (input, partition) products and reduce through distributed shared memory
  * (hb_conv_fused.cuh).  overlapped = 0 / 1 never fuse.  Results differ by summation order only.  Takes effect with a reset. */
 int hb_conv_set_schedule(hb_conv *c, int overlapped);
+/* Overlapped schedule only: 1 (default) = every tail launch on one second stream, one after the other; 2 = the tails of
+ * consecutive hops alternate between two streams, so the CTAs of the next tail are placed on the SMs one by one as the CTAs
+ * of the running one leave (hides the ramp-up and drain of a launch: profiles/r2_tail_streams.txt).  Takes effect with a reset. */
+int hb_conv_set_tail_streams(hb_conv *c, int streams);
 /* schedule in effect after the last reset: 0 serial (also whenever only one partition is loaded), 1 overlapped, 2 fused */
 int hb_conv_schedule(const hb_conv *c);
 /* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in
@@ -261,6 +271,27 @@ int hb_matrix_reset(hb_matrix *m);
 int hb_matrix_process(hb_matrix *m, const void *const *ins, void *const *outs, uintptr_t num_samples, int accumulate);
 int hb_matrix_process_dev(hb_matrix *m, const void *d_in, uintptr_t in_ld, void *d_out, uintptr_t out_ld,
                           uintptr_t num_samples, int accumulate, void *stream);
+/* One matrix on several GPUs of this process -- the N x M Convolver of Convolver.h:25-50 behind ONE handle and ONE host-pointer
+ * process call, its input channels dealt to `n_devices` GPUs (device ordinals in `devices`; ins and outs multiples of n_devices),
+ * or, for parallel banks (groups > 1), its banks dealt to the GPUs (groups a multiple of n_devices).  Every hb_matrix_* entry point
+ * works on the returned handle as on a single-device matrix: set / resize go to the device that holds the pair, process(ins, outs)
+ * takes all input rows and returns all output rows.  Device d holds inputs [d * ins / n, (d + 1) * ins / n) against all outputs and
+ * sums outputs [d * outs / n, ...): the sum over inputs of NToMonoConvolve.cpp:39-42 crosses devices
+ *   - inside the inverse-FFT kernels (peer stores over NVLink, the fused exchange of hb_conv_shard_*) when the scheme is one uniform
+ *     FFT size without a head -- calls are pipelined behind the API's own latency of fft_size / 2 as on one device;
+ *   - by an owner-side kernel that reads the other devices' partial blocks out of their memory (any scheme, any call size).
+ * One host worker thread per device runs the per-device share of every call.  Peer access between all devices is required
+ * (HB_ERR_UNSUPPORTED otherwise).  hb_matrix_process_dev is not available on the front; its shards take device pointers. */
+int hb_matrix_create_multi(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                           int zero_latency, uint32_t A, uint32_t B, uint32_t C, uint32_t D, const int *devices, uint32_t n_devices);
+int hb_matrix_create_latency_multi(hb_matrix **out, int dtype, uint32_t groups, uint32_t ins, uint32_t outs, uintptr_t max_length,
+                                   int latency_mode, const int *devices, uint32_t n_devices);
+/* the per-device matrices behind a multi-device front (1 and the handle itself on a single-device matrix; borrowed) */
+uint32_t hb_matrix_shards(const hb_matrix *m);
+hb_matrix *hb_matrix_shard(hb_matrix *m, uint32_t index);
+/* how the sum over inputs crosses devices: 0 nothing crosses (one device, or parallel banks), 1 owner-side peer reads, 2 fused into
+ * the inverse-FFT kernels */
+int hb_matrix_exchange(const hb_matrix *m);
 /* introspection: the uniform engines behind the scheme (borrowed handles; the tail is the last) */
 uint32_t hb_matrix_parts(const hb_matrix *m);
 hb_conv *hb_matrix_part(hb_matrix *m, uint32_t index);

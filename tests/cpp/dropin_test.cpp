@@ -2,7 +2,7 @@
 // (HISSTools_FFT.h, PartitionedConvolve.h, MonoConvolve.h, NToMonoConvolve.h, Convolver.h), compiled
 // against this repo's include/ instead and linked to libhisstools_b200.so.  It writes every result to a
 // raw float32 file; tests/test_gpu_cpp_dropin.py regenerates the same inputs and checks them against
-// the oracle.  Usage: dropin_test <output file> [audio file]
+// the oracle.  Usage: dropin_test <output file> [audio file] [number of GPUs for the multi-device section]
 #include "HISSTools_FFT/HISSTools_FFT.h"
 #include "HIRT_Multichannel_Convolution/Convolver.h"
 #include "SpectralProcessor.hpp"
@@ -201,6 +201,67 @@ int main(int argc, char **argv)
         HISSTools::IAudioFile missing("/nonexistent/file.wav");
         dump_code(missing.isOpen() ? 1 : 0);
         dump_code(missing.getErrorFlags());
+    }
+
+    // 10. (argv[3] = number of GPUs, >= 2) the same Convolver class dealt to several GPUs of this process: a uniform 8 x 8
+    // matrix (exchange fused into the inverse-FFT kernels), Convolver(4, 4, kLatencyShort) (owner-side peer reads) and four
+    // parallel channels, all through the reference's process(ins, outs, ...) with host pointers and ragged call sizes
+    const int ndev = argc > 3 ? atoi(argv[3]) : 0;
+    if (ndev >= 2)
+    {
+        std::vector<int> devices;
+        for (int d = 0; d < ndev; d++) devices.push_back(d);
+        {
+            const uint32_t N = 8;
+            HISSTools::Convolver cv(N, N, 3000, devices, false, 512);
+            cv.setResetOffset(0);
+            std::vector<std::vector<float>> xs, ys(N, std::vector<float>(6000));
+            for (uint32_t i = 0; i < N; i++) xs.push_back(noise(6000, 100 + i));
+            for (uint32_t o = 0; o < N; o++)
+                for (uint32_t i = 0; i < N; i++) { std::vector<float> ir = decaying(3000, 200 + o * N + i); dump_code(cv.set(i, o, ir.data(), 3000, false)); }
+            const size_t sizes[] = {256, 256, 100, 1024, 1, 411, 256};
+            size_t pos = 0, k = 0;
+            while (pos < 6000)
+            {
+                const size_t n = std::min(sizes[k++ % 7], 6000 - pos);
+                const float *ins[N]; float *outs[N];
+                for (uint32_t i = 0; i < N; i++) { ins[i] = xs[i].data() + pos; outs[i] = ys[i].data() + pos; }
+                cv.process(ins, outs, N, N, n);
+                pos += n;
+            }
+            dump_code(hb_matrix_exchange(cv.handle()));
+            for (auto &y : ys) dump(y);
+        }
+        const std::vector<int> dev4(devices.begin(), devices.begin() + std::min(ndev, 4));      // four channels: at most four devices
+        {
+            const uint32_t N = 4;
+            HISSTools::Convolver cv(N, N, kLatencyShort, dev4);
+            cv.setResetOffset(0);
+            std::vector<std::vector<float>> xs, ys(N, std::vector<float>(4096));
+            for (uint32_t i = 0; i < N; i++) xs.push_back(noise(4096, 300 + i));
+            for (uint32_t o = 0; o < N; o++)
+                for (uint32_t i = 0; i < N; i++) { std::vector<float> ir = decaying(9000, 400 + o * N + i); dump_code(cv.set(i, o, ir.data(), 9000, false)); }
+            for (size_t pos = 0; pos < 4096; pos += 512)
+            {
+                const float *ins[N]; float *outs[N];
+                for (uint32_t i = 0; i < N; i++) { ins[i] = xs[i].data() + pos; outs[i] = ys[i].data() + pos; }
+                cv.process(ins, outs, N, N, 512);
+            }
+            dump_code(hb_matrix_exchange(cv.handle()));
+            for (auto &y : ys) dump(y);
+        }
+        {
+            const uint32_t N = 4;
+            HISSTools::Convolver cv(N, kLatencyMedium, dev4);
+            cv.setResetOffset(0);
+            std::vector<std::vector<float>> xs, ys(N, std::vector<float>(4096));
+            for (uint32_t i = 0; i < N; i++) { xs.push_back(noise(4096, 500 + i)); std::vector<float> ir = decaying(3000, 600 + i); dump_code(cv.set(i, i, ir.data(), 3000, false)); }
+            const float *ins[N]; float *outs[N];
+            for (uint32_t i = 0; i < N; i++) { ins[i] = xs[i].data(); outs[i] = ys[i].data(); }
+            cv.process(ins, outs, N, N, 4096);
+            dump_code(hb_matrix_exchange(cv.handle()));
+            for (auto &y : ys) dump(y);
+        }
     }
 
     fclose(out_file);

@@ -50,10 +50,25 @@ def test_cpp_headers_compile_against_reference_style_caller():
 
 @pytest.mark.gpu
 def test_cpp_dropin_results():
+    _run_and_check(0)
+
+
+@pytest.mark.gpu
+def test_cpp_dropin_on_several_gpus():
+    """The same caller with the device-list constructors of HISSTools::Convolver: one object, one process(ins, outs, ...) call
+    with host pointers, the matrix dealt to every GPU of the box (section 10 of dropin_test.cpp)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    _run_and_check(8 if n >= 8 else (4 if n >= 4 else 2))
+
+
+def _run_and_check(ndev):
     exe, d = build_program()
     out = os.path.join(d, "out.bin")
     wav = os.path.join(ROOT, "tests", "golden", "audio", "wave_i24.wav")
-    res = subprocess.run([exe, out, wav], capture_output=True, text=True)
+    res = subprocess.run([exe, out, wav] + ([str(ndev)] if ndev else []), capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert "kernel launches" in res.stdout and int(res.stdout.split()[1]) > 0
     data = np.fromfile(out, np.float32)
@@ -158,4 +173,28 @@ def test_cpp_dropin_results():
     assert np.array_equal(take(100).view(np.uint32), GA["wave_i24_wav_ch1_from17_f32"].view(np.uint32))
     assert np.array_equal(take(int(meta[5]) * int(meta[6])).view(np.uint32), GA["wave_i24_wav_inter_f32"].view(np.uint32))
     assert code() == 0 and code() == 4
+    if ndev >= 2:
+        # 10. the Convolver class on ndev GPUs
+        N = 8
+        xs = [lcg_noise(6000, 100 + i) for i in range(N)]
+        irs = [[decaying(3000, 200 + o * N + i) for i in range(N)] for o in range(N)]
+        assert [code() for _ in range(N * N)] == [0] * (N * N)
+        assert code() == 2                                                # exchange fused into the inverse-FFT kernels
+        for o in range(N):
+            truth = sum(ck.direct_convolve_delayed(irs[o][i], xs[i], 256) for i in range(N))
+            assert ck.rel_rms(take(6000), truth) <= TOL32
+        N = 4
+        xs = [lcg_noise(4096, 300 + i) for i in range(N)]
+        irs = [[decaying(9000, 400 + o * N + i) for i in range(N)] for o in range(N)]
+        assert [code() for _ in range(N * N)] == [0] * (N * N)
+        assert code() == 1                                                # kLatencyShort: owner-side peer reads
+        for o in range(N):
+            truth = sum(ck.direct_convolve_delayed(irs[o][i], xs[i], 128) for i in range(N))
+            assert ck.rel_rms(take(4096), truth) <= TOL32
+        xs = [lcg_noise(4096, 500 + i) for i in range(N)]
+        irs = [decaying(3000, 600 + i) for i in range(N)]
+        assert [code() for _ in range(N)] == [0] * N
+        assert code() == 0                                                # parallel channels: nothing crosses
+        for i in range(N):
+            assert ck.rel_rms(take(4096), ck.direct_convolve_delayed(irs[i], xs[i], 512)) <= TOL32
     assert pos[0] == len(data)
