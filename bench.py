@@ -437,6 +437,14 @@ def run_ours(args):
     # ---- second pass with CUDA events around every kernel launch (roofline figure); kept out of the timed region
     # above because the event records open small gaps between the kernels
     prof_blocks = min(args.steps * R, 128)
+    tail_streams = eng.tail_streams
+    if tail_streams == 2:
+        # with two alternating tail streams a launch's events also span the time its CTAs wait for SMs: the kernel's own
+        # duration is taken with one tail stream (the timed region above ran with two)
+        eng.set_tail_streams(1)
+        for _ in range(4):
+            block(k)
+            k += 1
     eng.set_profiling(True)
     for _ in range(prof_blocks):
         block(k)
@@ -444,6 +452,12 @@ def run_ours(args):
     barrier()
     prof, hops = eng.get_profile()
     eng.set_profiling(False)
+    if tail_streams == 2:
+        eng.set_tail_streams(args.tail_streams)
+        for _ in range(4):
+            block(k)
+            k += 1
+        barrier()
     overlapped = eng.schedule == "overlapped"
     fused = eng.schedule == "fused"
     # the dominant launch: the tail multiply-accumulate (partitions 1..P-1, second stream) in the overlapped schedule,
@@ -470,23 +484,39 @@ def run_ours(args):
     # ---- multi-hop reuse: calls of 4 and 8 blocks, every IR spectrum streamed once per call (reported separately: the
     # per-hop byte figure above does not apply to it) --------------------------------------
     multi = None
-    if sharded is None and not args.no_multi_hop:
+    if not args.no_multi_hop:
         multi = []
-        for mh in (4, 8):
+        # HBM-bound engines: 4 / 8 blocks per call share one pass over the IR spectra; launch-latency-bound ones (configs 1-3): 8 / 64
+        # blocks per call share their launches
+        bytes_hint = eng.bytes_per_hop > 256e6
+        for mh in ((4, 8) if bytes_hint else (8, 64)):
             xm = [torch.rand(rows_in, n * mh, generator=gen, device=dev, dtype=tdt) * 2 - 1 for _ in range(2)]
-            ym = torch.zeros(rows_out, n * mh, device=dev, dtype=tdt)
+            ym = torch.zeros(shard_rows if sharded is not None else rows_out, n * mh, device=dev, dtype=tdt)
+
+            def call(q):
+                if sharded is not None:
+                    sharded.process_device(xm[q % 2], ym, n * mh, stream.cuda_stream)
+                else:
+                    eng.process_device(xm[q % 2].data_ptr(), n * mh, ym.data_ptr(), n * mh, n * mh, False, stream.cuda_stream)
             for q in range(3):
-                eng.process_device(xm[q % 2].data_ptr(), n * mh, ym.data_ptr(), n * mh, n * mh, False, stream.cuda_stream)
+                call(q)
             barrier()
-            m_calls = int(max(6, min(4096, math.ceil(0.3 / max(ms_per_block * 1e-3 * 2, 1e-6)))))
+            m_calls = int(max(6, min(4096, math.ceil(0.3 / max(t_block * 2, 1e-6)))))
+            if world > 1:
+                mc = torch.tensor([float(m_calls)], device=dev, dtype=torch.float64)
+                dist.all_reduce(mc, op=dist.ReduceOp.MAX)
+                m_calls = int(mc.item())
             m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             m0.record(stream)
             for q in range(m_calls):
-                eng.process_device(xm[q % 2].data_ptr(), n * mh, ym.data_ptr(), n * mh, n * mh, False, stream.cuda_stream)
+                call(q)
             eng.join(stream.cuda_stream)
             m1.record(stream)
             barrier()
-            mms = m0.elapsed_time(m1) / m_calls
+            mt = torch.tensor([m0.elapsed_time(m1) / m_calls], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+            mms = float(mt.item())
             multi.append({"blocks_per_call": mh, "value": job_rows * n * mh / (mms * 1e-3) / 1e6, "unit": UNIT, "ms_per_call": mms,
                           "ms_per_block": mms / mh, "calls": m_calls})
             del xm, ym
@@ -609,6 +639,7 @@ def run_ours(args):
                            "calls": "one process call per block of %d samples; a step is %d consecutive blocks" % (B, R),
                            "window": "CUDA events on the launching stream; the engine's look-ahead (tail) stream is joined before the closing event"},
                 "engine": {"sharding": mode, "local_inputs": l_ins, "outputs": outs, "groups": l_groups, "schedule": eng.schedule,
+                           "tail_streams": tail_streams,
                            "transforms": {1: "one CTA each", 2: "cluster of 8 CTAs each (DSMEM)", 3: "four-step chains"}.get(eng.fft_path, "?"),
                            "l2": "inputs larger than L2: %.2f GiB of IR spectra per rank streamed every block" % (bytes_per_hop / 2 ** 30)
                                  if bytes_per_hop > 256e6 else "working set %.1f MiB is L2-resident (not an HBM-roofline case)" % (bytes_per_hop / 2 ** 20),
@@ -625,7 +656,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if multi is not None:
             line["multi_hop_reuse"] = {"runs": multi, "note": "hop-aligned calls of several blocks: on HBM-bound engines every IR spectrum is read "
-                                                              "once per call (k_cmac_tma_mh)"}
+                                                              "once per call (k_cmac_mh2); on launch-latency-bound engines the blocks of a call share their launches"}
         print(json.dumps(line))
     if sharded is not None:
         sharded.close()

@@ -97,6 +97,7 @@ SIGNATURES = {
     "hb_conv_get_trace": (C.c_int, [V, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_conv_set_schedule": (C.c_int, [V, C.c_int]),
     "hb_conv_set_tail_streams": (C.c_int, [V, C.c_int]),
+    "hb_conv_tail_streams": (C.c_int, [V]),
     "hb_conv_schedule": (C.c_int, [V]),
     "hb_conv_bytes_per_launch": (C.c_uint64, [V]),
 }

@@ -180,6 +180,10 @@ class _Engine:
         return _abi.check(_abi.lib().hb_conv_set_tail_streams(self._h, int(streams)))
 
     @property
+    def tail_streams(self):
+        return _abi.lib().hb_conv_tail_streams(self._h)
+
+    @property
     def schedule(self):
         return ("serial", "overlapped", "fused")[_abi.lib().hb_conv_schedule(self._h)]
 

@@ -26,7 +26,8 @@ namespace
 {
 constexpr uintptr_t MIN_FFT_LOG2 = 5;       // PartitionedConvolve.h:18
 constexpr uintptr_t MAX_FFT_LOG2 = 20;      // PartitionedConvolve.h:19
-constexpr size_t INBOX_LATE_OFF = 192;     // inbox tail: arrival counters [2][world] (<= 128 bytes), then the late-peer flag word
+// inbox tail: arrival counters [HB_INBOX_DEPTH][world] (<= 1024 bytes), then the late-peer flag word
+constexpr size_t INBOX_LATE_OFF = 1024, INBOX_TAIL_BYTES = 1280;
 constexpr uint32_t MH_MAX = 8;              // hops one multi-hop multiply-accumulate launch covers at most
 constexpr uint32_t MH_EXTRA = MH_MAX - 1;   // extra delay-line slots that needs
 
@@ -108,14 +109,16 @@ struct hb_conv
     Range r_full{}, r_head{}, r_tail{};
     DevBuf d_St[2];                 // tail partial segments, double-buffered over hops
     cudaStream_t s_tail = nullptr, s_tail_b = nullptr;
-    int tail_streams = 1;           // hb_conv_set_tail_streams: 2 = the tails of consecutive hops alternate between two streams, so that the
-                                    // CTAs of the next tail take over the SMs one by one as the CTAs of the running one exit
+    int tail_streams_req = 0;       // hb_conv_set_tail_streams: 0 automatic, 1, or 2 = the tails of consecutive hops alternate between two
+    int tail_streams = 1;           // streams, so that the CTAs of the next tail take over the SMs as the CTAs of the running one exit (in effect)
     cudaEvent_t ev_fwd = nullptr, ev_tail[2] = {nullptr, nullptr};
     bool tail_valid = false;        // d_St[tail_par] holds the tail of the upcoming hop
     bool tail_missing = false;      // a multi-hop batch ran last: nothing was computed ahead for the upcoming hop
     int tail_par = 0;
     DevBuf d_trace;                 // optional kernel timeline (hb_conv_set_trace)
     DevBuf d_Smh;                   // partial segments of a multi-hop launch: [hop][cta + tile][row][TBV]
+    uint32_t extra_slots = MH_EXTRA;  // delay-line slots beyond P: the hops one launch may look ahead (63 while the delay line stays small)
+    uint32_t hb_max = 1;            // hops one batch of a launch-latency-bound engine covers at most (process_core), 1 = no batches
     int multi_hop = 1;              // hb_conv_set_multi_hop: batch the hops of one call over a single pass of the IR spectra
     bool mh_ok = false;             // eligible for the current geometry (plan_geometry)
     int mh_max = 1;                 // hops one multi-hop launch covers at most for the current geometry
@@ -145,7 +148,7 @@ struct hb_conv
     void *peer_base[HB_MAX_WORLD] = {};
     bool peers_attached = false;
     bool peers_local = false;       // peers of the same process (plain pointers, nothing to close)
-    uint32_t hop_seq = 0, parity_uses[2] = {0, 0};
+    uint32_t hop_seq = 0, parity_uses[HB_INBOX_DEPTH] = {};
 
     // optional per-kernel timing (hb_conv_set_profiling): PROF_EV events per hop, five on the launching stream
     // (around the forward FFTs, the whole / head multiply-accumulate, the wait for the tail, the inverse FFTs)
@@ -209,7 +212,7 @@ void plan_geometry(hb_conv *c)
     g.B = 1u << (g.log2n - 1);
     g.Pcap = (uint32_t) (c->max_length / g.B);
     g.P = c->P;
-    g.R = c->P ? c->P + MH_EXTRA : 0;             // the delay line keeps the look-ahead slots of a multi-hop launch
+    g.R = c->P ? c->P + c->extra_slots : 0;       // the delay line keeps the look-ahead slots of a multi-hop launch
     g.OT = choose_ot(c->outs);
     g.n_ot = (c->outs + g.OT - 1) / g.OT;
     const uint32_t xq = g.B / cpv;
@@ -256,6 +259,10 @@ void plan_geometry(hb_conv *c)
         if (per_output / cs <= (uint64_t(256) << 10)) { c->fused = true; c->fused_cs = cs; }
     }
     c->split = !c->fused && g.P >= 2 && (c->schedule == 1 || ((c->schedule == 2 || c->schedule == 3) && tail_bytes >= (uint64_t(4) << 20)));
+    // Short tail launches lose a visible share of the hop to their ramp-up and drain (about 10 us per launch): with two tail streams
+    // the next launch takes over the SMs as the running one leaves them.  Measured (profiles/r2_tail_streams.txt): one rank of config 4
+    // on 8 GPUs (1.07 GB per launch) 167.9 -> 164.5 us per hop, config 5 (0.53 GB) 90.9 -> 87.0 us, config 4 on one GPU (8.6 GB) unchanged.
+    c->tail_streams = c->tail_streams_req ? c->tail_streams_req : (tail_bytes <= (uint64_t(3) << 30) ? 2 : 1);
     // TMA ring depth: about 96 KB in flight per SM, 3 to 6 stages.  Measured on B200 at config 4 (32.5 KB stages,
     // profiles/r1_ring_depth.txt): 3 stages stream 7.2 TB/s, 2 stages 6.6, 5-6 stages 6.5 -- twice Little's law for
     // the chip (7.3 TB/s x ~1 us / 148 SMs = 49 KB) is enough, and a deeper ring only lowers the DRAM efficiency.
@@ -295,6 +302,9 @@ void plan_geometry(hb_conv *c)
                    c->mh_stages >= 2;
         static const char *env_scalar = getenv("HB_MH_SCALAR");              // experiments only: the scalar kernel on float engines
         c->mh_packed = c->mh_ok && c->dtype == HB_F32 && mh2_supported(g, 2) && !(env_scalar && atoi(env_scalar));
+        // batches of hops on engines that are NOT HBM-bound (launch-latency-bound: one cluster launch or three kernels per hop):
+        // a call that brings several hops runs their forward FFTs, multiply-accumulates and inverse FFTs as three launches
+        c->hb_max = (c->multi_hop && !c->mh_ok && (int) log2m <= single_cta_max_log2m(c) && g.P >= 1) ? c->extra_slots + 1 : 1;
         // hops one pass carries at most: 8 (half units) where the prepared delay-line tiles stay small beside the IR unit
         c->mh_max = !c->mh_ok ? 1 : (!c->mh_packed ? 4 : (mh2_supported(g, 8) ? 8 : (mh2_supported(g, 4) ? 4 : 2)));
     }
@@ -368,7 +378,7 @@ void free_device(hb_conv *c)
 size_t nyq_capacity(const hb_conv *c)
 {
     const size_t minB = size_t(1) << (MIN_FFT_LOG2 - 1);
-    return c->max_length / minB + MH_EXTRA;
+    return c->max_length / minB + c->extra_slots;
 }
 
 // allocate everything whose size depends on max_length (ctor and resize)
@@ -378,7 +388,10 @@ int alloc_capacity(hb_conv *c)
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = nullptr;
     const size_t hbytes = h_vectors(c) * 16;
     const size_t maxB_ = (size_t(1) << c->max_fft_log2) >> 1;
-    const size_t xbytes = size_t(c->groups) * c->ins * (c->max_length + MH_EXTRA * maxB_) * 2 * c->esize();
+    // look-ahead slots: 7 (multi-hop reuse on HBM-bound engines); 63 while they cost little memory, so that a launch-latency-bound
+    // engine can take up to 64 hops of a call in one set of launches
+    c->extra_slots = size_t(c->groups) * c->ins * 63 * maxB_ * 2 * c->esize() <= (size_t(32) << 20) ? 63u : MH_EXTRA;
+    const size_t xbytes = size_t(c->groups) * c->ins * (c->max_length + c->extra_slots * maxB_) * 2 * c->esize();
     const size_t pmax = nyq_capacity(c);
     if (cudaMalloc(&c->d_H, std::max<size_t>(hbytes, 16)) != cudaSuccess ||
         cudaMalloc(&c->d_X, std::max<size_t>(xbytes, 16)) != cudaSuccess ||
@@ -427,7 +440,7 @@ template <class T> int tw_fits(uint32_t log2m) { return fft_smem<T>(log2m) + tw_
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
 template <class T, int XA, int OB>
-int launch_cmac_inst(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t st)
+int launch_cmac_inst(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t st, uint32_t nb = 1, uint64_t set_stride = 0)
 {
     typedef typename VecOf<T>::type V;
     const Geom &g = c->g;
@@ -444,30 +457,32 @@ int launch_cmac_inst(hb_conv *c, const Range &r, void *S, int variant, cudaStrea
     {
         int rc = allow_smem(k_cmac_ldg<T, XA, OB>, 0);
         if (rc) return rc;
-        k_cmac_ldg<T, XA, OB><<<r.G, 256, 0, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S);
+        k_cmac_ldg<T, XA, OB><<<dim3(r.G, nb), 256, 0, st>>>(g, r, (const V *) c->d_H, (const V *) c->d_X, (V *) S, set_stride);
     }
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
 
 // one multiply-accumulate launch over the partitions of `r` into the partial segments S
+// nb > 1 (direct-load variant only): the same partitions for nb consecutive hops in one launch, hop j against the frame j slots
+// below r.slot, partial segments set_stride vectors apart
 template <class T>
-int launch_cmac(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t st)
+int launch_cmac(hb_conv *c, const Range &r, void *S, int variant, cudaStream_t st, uint32_t nb = 1, uint64_t set_stride = 0)
 {
     if (!r.U) return HB_OK;
     const uint32_t key = c->g.XA * 16 + c->g.OB;
     switch (key)
     {
-        case 1 * 16 + 1: return launch_cmac_inst<T, 1, 1>(c, r, S, variant, st);
-        case 1 * 16 + 2: return launch_cmac_inst<T, 1, 2>(c, r, S, variant, st);
-        case 1 * 16 + 4: return launch_cmac_inst<T, 1, 4>(c, r, S, variant, st);
-        case 1 * 16 + 8: return launch_cmac_inst<T, 1, 8>(c, r, S, variant, st);
-        case 2 * 16 + 1: return launch_cmac_inst<T, 2, 1>(c, r, S, variant, st);
-        case 2 * 16 + 2: return launch_cmac_inst<T, 2, 2>(c, r, S, variant, st);
-        case 2 * 16 + 4: return launch_cmac_inst<T, 2, 4>(c, r, S, variant, st);
-        case 4 * 16 + 1: return launch_cmac_inst<T, 4, 1>(c, r, S, variant, st);
-        case 4 * 16 + 2: return launch_cmac_inst<T, 4, 2>(c, r, S, variant, st);
-        case 8 * 16 + 1: return launch_cmac_inst<T, 8, 1>(c, r, S, variant, st);
+        case 1 * 16 + 1: return launch_cmac_inst<T, 1, 1>(c, r, S, variant, st, nb, set_stride);
+        case 1 * 16 + 2: return launch_cmac_inst<T, 1, 2>(c, r, S, variant, st, nb, set_stride);
+        case 1 * 16 + 4: return launch_cmac_inst<T, 1, 4>(c, r, S, variant, st, nb, set_stride);
+        case 1 * 16 + 8: return launch_cmac_inst<T, 1, 8>(c, r, S, variant, st, nb, set_stride);
+        case 2 * 16 + 1: return launch_cmac_inst<T, 2, 1>(c, r, S, variant, st, nb, set_stride);
+        case 2 * 16 + 2: return launch_cmac_inst<T, 2, 2>(c, r, S, variant, st, nb, set_stride);
+        case 2 * 16 + 4: return launch_cmac_inst<T, 2, 4>(c, r, S, variant, st, nb, set_stride);
+        case 4 * 16 + 1: return launch_cmac_inst<T, 4, 1>(c, r, S, variant, st, nb, set_stride);
+        case 4 * 16 + 2: return launch_cmac_inst<T, 4, 2>(c, r, S, variant, st, nb, set_stride);
+        case 8 * 16 + 1: return launch_cmac_inst<T, 8, 1>(c, r, S, variant, st, nb, set_stride);
     }
     set_error("internal: no multiply-accumulate kernel for XA=%u OB=%u", c->g.XA, c->g.OB);
     return HB_ERR_UNSUPPORTED;
@@ -1089,6 +1104,8 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
             const size_t left = nh - h;
             int nb = 1;
             while (nb * 2 <= c->mh_max && size_t(nb) * 2 <= left) nb *= 2;
+            const bool small_batch = nb == 1 && c->hb_max > 1 && left >= 2;
+            if (small_batch) nb = (int) std::min<size_t>(left, c->hb_max);
             if (nb == 1)
             {
                 const bool first = h == 0, last = h + 1 == nh;
@@ -1112,10 +1129,15 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
                                     last_in_batch ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st, (uint32_t) nb))) return rc;
             Range rf = c->r_full;
             rf.slot = slot0; rf.kind = 2;
-            const uint32_t split = mh_split(c, nb);
+            const uint32_t split = small_batch ? 1u : mh_split(c, nb);
             const uint64_t set_stride = uint64_t(rf.G + c->g.tiles * split) * (c->g.Q / split);
-            if ((rc = c->d_Smh.ensure(size_t(MH_MAX) * uint64_t(rf.G + c->g.tiles) * c->g.Q * 16))) return rc;
-            if ((rc = launch_cmac_mh<T>(c, rf, c->d_Smh.p, nb, set_stride, st))) return rc;
+            if ((rc = c->d_Smh.ensure(size_t(std::max<uint32_t>(MH_MAX, c->hb_max)) * uint64_t(rf.G + c->g.tiles) * c->g.Q * 16))) return rc;
+            if (small_batch)
+            {
+                // launch-latency-bound engine: nothing to reuse (its spectra sit in L2), the hops just share their launches
+                if ((rc = launch_cmac<T>(c, rf, c->d_Smh.p, 0, st, (uint32_t) nb, set_stride))) return rc;
+            }
+            else if ((rc = launch_cmac_mh<T>(c, rf, c->d_Smh.p, nb, set_stride, st))) return rc;
             // inverse transforms of the nb hops in one launch: hop j sums set j, runs its Nyquist products from slot0 - j and
             // leaves its block B samples further on; the last hop of the call stays behind in the staging row
             {
@@ -1205,10 +1227,8 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
     const size_t rw = c->rw;
     const size_t nh = (rw + n) / B;
 
-    // one hop: this rank's partial blocks to their owners, then the owner-side sum of the blocks that arrived here into
-    // row set `yout` at offset `off`; carry_dst (optional) first receives the block at carry_src (the output-ring read)
-    auto shard_hop = [&](const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld,
-                         T *yout, size_t ld, size_t off, int add_result, const T *carry_src, T *carry_dst, size_t carry_dst_ld) -> int
+    // the exchange of nb consecutive hops starting with the next sequence number: where every partial block goes ...
+    auto make_peer = [&](uint32_t nb, GatherBatch &gb) -> PeerOut
     {
         PeerOut peer;
         for (uint32_t r = 0; r < world; r++)
@@ -1217,9 +1237,36 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
             peer.count[r] = (uint32_t *) ((char *) c->peer_base[r] + c->inbox_data_bytes);
         }
         peer.world = world; peer.rank = c->shard_rank; peer.outs_local = o_loc;
-        peer.parity = (++c->hop_seq) & 1u;
+        peer.parity = (c->hop_seq + 1) % HB_INBOX_DEPTH;
         peer.slot = c->inbox_slot;
-        const uint32_t expected = (++c->parity_uses[peer.parity]) * o_loc;
+        memset(&gb, 0, sizeof(gb));
+        gb.last_j = -1;
+        for (uint32_t j = 0; j < nb; j++)
+        {
+            const uint32_t par = (++c->hop_seq) % HB_INBOX_DEPTH;
+            gb.e[j] = (++c->parity_uses[par]) * o_loc;
+        }
+        return peer;
+    };
+    // ... and the owner-side sum of the blocks that arrived here (nb hops in one launch)
+    auto gather = [&](const PeerOut &peer, const GatherBatch &gb, uint32_t nb, T *yout, size_t ld, size_t off, int add_result,
+                      const T *carry_src, T *carry_dst, size_t carry_dst_ld) -> int
+    {
+        k_gather<T><<<dim3(o_loc, nb), 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
+                                                     peer.parity, peer.slot, gb, (uint32_t) B, yout, ld, off, add_result,
+                                                     carry_src, c->yout_ld, carry_dst, carry_dst_ld, accumulate,
+                                                     (unsigned long long *) c->d_trace.p, c->g.hop, peer_timeout_ns(),
+                                                     (uint32_t *) ((char *) c->d_inbox + c->inbox_data_bytes + INBOX_LATE_OFF));
+        HB_LAUNCH_CHECK();
+        return HB_OK;
+    };
+    // one hop: this rank's partial blocks to their owners, then the owner-side sum of the blocks that arrived here into
+    // row set `yout` at offset `off`; carry_dst (optional) first receives the block at carry_src (the output-ring read)
+    auto shard_hop = [&](const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld,
+                         T *yout, size_t ld, size_t off, int add_result, const T *carry_src, T *carry_dst, size_t carry_dst_ld) -> int
+    {
+        GatherBatch gb;
+        const PeerOut peer = make_peer(1, gb);
         InvIO<T> io = {nullptr, 0, 0, 0, nullptr, 0, nullptr, 0, 0};
         int r;
         if (silent)
@@ -1228,13 +1275,7 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
             HB_LAUNCH_CHECK();
         }
         else if ((r = launch_hop<T>(c, st, prev, prev_ld, newest, new_ld, save, save_ld, io, peer))) return r;
-        k_gather<T><<<o_loc, 256, 0, st>>>((const T *) c->d_inbox, (const uint32_t *) ((const char *) c->d_inbox + c->inbox_data_bytes), world, o_loc,
-                                          peer.parity, peer.slot, expected, (uint32_t) B, yout, ld, off, add_result,
-                                          carry_src, c->yout_ld, carry_dst, carry_dst_ld, accumulate,
-                                          (unsigned long long *) c->d_trace.p, c->g.hop, peer_timeout_ns(),
-                                          (uint32_t *) ((char *) c->d_inbox + c->inbox_data_bytes + INBOX_LATE_OFF));
-        HB_LAUNCH_CHECK();
-        return HB_OK;
+        return gather(peer, gb, 1, yout, ld, off, add_result, carry_src, carry_dst, carry_dst_ld);
     };
 
     const char *ib = (const char *) d_in, *ie = (const char *) (d_in + (rows_in - 1) * in_ld + n);
@@ -1245,13 +1286,56 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
         const int cur = c->cur, nxt = cur ^ 1;
         const T *x_keep = (const T *) c->d_xin[cur].p + c->x_tail;
         const T *y_keep = (const T *) c->d_yout[cur].p + c->y_tail;
-        for (size_t h = 0; h < nh; h++)
+        size_t h = 0;
+        while (h < nh)
         {
-            const bool first = h == 0, last = h + 1 == nh;
-            if ((rc = shard_hop(first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
-                                last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld,
-                                last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
-                                first ? y_keep : nullptr, (first && d_out) ? d_out : nullptr, out_ld))) return rc;
+            const bool first = h == 0;
+            int nb = 1;
+            if (!silent && c->mh_ok) while (nb * 2 <= c->mh_max && size_t(nb) * 2 <= nh - h) nb *= 2;
+            if (nb == 1)
+            {
+                const bool last = h + 1 == nh;
+                if ((rc = shard_hop(first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                    last ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld,
+                                    last ? (T *) c->d_yout[nxt].p : d_out, last ? c->yout_ld : out_ld, last ? 0 : (h + 1) * B, last ? 0 : accumulate,
+                                    first ? y_keep : nullptr, (first && d_out) ? d_out : nullptr, out_ld))) return rc;
+                h++;
+                continue;
+            }
+            // ---- multi-hop reuse on the sharded engine: nb hops over ONE pass of this rank's IR spectra, their partial blocks
+            // delivered by one inverse launch (hop j into inbox slot seq + j), summed by one owner-side launch ----
+            if (c->split && c->tail_valid) HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
+            c->tail_valid = false;
+            const bool last_in_batch = h + nb == nh;
+            c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
+            const uint32_t slot0 = c->g.slot;
+            c->g.hop += nb;
+            c->g.trace = (unsigned long long *) c->d_trace.p;
+            if ((rc = launch_fwd<T>(c, first ? x_keep : d_in + (h - 1) * B, first ? c->xin_ld : in_ld, d_in + h * B, in_ld,
+                                    last_in_batch ? (T *) c->d_xin[nxt].p : nullptr, c->xin_ld, st, (uint32_t) nb))) return rc;
+            Range rf = c->r_full;
+            rf.slot = slot0; rf.kind = 2;
+            const uint32_t split = mh_split(c, nb);
+            const uint64_t set_stride = uint64_t(rf.G + c->g.tiles * split) * (c->g.Q / split);
+            if ((rc = c->d_Smh.ensure(size_t(MH_MAX) * uint64_t(rf.G + c->g.tiles) * c->g.Q * 16))) return rc;
+            if ((rc = launch_cmac_mh<T>(c, rf, c->d_Smh.p, nb, set_stride, st))) return rc;
+            GatherBatch gb;
+            const PeerOut peer = make_peer((uint32_t) nb, gb);
+            {
+                SegSets sets;
+                memset(&sets, 0, sizeof(sets));
+                sets.n = 1;
+                sets.s[0].S = c->d_Smh.p; sets.s[0].U = rf.U * split; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G; sets.s[0].split = split;
+                InvIO<T> io = {nullptr, 0, 0, 0, nullptr, 0, nullptr, 0, 0};
+                InvBatch ib = no_batch();
+                ib.set_stride = set_stride;
+                if ((rc = launch_inv<T>(c, sets, io, st, peer, (uint32_t) nb, ib))) return rc;
+            }
+            if (last_in_batch) { gb.last_j = nb - 1; gb.last_yout = c->d_yout[nxt].p; gb.last_ld = c->yout_ld; }
+            if ((rc = gather(peer, gb, (uint32_t) nb, d_out, out_ld, (h + 1) * B, accumulate, first ? y_keep : nullptr, (first && d_out) ? d_out : nullptr, out_ld))) return rc;
+            c->g.slot = slot0 >= uint32_t(nb - 1) ? slot0 - (nb - 1) : slot0 + c->g.R - (nb - 1);
+            if (c->split) c->tail_missing = true;
+            h += nb;
         }
         c->cur = nxt;
         c->x_tail = c->y_tail = 0;
@@ -1373,7 +1457,7 @@ extern "C" int hb_conv_create(hb_conv **out, int dtype, uint32_t groups, uint32_
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete c; return HB_ERR_CUDA; }
     static const char *env_ts = getenv("HB_TAIL_STREAMS");           // experiments: default number of tail streams
-    if (env_ts && atoi(env_ts) == 2) c->tail_streams = 2;
+    if (env_ts && (atoi(env_ts) == 1 || atoi(env_ts) == 2)) c->tail_streams_req = atoi(env_ts);
     c->tw_log2 = (int) l2;
     rc = make_twiddles(dtype, c->tw_log2, &c->d_tw);
     if (rc == HB_OK) rc = alloc_capacity(c);
@@ -1715,9 +1799,9 @@ extern "C" int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, v
     if (c->d_inbox) { set_error("hb_conv_shard_export: already exported"); return HB_ERR_BAD_ARG; }
     static_assert(sizeof(cudaIpcMemHandle_t) == HB_IPC_HANDLE_BYTES, "IPC handle size");
     const size_t slot = (size_t(1) << c->max_fft_log2) >> 1;
-    const size_t data = (size_t(2) * world * (c->outs / world) * slot * c->esize() + 255) & ~size_t(255);
-    HB_CUDA(cudaMalloc(&c->d_inbox, data + 256));
-    HB_CUDA(cudaMemset(c->d_inbox, 0, data + 256));
+    const size_t data = (size_t(HB_INBOX_DEPTH) * world * (c->outs / world) * slot * c->esize() + 255) & ~size_t(255);
+    HB_CUDA(cudaMalloc(&c->d_inbox, data + INBOX_TAIL_BYTES));
+    HB_CUDA(cudaMemset(c->d_inbox, 0, data + INBOX_TAIL_BYTES));
     HB_CUDA(cudaDeviceSynchronize());
     if (handle_out)                 // NULL: the peers live in this process (hb_conv_shard_attach_local)
     {
@@ -1727,7 +1811,8 @@ extern "C" int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, v
     }
     c->shard_world = world; c->shard_rank = rank;
     c->inbox_data_bytes = data; c->inbox_slot = slot;
-    c->hop_seq = 0; c->parity_uses[0] = c->parity_uses[1] = 0;
+    c->hop_seq = 0;
+    for (uint32_t k = 0; k < HB_INBOX_DEPTH; k++) c->parity_uses[k] = 0;
     return HB_OK;
 }
 
@@ -1839,9 +1924,9 @@ extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)
 extern "C" int hb_conv_set_tail_streams(hb_conv *c, int streams)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
-    if (streams != 1 && streams != 2) { set_error("tail streams must be 1 or 2"); return HB_ERR_BAD_ARG; }
+    if (streams < 0 || streams > 2) { set_error("tail streams must be 0 (automatic), 1 or 2"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
-    c->tail_streams = streams;
+    c->tail_streams_req = streams;
     c->need_reset = true;
     return HB_OK;
 }
@@ -1943,6 +2028,7 @@ extern "C" int hb_conv_get_profile(hb_conv *c, double *ms, uint64_t *hops)
     return HB_OK;
 }
 
+extern "C" int hb_conv_tail_streams(const hb_conv *c) { return c ? c->tail_streams : 0; }
 extern "C" int hb_conv_schedule(const hb_conv *c) { return !c ? 0 : (c->fused ? 2 : (c->split ? 1 : 0)); }
 
 extern "C" uint64_t hb_conv_bytes_per_launch(const hb_conv *c)

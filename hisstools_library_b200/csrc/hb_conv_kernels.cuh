@@ -467,12 +467,21 @@ __global__ void __launch_bounds__(288, 1) k_cmac_tma_mh(const Geom g, const Rang
 // k_cmac, variant "ldg": same decomposition, every thread loads its own vectors straight from global
 // memory (read-once, L1 bypass).  Kept as the comparison point for the TMA ring (profiles/).
 // ---------------------------------------------------------------------------------------------
+// blockIdx.y = hop j of a batch of hops (small engines, hb_conv.cu process_core): the frame of hop j sits j slots below rg.slot and
+// its partial segments go set_stride vectors further on -- nb hops of a launch-latency-bound engine in one launch.
 template <class T, int XA, int OB>
-__global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg, const typename VecOf<T>::type *__restrict__ H,
+__global__ void __launch_bounds__(256) k_cmac_ldg(const Geom g, const Range rg_in, const typename VecOf<T>::type *__restrict__ H,
                                                   const typename VecOf<T>::type *__restrict__ X,
-                                                  typename VecOf<T>::type *__restrict__ S)
+                                                  typename VecOf<T>::type *__restrict__ S, const uint64_t set_stride)
 {
     typedef typename VecOf<T>::type V;
+    Range rg = rg_in;
+    if (blockIdx.y)
+    {
+        const uint32_t j = blockIdx.y;
+        rg.slot = rg.slot >= j ? rg.slot - j : rg.slot + g.R - j;
+        S += uint64_t(j) * set_stride;
+    }
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid % g.TX, ty = tid / g.TX;
     trace_mark(g, rg.kind, 0);
@@ -695,11 +704,16 @@ __global__ void __launch_bounds__(512) k_fwd(const Geom g, const T *__restrict__
 // counter for (parity, source).  k_gather on the owner waits for the counters and sums the sources in rank
 // order (deterministic).  world == 0: not sharded.
 constexpr int HB_MAX_WORLD = 16;
+// The inbox keeps HB_INBOX_DEPTH hops apart ("parity" = hop sequence number mod depth).  A rank may be ahead of an owner by
+// the hops of its own launch plus those of the owner's launch in flight; with at most 8 hops per multi-hop launch, 16 slots
+// are never overwritten before the owner's sum has read them (the stream order of gather -> inverse on every rank does the
+// flow control: DESIGN.md 6).
+constexpr uint32_t HB_INBOX_DEPTH = 16;
 struct PeerOut
 {
     void *data[HB_MAX_WORLD];          // inbox data of every rank (own entry = local memory)
     uint32_t *count[HB_MAX_WORLD];     // arrival counters of every rank
-    uint32_t world, rank, outs_local, parity;
+    uint32_t world, rank, outs_local, parity;      // parity: inbox slot of hop 0 of the launch (hop j of a batch: parity + j mod depth)
     uint64_t slot;                     // elements per inbox block (hop capacity)
 };
 
@@ -925,7 +939,8 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
     {
         // partial block of output `ch` -> inbox of its owner, slot (parity, this rank, local output index)
         const uint32_t owner = ch / peer.outs_local, o_loc = ch - owner * peer.outs_local;
-        T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(peer.parity) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
+        const uint32_t par = (peer.parity + blockIdx.y) % HB_INBOX_DEPTH;
+        T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(par) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
 #pragma unroll
         for (int e = 0; e < EPT / 2; e++)
         {
@@ -942,7 +957,7 @@ __global__ void __launch_bounds__(512) k_inv(const Geom g, const SegSets sets,
         if (tid == 0)
         {
             __threadfence_system();
-            atomicAdd_system(peer.count[owner] + peer.parity * peer.world + peer.rank, 1u);
+            atomicAdd_system(peer.count[owner] + par * peer.world + peer.rank, 1u);
         }
         trace_mark(g, 3, 1);
         return;
@@ -987,14 +1002,15 @@ __global__ void __launch_bounds__(256) k_shard_silence(const PeerOut peer, uint3
 {
     const uint32_t ch = blockIdx.x;
     const uint32_t owner = ch / peer.outs_local, o_loc = ch - owner * peer.outs_local;
-    T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(peer.parity) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
+    const uint32_t par = peer.parity % HB_INBOX_DEPTH;
+    T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(par) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
     for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) pd[k] = T(0);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0)
     {
         __threadfence_system();
-        atomicAdd_system(peer.count[owner] + peer.parity * peer.world + peer.rank, 1u);
+        atomicAdd_system(peer.count[owner] + par * peer.world + peer.rank, 1u);
     }
 }
 
@@ -1007,15 +1023,37 @@ __device__ __forceinline__ unsigned long long global_ns()
 
 // `timeout_ns`: how long the owner waits for a peer's blocks; a peer that is later than that (stopped, crashed) raises
 // *late (read by hb_conv_shard_status) and the hop is summed from what has arrived -- the device is never trapped.
+// blockIdx.y = hop j of a multi-hop batch: inbox slot parity + j, arrival count expected.e[j], block j of the caller's rows --
+// except the hop flagged as the last of the call, which stays behind in the staging row (as InvBatch for k_inv)
+struct GatherBatch
+{
+    uint32_t e[8];         // expected arrival count per hop
+    void *last_yout;
+    uint64_t last_ld;
+    int32_t last_j;
+    int32_t pad;
+};
+
 template <class T>
 __global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, const uint32_t *count, uint32_t world, uint32_t outs_local,
-                                                uint32_t parity, uint64_t slot, uint32_t expected, uint32_t B,
+                                                uint32_t parity, uint64_t slot, const GatherBatch gb, uint32_t B,
                                                 T *__restrict__ yout, size_t ld, size_t off, int add_result,
                                                 const T *__restrict__ carry_src, size_t carry_src_ld,
                                                 T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
                                                 unsigned long long *trace, uint32_t hop, unsigned long long timeout_ns, uint32_t *late)
 {
     const uint32_t o = blockIdx.x;
+    const uint32_t expected = gb.e[blockIdx.y];
+    parity = (parity + blockIdx.y) % HB_INBOX_DEPTH;
+    if (blockIdx.y)
+    {
+        off += size_t(blockIdx.y) * B;
+        carry_dst = nullptr;
+    }
+    if (gb.last_j >= 0 && blockIdx.y == (uint32_t) gb.last_j)
+    {
+        yout = reinterpret_cast<T *>(gb.last_yout); ld = gb.last_ld; off = 0; add_result = 0;
+    }
     trace_mark(trace, hop, 4, 0);
     if (carry_dst)
     {

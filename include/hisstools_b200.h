@@ -196,10 +196,12 @@ uint64_t hb_conv_bytes_per_hop(const hb_conv *c);
  * cluster transform the inputs, split the (input, partition) products and reduce through distributed shared memory
  * (hb_conv_fused.cuh).  overlapped = 0 / 1 never fuse.  Results differ by summation order only.  Takes effect with a reset. */
 int hb_conv_set_schedule(hb_conv *c, int overlapped);
-/* Overlapped schedule only: 1 (default) = every tail launch on one second stream, one after the other; 2 = the tails of
- * consecutive hops alternate between two streams, so the CTAs of the next tail are placed on the SMs one by one as the CTAs
- * of the running one leave (hides the ramp-up and drain of a launch: profiles/r2_tail_streams.txt).  Takes effect with a reset. */
+/* Overlapped schedule only: 1 = every tail launch on one second stream, one after the other; 2 = the tails of consecutive hops
+ * alternate between two streams, so the CTAs of the next tail are placed on the SMs as the CTAs of the running one leave (hides
+ * part of the ramp-up and drain of a launch: profiles/r2_tail_streams.txt); 0 (default) = automatic: 2 when a tail launch streams
+ * 3 GiB or less.  Takes effect with a reset.  hb_conv_tail_streams: the number in effect. */
 int hb_conv_set_tail_streams(hb_conv *c, int streams);
+int hb_conv_tail_streams(const hb_conv *c);
 /* schedule in effect after the last reset: 0 serial (also whenever only one partition is loaded), 1 overlapped, 2 fused */
 int hb_conv_schedule(const hb_conv *c);
 /* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in

@@ -774,3 +774,39 @@ def test_reset_of_one_pair_restarts_the_whole_matrix_documented_difference(hb):
     for o in range(n_out):
         fresh = sum(ck.direct_convolve_delayed(irs[o][i], xs[i][half:], B) for i in range(n_in))
         assert ck.rel_rms(ya[o], fresh) <= TOL32              # every pair restarted, also those of output 1
+
+
+@pytest.mark.parametrize("ins,outs,groups,B,L", [(1, 1, 1, 512, 4096), (8, 1, 1, 2048, 40000), (3, 2, 2, 128, 1000), (1, 1, 1, 1024, 65536)])
+def test_hop_batches_on_small_engines(hb, ins, outs, groups, B, L):
+    """Launch-latency-bound engines (BASELINE configs 1-3 and their like) take the hops of a multi-block call as one set of
+    launches -- forward FFTs of all hops, multiply-accumulate over hop x bin, inverse FFTs of all hops -- instead of one
+    launch sequence per hop: calls of 64, 5, 2 ... hops mixed with single blocks and ragged calls against the same engine
+    fed hop by hop (summation order only) and, for the first output, the reference / float64 direct convolution."""
+    from hisstools_library_b200.convolve import _Engine
+    irs = [[[ck.synth_ir(L, 2100 + 100 * g + 10 * o + i) for i in range(ins)] for o in range(outs)] for g in range(groups)]
+    calls = [64 * B, B, 5 * B, 100, B - 100, 2 * B, 70 * B, B, 3 * B + 17, B - 17, 9 * B]
+    n = sum(calls)
+    xs = np.stack([ck.synth_audio(n, 2100 + r) for r in range(groups * ins)])
+    res = {}
+    for batches in (True, False):
+        e = _Engine(np.float32, groups, ins, outs, 2 * B, L, 0, 0, 0)
+        e.set_multi_hop(batches)
+        e.set_reset_offset(0)
+        for g in range(groups):
+            for o in range(outs):
+                for i in range(ins):
+                    e.set_ir(g, i, o, irs[g][o][i], L)
+        y = np.zeros((groups * outs, n), np.float32)
+        pos = 0
+        for m in calls:
+            yo = [np.zeros(m, np.float32) for _ in range(groups * outs)]
+            e.process([np.ascontiguousarray(xs[r, pos:pos + m]) for r in range(groups * ins)], yo, m)
+            for r in range(groups * outs):
+                y[r, pos:pos + m] = yo[r]
+            pos += m
+        res[batches] = y
+        e.close()
+    for r in range(groups * outs):
+        assert ck.rel_rms(res[True][r], res[False][r]) <= 2e-6
+    truth = sum(ck.direct_convolve_delayed_fft(irs[0][0][i], xs[i], B) for i in range(ins))
+    assert ck.rel_rms(res[True][0], truth) <= TOL32

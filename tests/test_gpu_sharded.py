@@ -115,16 +115,25 @@ def _c4_worker(rank, world, port, out_dir):
     pool = bench.input_pool(gen, rank, plan.local_ins, C4_B, 4, torch.float32, dev)
     stream = torch.cuda.Stream(device=dev)
     keep = [0, plan.local_outs - 1]
-    got = torch.zeros(2, hops * C4_B, device=dev)
-    yb = torch.zeros(plan.local_outs, C4_B, device=dev)
-    with torch.cuda.stream(stream):
-        for k in range(hops):
-            assert cv.process_device(pool[k % 4], yb, C4_B, stream.cuda_stream)
-            for q, r in enumerate(keep):
-                got[q, k * C4_B:(k + 1) * C4_B].copy_(yb[r], non_blocking=True)
-    torch.cuda.synchronize()
-    assert eng.shard_status() == 0
-    np.save(os.path.join(out_dir, "c4_rank%d.npy" % rank), got.cpu().numpy())
+    xs = torch.cat([pool[k % 4] for k in range(hops)], dim=1).contiguous()
+    # one block per call (the timed path), then calls of several blocks: multi-hop batches on the sharded engine (one pass of
+    # this rank's IR spectra for up to 8 hops, one inverse launch and one owner-side sum for the whole batch)
+    for tag, calls in (("", [1]), ("_b8", [8]), ("_mixed", [4, 1, 2, 8, 3])):
+        cv.reset()
+        got = torch.zeros(2, hops * C4_B, device=dev)
+        with torch.cuda.stream(stream):
+            pos, k = 0, 0
+            while pos < hops * C4_B:
+                m = min(calls[k % len(calls)] * C4_B, hops * C4_B - pos)
+                yb = torch.zeros(plan.local_outs, m, device=dev)
+                assert cv.process_device(xs[:, pos:pos + m].contiguous(), yb, m, stream.cuda_stream)
+                for q, r in enumerate(keep):
+                    got[q, pos:pos + m].copy_(yb[r], non_blocking=True)
+                pos += m
+                k += 1
+        torch.cuda.synchronize()
+        assert eng.shard_status() == 0
+        np.save(os.path.join(out_dir, "c4%s_rank%d.npy" % (tag, rank)), got.cpu().numpy())
     dist.barrier()
     cv.close()
     dist.destroy_process_group()
@@ -155,10 +164,11 @@ def test_multi_gpu_config4_full_size_against_reference(tmp_path, world):
         pool = bench.input_pool(gen, r, l_ins, C4_B, 4, torch.float32, dev)
         xs.append(torch.cat([pool[k % 4] for k in range(hops)], dim=1).cpu().numpy())
     want = ck.ref_matrix_run(irs, np.concatenate(xs, axis=0), 2 * C4_B)
-    first, last = np.load(tmp_path / "c4_rank0.npy"), np.load(tmp_path / ("c4_rank%d.npy" % (world - 1)))
-    for q, got in enumerate([first[0], first[1], last[0], last[1]]):
-        assert ck.rel_rms(got, want[q]) <= 1e-5, (q, ck.rel_rms(got, want[q]))
-        assert ck.rel_rms(got[-16 * C4_B:], want[q][-16 * C4_B:]) <= 1e-5
+    for tag in ("", "_b8", "_mixed"):
+        first, last = np.load(tmp_path / ("c4%s_rank0.npy" % tag)), np.load(tmp_path / ("c4%s_rank%d.npy" % (tag, world - 1)))
+        for q, got in enumerate([first[0], first[1], last[0], last[1]]):
+            assert ck.rel_rms(got, want[q]) <= 1e-5, (tag, q, ck.rel_rms(got, want[q]))
+            assert ck.rel_rms(got[-16 * C4_B:], want[q][-16 * C4_B:]) <= 1e-5
 
 
 # ---- a rank with nothing loaded must not stall or trap its peers -------------------------------------------------------
