@@ -16,8 +16,13 @@
 #include "hb_conv_mh.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace hb;
@@ -1647,12 +1652,95 @@ extern "C" int hb_conv_process_dev(hb_conv *c, const void *d_in, uintptr_t in_ld
 
 namespace
 {
+// Row copies between the caller's arrays and the pinned staging buffers are the host cost of a large call (config 5: 1 MiB each
+// way per 90 us hop -- a single thread's memcpy alone takes longer than the hop).  Calls that move 256 KiB or more share their rows
+// out to a few helper threads (started on first use, spinning briefly between calls of a streaming caller, asleep otherwise).
+class RowCopyPool
+{
+public:
+    static RowCopyPool &get() { static RowCopyPool p; return p; }
+    // fn(r) for r in [0, rows), rows dealt to the helpers and the caller
+    void run(size_t rows, size_t bytes, const std::function<void(size_t)> &fn)
+    {
+        if (bytes < (size_t(256) << 10) || rows < 2 || !helpers_) { for (size_t r = 0; r < rows; r++) fn(r); return; }
+        std::lock_guard<std::mutex> one(call_);                      // one call at a time owns the helpers
+        fn_ = &fn;
+        rows_ = rows;
+        next_.store(0, std::memory_order_relaxed);
+        pending_.store(helpers_, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> l(m_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        work();
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_pause();
+    }
+    ~RowCopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            quit_.store(true, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (std::thread &t : threads_) t.join();
+    }
+
+private:
+    RowCopyPool()
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        helpers_ = hw >= 8 ? 3 : (hw >= 4 ? 1 : 0);
+        for (unsigned k = 0; k < helpers_; k++) threads_.emplace_back([this]() { loop(); });
+    }
+    static void cpu_pause()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void work()
+    {
+        for (size_t r; (r = next_.fetch_add(1, std::memory_order_relaxed)) < rows_;) (*fn_)(r);
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            uint32_t spins = 0;
+            while (gen_.load(std::memory_order_acquire) == seen && !quit_.load(std::memory_order_acquire))
+            {
+                if (++spins < 20000) { cpu_pause(); continue; }
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait_for(l, std::chrono::milliseconds(20), [&]() { return gen_.load(std::memory_order_acquire) != seen || quit_.load(std::memory_order_acquire); });
+            }
+            if (quit_.load(std::memory_order_acquire)) return;
+            seen = gen_.load(std::memory_order_acquire);
+            work();
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    unsigned helpers_ = 0;
+    std::vector<std::thread> threads_;
+    std::mutex m_, call_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<unsigned> pending_{0};
+    std::atomic<size_t> next_{0};
+    std::atomic<bool> quit_{false};
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t rows_ = 0;
+};
+
 void scatter_rows(hb_conv *c, void *const *outs, const char *src, size_t src_ld, size_t src_off, size_t n, int accumulate)
 {
     const size_t es = c->esize(), rows_out = host_rows_out(c);
-    for (size_t r = 0; r < rows_out; r++)
+    RowCopyPool::get().run(rows_out, rows_out * n * es, [&](size_t r)
     {
-        if (!outs[r]) continue;
+        if (!outs[r]) return;
         const char *sp = src + (r * src_ld + src_off) * es;
         if (!accumulate) memcpy(outs[r], sp, n * es);
         else if (c->dtype == HB_F64)
@@ -1667,18 +1755,18 @@ void scatter_rows(hb_conv *c, void *const *outs, const char *src, size_t src_ld,
             const float *q = (const float *) sp;
             for (size_t k = 0; k < n; k++) d[k] += q[k];
         }
-    }
+    });
 }
 
 void gather_rows(hb_conv *c, const void *const *ins, char *dst, size_t n)
 {
     const size_t es = c->esize(), rows_in = host_rows_in(c);
-    for (size_t r = 0; r < rows_in; r++)
+    RowCopyPool::get().run(rows_in, rows_in * n * es, [&](size_t r)
     {
         // a null input row is an inactive channel: silence (NToMonoConvolve.cpp:41 stops at activeInChans)
         if (ins[r]) memcpy(dst + r * n * es, ins[r], n * es);
         else memset(dst + r * n * es, 0, n * es);
-    }
+    });
 }
 
 // Deferred host call, possible when every output sample of this call lies in the block finished by an

@@ -51,6 +51,9 @@ def traffic(src, key):
     except Exception:
         d = {}
     d[key] = sum(tot) / len(tot)
+    # provenance: which capture the figure came from and when it was condensed (bench.py prints it as roofline.traffic_source)
+    import datetime
+    d.setdefault("_source", {})[key] = "%s (ncu --set full, %d launch(es); condensed %s)" % (os.path.basename(src), len(tot), datetime.date.today().isoformat())
     json.dump(d, open(path, "w"), indent=1, sort_keys=True)
     print(key, d[key])
 
