@@ -258,10 +258,15 @@ void plan_geometry(hb_conv *c)
         // spectra one output's cluster reads per hop: its IR partitions and the delay line of every input
         const uint64_t per_output = uint64_t(g.ins) * (g.P - 1) * g.B * 4 * c->esize();
         uint32_t cs = 1;
-        while (cs < 8 && per_output / cs > (uint64_t(96) << 10)) cs <<= 1;
-        // measured (profiles/r1_small_hops.txt): config 1 15 us against 21, config 2 21 us against 27; an 8 -> 1 engine with
-        // 2 MiB per rank is slower fused (42 us) than overlapped (36 us)
-        if (per_output / cs <= (uint64_t(256) << 10)) { c->fused = true; c->fused_cs = cs; }
+        static const char *env_cs = getenv("HB_FUSED_MAX_CS"), *env_kb = getenv("HB_FUSED_MAX_KB");      // experiments only
+        const uint32_t cs_max = env_cs && atoi(env_cs) >= 1 ? (uint32_t) atoi(env_cs) : 16u;
+        const uint64_t per_rank_max = (env_kb && atoi(env_kb) > 0 ? (uint64_t) atoi(env_kb) : 1152u) << 10;
+        while (cs < cs_max && per_output / cs > (uint64_t(96) << 10)) cs <<= 1;
+        // measured: config 1 15 us per hop against 21 for the three-kernel hop, config 2 21 against 27 (profiles/r1_small_hops.txt).  With
+        // programmatic dependent launch (hb_conv_fused.cuh) all partitions >= 2 are multiplied beside the previous hop, so a rank may
+        // read much more: config 3 (8 -> 1, 16 MiB of spectra per hop) on a cluster of 16 with 1 MiB per rank runs 21.8 us per hop against
+        // 34.8 overlapped (and 41 us on a cluster of 8 with 2 MiB per rank); profiles/r2_small_hops.txt
+        if (per_output / cs <= per_rank_max) { c->fused = true; c->fused_cs = cs; }
     }
     c->split = !c->fused && g.P >= 2 && (c->schedule == 1 || ((c->schedule == 2 || c->schedule == 3) && tail_bytes >= (uint64_t(4) << 20)));
     // Short tail launches lose a visible share of the hop to their ramp-up and drain (about 10 us per launch): with two tail streams
@@ -692,18 +697,23 @@ int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, siz
     }
     FusedArgs fa;
     fa.cs = cs;
-    fa.tail_items = g.ins * (g.P - 1);
+    fa.tail_items = g.P > 2 ? g.ins * (g.P - 2) : 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(g.groups * g.outs * cs);
     cfg.blockDim = dim3(std::max<uint32_t>(std::min<uint32_t>(B / EPT, 512u), 128u));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    // programmatic dependent launch: this hop may start beside the previous kernel of the stream and runs what does not depend on
+    // it (twiddles, newest block, partitions >= 2) until griddepcontrol.wait (hb_conv_fused.cuh); HB_NO_PDL: experiments only
+    static const char *env_pdl = getenv("HB_NO_PDL");
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = (env_pdl && atoi(env_pdl)) ? 0 : 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     HB_CUDA(cudaLaunchKernelEx(&cfg, kernel, g, fa, prev, prev_ld, newest, new_ld, save, save_ld, (const Cx<T> *) c->d_H, (Cx<T> *) c->d_X,
                                (const T *) c->d_Hnyq, (T *) c->d_Xnyq, io.yout, io.ld, io.off, io.add_result,
                                io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry, (const Cx<T> *) c->d_tw, c->tw_log2));

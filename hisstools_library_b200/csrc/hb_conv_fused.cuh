@@ -13,6 +13,17 @@
 //               (distributed shared memory), then inverse split, inverse FFT, scale 1/(4N), first B samples out.
 // Layouts are the engine's own (hb_conv_kernels.cuh) with OT = 1 and one bin tile, so IR loading and the other
 // schedules are unchanged.
+//
+// Programmatic dependent launch (round 2).  Back-to-back hops of a stream are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and the kernel is ordered in two phases around griddepcontrol.wait:
+//   before the wait  what does not depend on the previous hop: twiddles into shared memory, the newest input block into
+//                    registers, and the products of partitions p >= 2 -- they meet spectra that are at least two hops old,
+//                    written by kernels that had completed before this one could start (a kernel releases its successor only
+//                    after its own wait has returned);
+//   after the wait   the previous block (saved by the previous hop), the forward FFT, partitions 0 and 1 (p = 1 meets the
+//                    spectrum the previous hop wrote), the reduction, the inverse FFT and the store.
+// So the launch latency of hop t+1 and most of its L2 round trips run beside the critical part of hop t.  Without the launch
+// attribute (or with anything else between two hops in the stream) the wait returns at once and the kernel is what it was.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -26,7 +37,7 @@ namespace cg = cooperative_groups;
 struct FusedArgs
 {
     uint32_t cs;               // cluster size
-    uint32_t tail_items;       // ins * (P - 1)
+    uint32_t tail_items;       // ins * (P - 2): the products of partitions p >= 2 (p = 1 waits for the previous hop)
 };
 
 template <class T, int EPT>
@@ -64,6 +75,65 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     const Cx<T> *twl = stw;
     const int twl_log2 = (int) g.log2n;
 
+    Cx<T> acc[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) acc[e] = cx<T>(T(0), T(0));
+    T nyq = T(0);
+
+    // ================= before the wait: nothing here depends on the previous hop =================
+    // the newest block of the first input this rank transforms (the caller's rows are complete before the launch)
+    // (float only: the double instance has no registers to carry values across the transform -- 128 at 512 threads)
+    constexpr bool EARLY = sizeof(T) == 4;
+    T na[EARLY ? EPT : 1], nbv[EARLY ? EPT : 1];
+    if (EARLY && rank < g.ins)
+    {
+        const T *pn = newest + size_t(grp * g.ins + rank) * new_ld;
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+        {
+            const uint32_t k = tid + e * nthr, j = 2 * k;
+            if (k < B && j < B) { na[e] = pn[j]; nbv[e] = pn[j + 1]; }
+        }
+    }
+    trace_mark(g, 1, 0);
+    // this rank's share of the (input, partition >= 2) products: spectra that are at least two hops old
+    if (P > 2)
+    {
+        const uint32_t q0 = (uint32_t) ((uint64_t(rank) * fa.tail_items) / cs), q1 = (uint32_t) ((uint64_t(rank + 1) * fa.tail_items) / cs);
+        const uint32_t pm2 = P - 2;
+        for (uint32_t q = q0; q < q1; q++)
+        {
+            const uint32_t in = q / pm2, p = 2 + (q - in * pm2);
+            const uint32_t ch = grp * g.ins + in;
+            uint32_t sl = g.slot + p;
+            if (sl >= R) sl -= R;
+            const Cx<T> *hp = H + (((size_t(tile) * g.ins + in) * g.Pcap + p) * g.OT + row) * B;
+            const Cx<T> *xp = X + (size_t(ch) * R + sl) * B;
+            Cx<T> hv[EPT], xv[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B) { hv[e] = hp[k]; xv[e] = xp[k]; }
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B)
+                {
+                    acc[e].x = fma(xv[e].x, hv[e].x, acc[e].x); acc[e].x = fma(-xv[e].y, hv[e].y, acc[e].x);
+                    acc[e].y = fma(xv[e].x, hv[e].y, acc[e].y); acc[e].y = fma(xv[e].y, hv[e].x, acc[e].y);
+                }
+            }
+            if (tid == 0) nyq += Xnyq[size_t(ch) * R + sl] * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
+        }
+    }
+
+    // ================= the previous hop must be complete from here on; release the next one =================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (rank == 0 && carry_dst)
     {
         // hand the block computed by the previous hop to the caller (the output-ring read of PartitionedConvolve.cpp:307)
@@ -72,17 +142,29 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
         for (uint32_t k = tid; k < B; k += nthr) cd[k] = add_carry ? cd[k] + cs_[k] : cs_[k];
     }
 
-    Cx<T> acc[EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; e++) acc[e] = cx<T>(T(0), T(0));
-    T nyq = T(0);
-
-    // ---- inputs this rank transforms: forward FFT, newest FDL slot, partition 0 ----
+    // ---- inputs this rank transforms: forward FFT, newest FDL slot, partitions 0 and 1 ----
     for (uint32_t in = rank; in < g.ins; in += cs)
     {
         const uint32_t ch = grp * g.ins + in;
         const T *pn = newest + size_t(ch) * new_ld, *pp = prev + size_t(ch) * prev_ld;
         T *ps = (save && writer) ? save + size_t(ch) * save_ld : nullptr;
+        // partition 1 meets the spectrum the previous hop wrote: fetched now, used after the transform
+        Cx<T> x1[EPT], h1[EPT];
+        T xn1 = T(0), hn1 = T(0);
+        uint32_t sl1 = g.slot + 1;
+        if (sl1 >= R) sl1 -= R;
+        const Cx<T> *hp1 = H + (((size_t(tile) * g.ins + in) * g.Pcap + 1) * g.OT + row) * B;
+        const Cx<T> *xp1 = X + (size_t(ch) * R + sl1) * B;
+        if (EARLY && P > 1)
+        {
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B) { h1[e] = hp1[k]; x1[e] = xp1[k]; }
+            }
+        }
+        if (P > 1 && tid == 0) { xn1 = Xnyq[size_t(ch) * R + sl1]; hn1 = Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + 1]; }
         __syncthreads();                                        // s is free (previous input's spectrum consumed)
 #pragma unroll
         for (int e = 0; e < EPT; e++)
@@ -93,7 +175,8 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 T a, b;
                 if (j < B)
                 {
-                    a = pn[j]; b = pn[j + 1];
+                    if (EARLY && in == rank) { a = na[EARLY ? e : 0]; b = nbv[EARLY ? e : 0]; }      // loaded before the wait
+                    else { a = pn[j]; b = pn[j + 1]; }
                     if (ps) { ps[j] = a; ps[j + 1] = b; }
                 }
                 else { a = pp[j - B]; b = pp[j - B + 1]; }
@@ -128,27 +211,16 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 acc[e].y = fma(z.x, h.y, acc[e].y); acc[e].y = fma(z.y, h.x, acc[e].y);
             }
         }
-    }
-
-    trace_mark(g, 1, 0);                                        // phase stamps (trace only): forward part done
-    // ---- this rank's share of the (input, partition >= 1) products: spectra already in the delay line ----
-    {
-        const uint32_t q0 = (uint32_t) ((uint64_t(rank) * fa.tail_items) / cs), q1 = (uint32_t) ((uint64_t(rank + 1) * fa.tail_items) / cs);
-        const uint32_t pm1 = P - 1;
-        for (uint32_t q = q0; q < q1; q++)
+        if (P > 1)
         {
-            const uint32_t in = q / pm1, p = 1 + (q - in * pm1);
-            const uint32_t ch = grp * g.ins + in;
-            uint32_t sl = g.slot + p;
-            if (sl >= R) sl -= R;
-            const Cx<T> *hp = H + (((size_t(tile) * g.ins + in) * g.Pcap + p) * g.OT + row) * B;
-            const Cx<T> *xp = X + (size_t(ch) * R + sl) * B;
-            Cx<T> hv[EPT], xv[EPT];
-#pragma unroll
-            for (int e = 0; e < EPT; e++)
+            if (!EARLY)
             {
-                const uint32_t k = tid + e * nthr;
-                if (k < B) { hv[e] = hp[k]; xv[e] = xp[k]; }
+#pragma unroll
+                for (int e = 0; e < EPT; e++)
+                {
+                    const uint32_t k = tid + e * nthr;
+                    if (k < B) { h1[e] = hp1[k]; x1[e] = xp1[k]; }
+                }
             }
 #pragma unroll
             for (int e = 0; e < EPT; e++)
@@ -156,11 +228,11 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 const uint32_t k = tid + e * nthr;
                 if (k < B)
                 {
-                    acc[e].x = fma(xv[e].x, hv[e].x, acc[e].x); acc[e].x = fma(-xv[e].y, hv[e].y, acc[e].x);
-                    acc[e].y = fma(xv[e].x, hv[e].y, acc[e].y); acc[e].y = fma(xv[e].y, hv[e].x, acc[e].y);
+                    acc[e].x = fma(x1[e].x, h1[e].x, acc[e].x); acc[e].x = fma(-x1[e].y, h1[e].y, acc[e].x);
+                    acc[e].y = fma(x1[e].x, h1[e].y, acc[e].y); acc[e].y = fma(x1[e].y, h1[e].x, acc[e].y);
                 }
             }
-            if (tid == 0) nyq += Xnyq[size_t(ch) * R + sl] * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
+            if (tid == 0) nyq += xn1 * hn1;
         }
     }
 

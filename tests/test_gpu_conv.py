@@ -123,14 +123,15 @@ def test_schedules_agree_and_survive_mid_stream_changes(hb, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("ins,outs,groups,B,L,fused", [(1, 1, 1, 512, 4096, True), (1, 1, 1, 1024, 65536, True), (8, 1, 1, 2048, 30000, False),
+@pytest.mark.parametrize("ins,outs,groups,B,L,fused", [(1, 1, 1, 512, 4096, True), (1, 1, 1, 1024, 65536, True), (8, 1, 1, 2048, 30000, True),
+                                                       (8, 1, 1, 2048, 131072, True), (8, 1, 1, 2048, 400000, False),
                                                        (3, 1, 2, 256, 5000, True), (1, 1, 3, 16, 100, True), (5, 1, 1, 64, 64, True),
                                                        (2, 2, 1, 512, 3000, True), (3, 5, 1, 256, 2000, True), (2, 8, 2, 128, 1000, True)])
 def test_fused_hop_against_serial_and_truth(hb, dtype, ins, outs, groups, B, L, fused):
     """The fused single-launch hop (one thread-block cluster per output: hb_conv_fused.cuh) on small engines -- BASELINE
-    configs 1 and 2, several groups, tiny and one-partition sizes, stereo and wider matrices (every output's cluster
-    transforms the inputs for itself) -- against the serial three-kernel hop (summation order only) and float64 direct
-    convolution, ragged calls included; an 8 -> 1 engine with 3.7 MB of spectra per output is not eligible."""
+    configs 1, 2 and 3 (the last on a cluster of 16), several groups, tiny and one-partition sizes, stereo and wider matrices
+    (every output's cluster transforms the inputs for itself) -- against the serial three-kernel hop (summation order only) and
+    float64 direct convolution, ragged calls included; an 8 -> 1 engine with 51 MB of spectra per output is not eligible."""
     from hisstools_library_b200.convolve import _Engine
     if dtype == np.float64 and B > 2048:
         pytest.skip("spectrum above one bin tile")

@@ -205,3 +205,34 @@ def test_against_compiled_reference(hb):
             got = np.zeros(7000, dt)
             assert sp.convolve(got, a, b, mode) == size
             assert ck.rel_rms(got[:size], want[:size]) <= TOL[suf]
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_kernel_smoother_shaped_caller(hb, suf):
+    """The one-shot path as its caller in the reference uses it: kernel_smoother::apply_filter_fft (KernelSmoother.hpp:317-326)
+    convolves n + width - 1 data samples with a filter of `width` taps in Linear mode and keeps outputs [width - 1, width - 1 + n)
+    times a gain.  Same sizes and slicing here, against the compiled reference's spectral_processor where shipped, the oracle and
+    the direct form the smoother's time-domain branch computes (apply_filter :288-301)."""
+    dt = DT[suf]
+    rng = np.random.default_rng(31)
+    sp = hb.spectral_processor(MAXFFT[suf], dt)
+    lib = ck.oracle()
+    fn = getattr(lib, "orc_spectral_convolve_" + suf)
+    rs = ck.ref_spectral()
+    for n, width, gain in [(512, 33, 0.25), (2048, 257, 1.0 / 257), (4000, 1001, 0.003), (16, 5, 2.0)]:
+        data = rng.uniform(-1, 1, n + width - 1).astype(dt)
+        filt = np.hanning(width + 2)[1:-1].astype(dt)
+        full = np.zeros(n + 2 * width, dt)
+        size = sp.convolve(full, data, filt, hb.EdgeMode.Linear)
+        assert size == n + 2 * width - 2
+        out = full[width - 1:width - 1 + n] * dt(gain)
+        want = np.zeros(n + 2 * width, dt)
+        assert fn(ck.fptr(want), ck.fptr(data), len(data), ck.fptr(filt), width, 0, MAXFFT[suf]) == size
+        assert ck.rel_rms(out, want[width - 1:width - 1 + n] * dt(gain)) <= TOL[suf]
+        if rs is not None:
+            refo = np.zeros(n + 2 * width, dt)
+            assert getattr(rs, "ref_spectral_convolve_" + suf)(ck.fptr(refo), ck.fptr(data), len(data), ck.fptr(filt), width, 0, MAXFFT[suf]) == size
+            assert ck.rel_rms(out, refo[width - 1:width - 1 + n] * dt(gain)) <= TOL[suf]
+        # the time-domain branch of the smoother: out[i] = gain * sum_j filter[j] * data[i + width - 1 - j]
+        direct = np.array([np.dot(filt.astype(np.float64), data[i:i + width][::-1].astype(np.float64)) for i in range(min(n, 64))]) * gain
+        assert ck.rel_rms(out[:len(direct)], direct) <= TOL[suf] * 10
