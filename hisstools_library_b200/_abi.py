@@ -39,6 +39,8 @@ SIGNATURES = {
     "hb_conv_set_offset": (C.c_int, [V, UP]),
     "hb_conv_set_reset_offset": (C.c_int, [V, IP]),
     "hb_conv_set_ir": (C.c_int, [V, U32, U32, U32, V, C.c_int, UP]),
+    "hb_conv_set_ir_live": (C.c_int, [V, U32, U32, U32, V, C.c_int, UP]),
+    "hb_conv_reset_pair": (C.c_int, [V, U32, U32, U32]),
     "hb_conv_set_ir_dev": (C.c_int, [V, U32, U32, U32, V, UP]),
     "hb_conv_resize": (C.c_int, [V, UP]),
     "hb_conv_reset": (C.c_int, [V]),
@@ -68,6 +70,7 @@ SIGNATURES = {
     "hb_matrix_resize": (C.c_int, [V, U32, U32, U32, UP]),
     "hb_matrix_set": (C.c_int, [V, U32, U32, U32, V, C.c_int, UP, C.c_int]),
     "hb_matrix_reset": (C.c_int, [V]),
+    "hb_matrix_reset_pair": (C.c_int, [V, U32, U32, U32]),
     "hb_matrix_process": (C.c_int, [V, C.POINTER(V), C.POINTER(V), UP, C.c_int]),
     "hb_matrix_process_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
     "hb_matrix_parts": (U32, [V]),

@@ -85,6 +85,19 @@ class _Engine:
             raise ValueError("length exceeds the impulse response array")
         return _abi.check(_abi.lib().hb_conv_set_ir(self._h, group, i, o, ir.ctypes.data_as(C.c_void_p), _hb_dtype(ir.dtype), n))
 
+    def set_ir_live(self, group, i, o, ir, length=None):
+        """set_ir on a running engine that restarts this pair only (hb_conv_set_ir_live)"""
+        if ir is None or (length is not None and length == 0):
+            return _abi.check(_abi.lib().hb_conv_set_ir_live(self._h, group, i, o, None, _abi.HB_F32, 0))
+        ir = np.ascontiguousarray(ir)
+        if ir.dtype not in (np.float32, np.float64):
+            ir = ir.astype(self.dtype)
+        n = ir.size if length is None else int(length)
+        return _abi.check(_abi.lib().hb_conv_set_ir_live(self._h, group, i, o, ir.ctypes.data_as(C.c_void_p), _hb_dtype(ir.dtype), n))
+
+    def reset_pair(self, group, i, o):
+        return _abi.check(_abi.lib().hb_conv_reset_pair(self._h, group, i, o))
+
     def set_ir_device(self, group, i, o, data_ptr, length):
         return _abi.check(_abi.lib().hb_conv_set_ir_dev(self._h, group, i, o, C.c_void_p(data_ptr), int(length)))
 
@@ -374,6 +387,10 @@ class _Matrix:
         _abi.check(_abi.lib().hb_matrix_reset(self._h))
         return _ERR.CONVOLVE_ERR_NONE
 
+    def reset_pair(self, g, i, o):
+        """Convolver::reset(inChan, outChan) (Convolver.cpp:88-97): that pair restarts from silence, the others keep running"""
+        return _ERR(_abi.check(_abi.lib().hb_matrix_reset_pair(self._h, g, i, o)))
+
     def process(self, in_rows, out_rows, n, accumulate):
         """Sum of all parts into out_rows (None rows: silent input / unwanted output); True when written."""
         ip = (C.c_void_p * len(in_rows))(*[None if r is None else r.ctypes.data for r in in_rows])
@@ -472,9 +489,11 @@ class NToMonoConvolve:
         return self._m.set(0, inChan, 0, input, impulse_length, resize)
 
     def reset(self, inChan=None):
-        if inChan is not None and not self._chan(inChan):
+        if inChan is None:
+            return self._m.reset()
+        if not self._chan(inChan):
             return _ERR.CONVOLVE_ERR_IN_CHAN_OUT_OF_RANGE
-        return self._m.reset()
+        return self._m.reset_pair(0, inChan, 0)             # that input's convolver only (NToMonoConvolve.cpp:28-33)
 
     def setResetOffset(self, offset=-1):
         self._m.setResetOffset(offset)
@@ -550,10 +569,10 @@ class Convolver:
         if inChan is None:
             self._m.reset()
             return None
-        _, err = self._pair(inChan, outChan)
+        pair, err = self._pair(inChan, outChan)
         if err:
             return err
-        return self._m.reset()
+        return self._m.reset_pair(pair[0], pair[1], pair[2])
 
     def resize(self, inChan, outChan, length):
         pair, err = self._pair(inChan, outChan)

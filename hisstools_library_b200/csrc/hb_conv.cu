@@ -165,6 +165,18 @@ struct hb_conv
     double prof_ms[5] = {0, 0, 0, 0, 0};  // forward, whole/head multiply-accumulate, wait for tail, inverse, tail
     uint64_t prof_hops = 0;
 
+    // pairs restarted while the stream runs (hb_conv_set_ir_live / hb_conv_reset_pair): their spectra wait in a private buffer and
+    // are copied into the IR array one partition per hop (k_pair_copy)
+    struct Reveal
+    {
+        uint32_t grp, in, out;
+        uint32_t np;                // partitions of the pair
+        uint32_t shown;             // partitions already in place
+        uint32_t age;               // hops processed since the restart
+        void *side;                 // [np][B] bins in natural order, then np Nyquist values
+    };
+    std::vector<Reveal> reveals;
+
     size_t esize() const { return dtype_size(dtype); }
     size_t pairs() const { return size_t(groups) * ins * outs; }
 };
@@ -350,6 +362,8 @@ size_t h_vectors(const hb_conv *c)
 
 void free_device(hb_conv *c)
 {
+    for (hb_conv::Reveal &r : c->reveals) cudaFree(r.side);
+    c->reveals.clear();
     cudaFree(c->d_H); cudaFree(c->d_X); cudaFree(c->d_Hnyq); cudaFree(c->d_Xnyq); cudaFree(c->d_tw);
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = c->d_tw = nullptr;
     c->d_S.release();
@@ -394,6 +408,8 @@ size_t nyq_capacity(const hb_conv *c)
 // allocate everything whose size depends on max_length (ctor and resize)
 int alloc_capacity(hb_conv *c)
 {
+    for (hb_conv::Reveal &r : c->reveals) cudaFree(r.side);     // (resize puts them in place first)
+    c->reveals.clear();
     cudaFree(c->d_H); cudaFree(c->d_X); cudaFree(c->d_Hnyq); cudaFree(c->d_Xnyq);
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = nullptr;
     const size_t hbytes = h_vectors(c) * 16;
@@ -722,14 +738,15 @@ int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, siz
 }
 
 template <class T, int EPT>
-int launch_ir_ept(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
+int launch_ir_ept(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st, void *side)
 {
     const Geom &g = c->g;
     const uint32_t log2m = g.log2n - 1;
     const size_t smem = fft_smem<T>(log2m);
     int rc = allow_smem(k_ir<T, EPT>, smem);
     if (rc) return rc;
-    k_ir<T, EPT><<<nwrite, fft_threads(log2m, EPT), smem, st>>>(g, d_ir, taps, grp, in, o, (Cx<T> *) c->d_H, (T *) c->d_Hnyq, (const Cx<T> *) c->d_tw, c->tw_log2);
+    k_ir<T, EPT><<<nwrite, fft_threads(log2m, EPT), smem, st>>>(g, d_ir, taps, grp, in, o, (Cx<T> *) c->d_H, (T *) c->d_Hnyq, (const Cx<T> *) c->d_tw, c->tw_log2,
+                                                                (Cx<T> *) side, nwrite);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
@@ -772,12 +789,72 @@ int launch_ir_big(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t
     return HB_OK;
 }
 
+// side != nullptr (single-CTA transform sizes only): the spectra of the nwrite partitions go to that private buffer (k_ir)
 template <class T>
-int launch_ir(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st)
+int launch_ir(hb_conv *c, const T *d_ir, size_t taps, uint32_t grp, uint32_t in, uint32_t o, uint32_t nwrite, cudaStream_t st, void *side = nullptr)
 {
     if (!nwrite) return HB_OK;
     if (is_big<T>(c)) return launch_ir_big<T>(c, d_ir, taps, grp, in, o, nwrite, st);
-    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_ir_ept<T, EPT>(c, d_ir, taps, grp, in, o, nwrite, st));
+    HB_EPT_DISPATCH(c->g.log2n - 1, return launch_ir_ept<T, EPT>(c, d_ir, taps, grp, in, o, nwrite, st, side));
+}
+
+// ---- pairs restarted while the stream runs ----------------------------------------------------------
+template <class T>
+int pair_copy(hb_conv *c, const hb_conv::Reveal &r, uint32_t p0, uint32_t count, int mode, cudaStream_t st)
+{
+    if (!count) return HB_OK;
+    k_pair_copy<T><<<count, 256, 0, st>>>(c->g, (Cx<T> *) r.side, r.np, r.grp, r.in, r.out, p0, (Cx<T> *) c->d_H, (T *) c->d_Hnyq, mode);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+// before the multiply-accumulate of a hop: every restarted pair gets the partition whose frame is the first one recorded after
+// its restart (partition p at age p), so that it never meets input from before the restart
+template <class T>
+int advance_reveals(hb_conv *c, cudaStream_t st)
+{
+    for (size_t k = 0; k < c->reveals.size();)
+    {
+        hb_conv::Reveal &r = c->reveals[k];
+        const uint32_t want = std::min(r.np, r.age + 1);
+        int rc = pair_copy<T>(c, r, r.shown, want - r.shown, 0, st);
+        if (rc) return rc;
+        r.shown = want;
+        r.age++;
+        if (r.shown == r.np)
+        {
+            // the buffer may still be read by the copy just enqueued: freed behind the stream
+            HB_CUDA(cudaFreeAsync(r.side, st));
+            c->reveals.erase(c->reveals.begin() + k);
+        }
+        else k++;
+    }
+    return HB_OK;
+}
+
+// everything in place at once (whole-engine reset, resize): after a reset the history is silence anyway
+template <class T>
+int finish_reveals(hb_conv *c, cudaStream_t st)
+{
+    for (hb_conv::Reveal &r : c->reveals)
+    {
+        int rc = pair_copy<T>(c, r, r.shown, r.np - r.shown, 0, st);
+        if (rc) return rc;
+        HB_CUDA(cudaFreeAsync(r.side, st));
+    }
+    c->reveals.clear();
+    return HB_OK;
+}
+
+void drop_reveal(hb_conv *c, uint32_t grp, uint32_t in, uint32_t o)
+{
+    for (size_t k = 0; k < c->reveals.size(); k++)
+        if (c->reveals[k].grp == grp && c->reveals[k].in == in && c->reveals[k].out == o)
+        {
+            cudaFree(c->reveals[k].side);
+            c->reveals.erase(c->reveals.begin() + k);
+            return;
+        }
 }
 
 template <class T>
@@ -814,6 +891,8 @@ int apply_fft_size(hb_conv *c, uintptr_t fft_size)
         HB_CUDA(cudaMemsetAsync(c->d_Hnyq, 0, std::max<size_t>(c->pairs() * nyq_capacity(c) * c->esize(), 16), c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
         c->tail_valid = false;
+        for (hb_conv::Reveal &r : c->reveals) cudaFree(r.side);
+        c->reveals.clear();
         std::fill(c->nparts.begin(), c->nparts.end(), 0u);
         c->P = 0;
         c->fft_log2 = l2;
@@ -895,6 +974,7 @@ int do_reset(hb_conv *c, cudaStream_t st)
         for (int k = 0; k < 2; k++)
             if (!c->ev_tail[k]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[k], cudaEventDisableTiming));
     }
+    if ((rc = finish_reveals<T>(c, st))) return rc;
     // FDL silence: stale slots are masked in the reference by mValidPartitions (:285,373); zeros do the same
     HB_CUDA(cudaMemsetAsync(c->d_X, 0, size_t(g.groups) * g.ins * g.R * g.B * 2 * sizeof(T), st));
     HB_CUDA(cudaMemsetAsync(c->d_Xnyq, 0, size_t(g.groups) * g.ins * g.R * sizeof(T), st));
@@ -1009,6 +1089,10 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     c->g.slot = c->g.slot ? c->g.slot - 1 : c->g.R - 1;
     c->g.hop++;
     c->g.trace = (unsigned long long *) c->d_trace.p;
+    // restarted pairs: the partition that becomes valid at this hop is put in place first; while any is pending the hop runs all its
+    // partitions itself (a tail computed a hop ahead would need the next partition already)
+    const bool revealing = !c->reveals.empty();
+    if (revealing && (r = advance_reveals<T>(c, st))) return r;
     if (pe) HB_CUDA(cudaEventRecord(pe[0], st));
     if (c->fused && !peer.world)
     {
@@ -1020,7 +1104,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     if (pe) HB_CUDA(cudaEventRecord(pe[1], st));
     SegSets sets;
     memset(&sets, 0, sizeof(sets));
-    if (!c->split)
+    if (!c->split || revealing)
     {
         Range rf = c->r_full;
         rf.slot = c->g.slot; rf.kind = 2;
@@ -1028,6 +1112,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
         if (pe) { HB_CUDA(cudaEventRecord(pe[2], st)); HB_CUDA(cudaEventRecord(pe[3], st)); }
         sets.n = 1;
         sets.s[0].S = c->d_S.p; sets.s[0].U = rf.U; sets.s[0].upt = rf.upt; sets.s[0].G = rf.G;
+        if (c->split) { c->tail_valid = false; c->tail_missing = true; }     // the overlapped schedule resumes with a full hop
     }
     else
     {
@@ -1118,8 +1203,9 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
         {
             const size_t left = nh - h;
             int nb = 1;
-            while (nb * 2 <= c->mh_max && size_t(nb) * 2 <= left) nb *= 2;
-            const bool small_batch = nb == 1 && c->hb_max > 1 && left >= 2;
+            const bool quiet = c->reveals.empty();                    // restarted pairs come back one partition per hop: no batches meanwhile
+            while (quiet && nb * 2 <= c->mh_max && size_t(nb) * 2 <= left) nb *= 2;
+            const bool small_batch = quiet && nb == 1 && c->hb_max > 1 && left >= 2;
             if (small_batch) nb = (int) std::min<size_t>(left, c->hb_max);
             if (nb == 1)
             {
@@ -1306,7 +1392,7 @@ int process_shard(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_
         {
             const bool first = h == 0;
             int nb = 1;
-            if (!silent && c->mh_ok) while (nb * 2 <= c->mh_max && size_t(nb) * 2 <= nh - h) nb *= 2;
+            if (!silent && c->mh_ok && c->reveals.empty()) while (nb * 2 <= c->mh_max && size_t(nb) * 2 <= nh - h) nb *= 2;
             if (nb == 1)
             {
                 const bool last = h + 1 == nh;
@@ -1415,12 +1501,66 @@ int set_ir_core(hb_conv *c, uint32_t grp, uint32_t in, uint32_t o, const T *d_ir
     const uint32_t np = (uint32_t) ((length + B - 1) / B);
     const size_t pair = (size_t(grp) * c->outs + o) * c->ins + in;
     const uint32_t nwrite = std::max(np, c->nparts[pair]);
+    drop_reveal(c, grp, in, o);
     int rc = launch_ir<T>(c, d_ir, length, grp, in, o, nwrite, st);
     if (rc) return rc;
     c->nparts[pair] = np;
     c->P = *std::max_element(c->nparts.begin(), c->nparts.end());
     c->need_reset = true;
     return error;
+}
+
+// Can pair restarts be done in place?  The stream must be running (otherwise a plain set / reset is the same thing), the pair must fit
+// the delay line as it is (a longer ring is a new geometry) and the transforms must be single-CTA ones (k_ir's side output).
+template <class T>
+bool live_possible(hb_conv *c, uint32_t np)
+{
+    return !c->need_reset && c->P > 0 && np <= c->P && !is_big<T>(c);
+}
+
+// hide the pair and register its spectra for the partition-per-hop return; `from_ir`: transform d_ir (nullptr / 0 taps = clear the pair),
+// else gather the spectra it has now (reset of the pair)
+template <class T>
+int restart_pair(hb_conv *c, uint32_t grp, uint32_t in, uint32_t o, bool from_ir, const T *d_ir, uintptr_t length, uint32_t np)
+{
+    // the hops in flight read the spectra that are about to change
+    HB_CUDA(cudaDeviceSynchronize());
+    const size_t pair = (size_t(grp) * c->outs + o) * c->ins + in;
+    const uint32_t old_np = c->nparts[pair];
+    drop_reveal(c, grp, in, o);
+    if (c->split) { c->tail_valid = false; c->tail_missing = true; }      // the tail computed ahead holds the old pair
+    hb_conv::Reveal r;
+    r.grp = grp; r.in = in; r.out = o; r.np = np; r.shown = 0; r.age = 0; r.side = nullptr;
+    int rc = HB_OK;
+    if (np)
+    {
+        HB_CUDA(cudaMalloc(&r.side, size_t(np) * c->g.B * sizeof(Cx<T>) + size_t(np) * sizeof(T)));
+        if (from_ir) rc = launch_ir<T>(c, d_ir, length, grp, in, o, np, c->stream, r.side);
+        else rc = pair_copy<T>(c, r, 0, np, 1, c->stream);
+    }
+    if (rc == HB_OK) rc = pair_copy<T>(c, r, 0, std::max(old_np, np), 2, c->stream);
+    if (rc) { cudaFree(r.side); return rc; }
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    c->nparts[pair] = np;
+    if (np) c->reveals.push_back(r);
+    return HB_OK;
+}
+
+template <class T>
+int set_ir_live_core(hb_conv *c, uint32_t grp, uint32_t in, uint32_t o, const T *d_ir, uintptr_t length)
+{
+    int error = ERR_NONE;
+    if (c->length && c->length < length) length = c->length;
+    if (length > c->max_length) { length = c->max_length; error = ERR_MEM_ALLOC_TOO_SMALL; }
+    const uint32_t B = c->g.B;
+    const uint32_t np = (uint32_t) ((length + B - 1) / B);
+    if (!live_possible<T>(c, np))
+    {
+        int rc = set_ir_core<T>(c, grp, in, o, d_ir, length, c->stream);
+        return rc < 0 ? rc : (rc ? rc : error);
+    }
+    int rc = restart_pair<T>(c, grp, in, o, true, d_ir, length, np);
+    return rc ? rc : error;
 }
 
 int check_handle(hb_conv *c)
@@ -1531,7 +1671,46 @@ extern "C" int hb_conv_set_reset_offset(hb_conv *c, intptr_t offset)
     return ERR_NONE;
 }
 
+namespace
+{
+int set_ir_host(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length, bool live);
+}
+
 extern "C" int hb_conv_set_ir(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length)
+{
+    return set_ir_host(c, group, in, out, ir, ir_dtype, length, false);
+}
+
+extern "C" int hb_conv_set_ir_live(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length)
+{
+    return set_ir_host(c, group, in, out, ir, ir_dtype, length, true);
+}
+
+extern "C" int hb_conv_reset_pair(hb_conv *c, uint32_t group, uint32_t in, uint32_t out)
+{
+    int rc = check_handle(c);
+    if (rc) return rc;
+    if (group >= c->groups || in >= c->ins || out >= c->outs) { set_error("hb_conv_reset_pair: bad argument"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    const size_t pair = (size_t(group) * c->outs + out) * c->ins + in;
+    const uint32_t np = c->nparts[pair];
+    const bool live = c->dtype == HB_F64 ? live_possible<double>(c, np) : live_possible<float>(c, np);
+    if (!live) { c->need_reset = true; return ERR_NONE; }              // nothing running yet, or not possible in place: the whole stream restarts
+    if (!np) return ERR_NONE;
+    // a pair that is still coming back keeps the spectra it has not shown yet: put them in place before they are gathered again
+    for (hb_conv::Reveal &r : c->reveals)
+        if (r.grp == group && r.in == in && r.out == out)
+        {
+            rc = c->dtype == HB_F64 ? pair_copy<double>(c, r, r.shown, r.np - r.shown, 0, c->stream) : pair_copy<float>(c, r, r.shown, r.np - r.shown, 0, c->stream);
+            if (rc) return rc;
+            HB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    return c->dtype == HB_F64 ? restart_pair<double>(c, group, in, out, false, nullptr, 0, np) : restart_pair<float>(c, group, in, out, false, nullptr, 0, np);
+}
+
+namespace
+{
+int set_ir_host(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length, bool live)
 {
     int rc = check_handle(c);
     if (rc) return rc;
@@ -1562,12 +1741,17 @@ extern "C" int hb_conv_set_ir(hb_conv *c, uint32_t group, uint32_t in, uint32_t 
         }
         HB_CUDA(cudaMemcpyAsync(c->d_ir.p, c->h_ir.p, take * es, cudaMemcpyHostToDevice, c->stream));
     }
-    rc = c->dtype == HB_F64 ? set_ir_core<double>(c, group, in, out, (const double *) c->d_ir.p, len, c->stream)
-                            : set_ir_core<float>(c, group, in, out, (const float *) c->d_ir.p, len, c->stream);
+    if (live)
+        rc = c->dtype == HB_F64 ? set_ir_live_core<double>(c, group, in, out, (const double *) c->d_ir.p, len)
+                                : set_ir_live_core<float>(c, group, in, out, (const float *) c->d_ir.p, len);
+    else
+        rc = c->dtype == HB_F64 ? set_ir_core<double>(c, group, in, out, (const double *) c->d_ir.p, len, c->stream)
+                                : set_ir_core<float>(c, group, in, out, (const float *) c->d_ir.p, len, c->stream);
     if (rc < 0) return rc;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     return rc;
 }
+} // namespace
 
 extern "C" int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *d_ir, uintptr_t length)
 {
@@ -1603,6 +1787,8 @@ extern "C" int hb_conv_resize(hb_conv *c, uintptr_t max_length)
 
     // keep what is loaded: same tiling, only the partition stride (Pcap) of the layout changes
     plan_geometry(c);
+    if ((rc = c->dtype == HB_F64 ? finish_reveals<double>(c, c->stream) : finish_reveals<float>(c, c->stream))) return rc;
+    HB_CUDA(cudaStreamSynchronize(c->stream));
     const Geom old = c->g;
     void *oldH = c->d_H, *oldHn = c->d_Hnyq;
     const std::vector<uint32_t> old_parts = c->nparts;

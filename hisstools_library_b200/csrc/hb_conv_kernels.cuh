@@ -1085,11 +1085,13 @@ __global__ void __launch_bounds__(256) k_gather(const T *__restrict__ inbox, con
 // (PartitionedConvolve.cpp:203-219).  blockIdx.x = partition; `taps` effective taps at `ir`
 // (offset / length clipping already applied by the host).  Partitions past the end are written as zeros.
 // ---------------------------------------------------------------------------------------------
+// side != nullptr: the spectra go to a private buffer instead ([partition][B] bins in natural order, then one Nyquist value per
+// partition) -- a pair that is replaced while the stream runs is revealed partition by partition (hb_conv.cu, k_pair_copy).
 template <class T, int EPT>
 __global__ void __launch_bounds__(512) k_ir(const Geom g, const T *__restrict__ ir, size_t taps,
                                              uint32_t grp, uint32_t in, uint32_t o,
                                              Cx<T> *__restrict__ H, T *__restrict__ Hnyq,
-                                             const Cx<T> *__restrict__ tw, int tw_log2)
+                                             const Cx<T> *__restrict__ tw, int tw_log2, Cx<T> *__restrict__ side, uint32_t side_parts)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);
@@ -1117,6 +1119,12 @@ __global__ void __launch_bounds__(512) k_ir(const Geom g, const T *__restrict__ 
     for (uint32_t k = threadIdx.x; k < B; k += blockDim.x)
     {
         Cx<T> v = have ? s[sidx<HB_PADSH>(k)] : cx<T>(T(0), T(0));
+        if (side)
+        {
+            if (k == 0) { reinterpret_cast<T *>(side + size_t(side_parts) * B)[p] = v.y; v.y = T(0); }
+            side[size_t(p) * B + k] = v;
+            continue;
+        }
         if (k == 0)
         {
             Hnyq[((size_t(grp) * g.outs + o) * g.ins + in) * g.Pcap + p] = v.y;
@@ -1126,6 +1134,37 @@ __global__ void __launch_bounds__(512) k_ir(const Geom g, const T *__restrict__ 
         const uint64_t tile = (uint64_t(grp) * g.n_ot + ot) * g.n_bt + bt;
         const uint64_t unit = (tile * g.ins + in) * g.Pcap + p;
         H[unit * (uint64_t(g.Q) * VecOf<T>::CPV) + size_t(row) * TB + j] = v;
+    }
+}
+
+// Spectra of ONE pair between the engine's unit layout and a private buffer (layout as k_ir's `side`), partitions p0 + blockIdx.x:
+// mode 0 reveal (H <- side), 1 gather (side <- H), 2 hide (H <- 0).  A pair whose impulse response is replaced (or that is reset)
+// while the stream runs starts again from silence without disturbing the other pairs: its partitions are hidden and come back one
+// per hop, partition p at the hop where the frame it meets is the first one recorded after the restart (hb_conv.cu advance_reveals).
+template <class T>
+__global__ void __launch_bounds__(256) k_pair_copy(const Geom g, Cx<T> *__restrict__ side, uint32_t side_parts, uint32_t grp, uint32_t in, uint32_t o,
+                                                   uint32_t p0, Cx<T> *__restrict__ H, T *__restrict__ Hnyq, int mode)
+{
+    const uint32_t p = p0 + blockIdx.x;
+    const uint32_t B = g.B, TB = tile_bins<T>(g);
+    const uint32_t ot = o / g.OT, row = o - ot * g.OT;
+    T *side_nyq = reinterpret_cast<T *>(side + size_t(side_parts) * B);
+    T *hn = Hnyq + ((size_t(grp) * g.outs + o) * g.ins + in) * g.Pcap + p;
+    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x)
+    {
+        const uint32_t bt = k / TB, j = k - bt * TB;
+        const uint64_t tile = (uint64_t(grp) * g.n_ot + ot) * g.n_bt + bt;
+        const uint64_t unit = (tile * g.ins + in) * g.Pcap + p;
+        Cx<T> *h = H + unit * (uint64_t(g.Q) * VecOf<T>::CPV) + size_t(row) * TB + j;
+        if (mode == 0) *h = side[size_t(p) * B + k];
+        else if (mode == 1) side[size_t(p) * B + k] = *h;
+        else *h = cx<T>(T(0), T(0));
+    }
+    if (threadIdx.x == 0)
+    {
+        if (mode == 0) *hn = side_nyq[p];
+        else if (mode == 1) side_nyq[p] = *hn;
+        else *hn = T(0);
     }
 }
 

@@ -30,10 +30,12 @@ constexpr int TD_BLOCK = 256;
 //   out[g][o][s] (+)= sum_i sum_{k < T} h[g][o][i][k] * x[g][i][s - k]
 // x for negative sample indices comes from `hist` (the last T samples of the previous calls).
 // grid = (ceil(n / TD_BLOCK), groups * outs); shared memory: T taps + (T + TD_BLOCK) samples.
+// age (optional): samples each pair has seen since it was restarted alone (hb_matrix_set on a running matrix, hb_matrix_reset_pair),
+// saturating at `taps`: a pair only reaches that far back into the input, as a freshly reset TimeDomainConvolve would.
 template <class T>
 __global__ void __launch_bounds__(TD_BLOCK) k_td(const T *__restrict__ h, const T *__restrict__ x, size_t x_ld,
                                                  const T *__restrict__ hist, T *__restrict__ out, size_t out_ld,
-                                                 uint32_t ins, uint32_t outs, uint32_t taps, size_t n, int add)
+                                                 uint32_t ins, uint32_t outs, uint32_t taps, size_t n, int add, const uint32_t *__restrict__ age)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sh = reinterpret_cast<T *>(smem_raw);
@@ -60,8 +62,10 @@ __global__ void __launch_bounds__(TD_BLOCK) k_td(const T *__restrict__ h, const 
         }
         __syncthreads();
         const T *w = sx + threadIdx.x + taps;       // w[-k] = x[s - k]
+        uint32_t reach = taps;                      // taps k < reach: x[s - k] is input from after the pair's restart
+        if (age) reach = (uint32_t) min((unsigned long long) taps, (unsigned long long) s + age[size_t(row) * ins + i] + 1ull);
 #pragma unroll 4
-        for (uint32_t k = 0; k < taps; k++) acc = fma(sh[k], w[-(int) k], acc);
+        for (uint32_t k = 0; k < reach; k++) acc = fma(sh[k], w[-(int) k], acc);
     }
     if (s < n)
     {
@@ -182,6 +186,11 @@ struct hb_matrix
     bool head_reset = true;
     std::vector<uint8_t> head_loaded;        // per pair
     size_t head_count = 0;
+    std::vector<uint32_t> head_age;          // per pair: samples since the pair was restarted alone, saturating at head_taps
+    size_t head_young = 0;                   // pairs whose age is below head_taps
+    void *d_head_age = nullptr;
+    bool head_age_dirty = false;
+    bool running = false;                    // a block has been processed since the last whole reset
     // host-call staging
     cudaStream_t stream = nullptr;
     DevBuf d_in, d_out, d_ir;
@@ -210,7 +219,7 @@ void destroy(hb_matrix *m)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (hb_conv *p : m->parts) hb_conv_destroy(p);
-    cudaFree(m->d_head); cudaFree(m->d_hist[0]); cudaFree(m->d_hist[1]);
+    cudaFree(m->d_head); cudaFree(m->d_hist[0]); cudaFree(m->d_hist[1]); cudaFree(m->d_head_age);
     m->d_in.release(); m->d_out.release(); m->d_ir.release();
     m->h_in.release(); m->h_out.release(); m->h_ir.release();
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -236,6 +245,14 @@ int grow_tail(hb_matrix *m, uintptr_t size)
     return 0;
 }
 
+void head_restart_pair(hb_matrix *m, size_t pair)
+{
+    if (!m->head_taps) return;
+    if (m->head_age[pair] >= m->head_taps) m->head_young++;
+    m->head_age[pair] = 0;
+    m->head_age_dirty = true;
+}
+
 template <class T>
 int head_store(hb_matrix *m, size_t pair, const void *ir, int ir_dtype, uintptr_t length)
 {
@@ -254,7 +271,10 @@ int head_store(hb_matrix *m, size_t pair, const void *ir, int ir_dtype, uintptr_
     m->head_count += now;
     m->head_count -= m->head_loaded[pair];
     m->head_loaded[pair] = now;
-    m->head_reset = true;
+    // a matrix that is running restarts this pair alone (MonoConvolve::set resets one object, MonoConvolve.cpp:118-140): the pair
+    // forgets the input it has seen, the other pairs keep their history
+    if (m->running && !m->head_reset) head_restart_pair(m, pair);
+    else m->head_reset = true;
     return HB_OK;
 }
 
@@ -269,7 +289,8 @@ int set_parts(hb_matrix *m, uint32_t g, uint32_t i, uint32_t o, const void *ir, 
     }
     for (hb_conv *p : m->parts)
     {
-        rc = hb_conv_set_ir(p, g, i, o, ir, ir_dtype, ir ? length : 0);
+        // on a running engine the pair restarts alone where that is possible in place (hb_conv_set_ir_live)
+        rc = hb_conv_set_ir_live(p, g, i, o, ir, ir_dtype, ir ? length : 0);
         if (rc < 0) return rc;
     }
     return HB_OK;
@@ -303,8 +324,23 @@ int process_rows(hb_matrix *m, const T *d_in, size_t in_ld, T *d_out, size_t out
             {
                 HB_CUDA(cudaMemsetAsync(m->d_hist[m->hist_cur], 0, rows_in * taps * sizeof(T), st));
                 m->head_reset = false;
+                // a whole reset: every pair starts from silence together, no pair is younger than the history
+                std::fill(m->head_age.begin(), m->head_age.end(), taps);
+                m->head_young = 0;
+                m->head_age_dirty = false;
             }
-            if (n >= 4 * TD_BLOCK && taps % 4 == 0)
+            const uint32_t *d_age = nullptr;
+            if (m->head_young)
+            {
+                if (m->head_age_dirty)
+                {
+                    HB_CUDA(cudaMemcpyAsync(m->d_head_age, m->head_age.data(), m->head_age.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                    HB_CUDA(cudaStreamSynchronize(st));                  // the host copy changes below
+                    m->head_age_dirty = false;
+                }
+                d_age = (const uint32_t *) m->d_head_age;
+            }
+            if (!d_age && n >= 4 * TD_BLOCK && taps % 4 == 0)
             {
                 // long calls: register-blocked kernel (TD_R samples per thread)
                 const size_t span = size_t(TDB) * TD_R;
@@ -318,7 +354,18 @@ int process_rows(hb_matrix *m, const T *d_in, size_t in_ld, T *d_out, size_t out
                 dim3 grid((unsigned) ((n + TD_BLOCK - 1) / TD_BLOCK), m->groups * m->outs);
                 const size_t smem = (size_t(2) * taps + TD_BLOCK) * sizeof(T);
                 k_td<T><<<grid, TD_BLOCK, smem, st>>>((const T *) m->d_head, d_in, in_ld, (const T *) m->d_hist[m->hist_cur], d_out, out_ld,
-                                                     m->ins, m->outs, taps, n, add ? 1 : 0);
+                                                     m->ins, m->outs, taps, n, add ? 1 : 0, d_age);
+            }
+            if (m->head_young)
+            {
+                // the restarted pairs have now seen n more samples
+                for (uint32_t &a : m->head_age)
+                    if (a < taps)
+                    {
+                        a = (uint32_t) std::min<size_t>(taps, size_t(a) + n);
+                        if (a >= taps) m->head_young--;
+                    }
+                m->head_age_dirty = true;
             }
             HB_LAUNCH_CHECK();
             dim3 hgrid((taps + 255) / 256, (unsigned) rows_in);
@@ -333,6 +380,7 @@ int process_rows(hb_matrix *m, const T *d_in, size_t in_ld, T *d_out, size_t out
         if (rc == HB_OK) any = true;
         else if (rc != HB_ERR_NO_IR) return rc;
     }
+    if (any) m->running = true;
     return any ? HB_OK : HB_ERR_NO_IR;
 }
 
@@ -784,6 +832,13 @@ extern "C" int hb_matrix_create(hb_matrix **out, int dtype, uint32_t groups, uin
         }
         cudaMemset(m->d_head, 0, hb_);
         m->head_loaded.assign(m->pairs(), 0);
+        m->head_age.assign(m->pairs(), m->head_taps);
+        if (cudaMalloc(&m->d_head_age, m->pairs() * sizeof(uint32_t)) != cudaSuccess)
+        {
+            set_error("device allocation failed for the zero-latency head");
+            destroy(m);
+            return HB_ERR_CUDA;
+        }
     }
     apply_reset_offset(m, 0);
     *out = m;
@@ -830,9 +885,7 @@ extern "C" int hb_matrix_resize(hb_matrix *m, uint32_t group, uint32_t in, uint3
     {
         DeviceRestore keep;
         const uint32_t d = front_locate(m, group, in);
-        rc = hb_matrix_resize(m->multi->sh[d].m, group, in, out, length);
-        for (MultiShard &s : m->multi->sh) hb_matrix_reset(s.m);          // a changed pair restarts the whole matrix
-        return rc;
+        return hb_matrix_resize(m->multi->sh[d].m, group, in, out, length);
     }
     const size_t pair = m->pair_index(group, in, out);
     m->pair_len[pair] = 0;
@@ -854,9 +907,7 @@ extern "C" int hb_matrix_set(hb_matrix *m, uint32_t group, uint32_t in, uint32_t
     {
         DeviceRestore keep;
         const uint32_t d = front_locate(m, group, in);
-        rc = hb_matrix_set(m->multi->sh[d].m, group, in, out, ir, ir_dtype, length, request_resize);
-        for (MultiShard &s : m->multi->sh) hb_matrix_reset(s.m);          // a changed pair restarts the whole matrix
-        return rc;
+        return hb_matrix_set(m->multi->sh[d].m, group, in, out, ir, ir_dtype, length, request_resize);
     }
     if (!ir) length = 0;
     const size_t pair = m->pair_index(group, in, out);
@@ -891,6 +942,33 @@ extern "C" int hb_matrix_reset(hb_matrix *m)
     }
     for (hb_conv *p : m->parts) hb_conv_reset(p);
     m->head_reset = true;
+    m->running = false;
+    return 0;
+}
+
+extern "C" int hb_matrix_reset_pair(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out)
+{
+    int rc = check(m);
+    if (rc) return rc;
+    if (group >= m->groups || in >= m->ins || out >= m->outs) { set_error("hb_matrix_reset_pair: pair out of range"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(m->lock);
+    if (m->multi)
+    {
+        DeviceRestore keep;
+        const uint32_t d = front_locate(m, group, in);
+        return hb_matrix_reset_pair(m->multi->sh[d].m, group, in, out);
+    }
+    // MonoConvolve::reset of one object (Convolver.cpp:88-97): every part of the pair and its head restart from silence
+    for (hb_conv *p : m->parts)
+    {
+        rc = hb_conv_reset_pair(p, group, in, out);
+        if (rc < 0) return rc;
+    }
+    if (m->head_taps)
+    {
+        if (m->running && !m->head_reset) head_restart_pair(m, m->pair_index(group, in, out));
+        else m->head_reset = true;
+    }
     return 0;
 }
 

@@ -59,7 +59,7 @@ namespace HISSTools
         {
             uint32_t g, i, o;
             const ConvolveError err = pair(inChan, outChan, g, i, o);
-            return err ? err : b200::to_error(hb_matrix_reset(mMatrix.handle()));
+            return err ? err : b200::to_error(hb_matrix_reset_pair(mMatrix.handle(), g, i, o));
         }
 
         // Resize and set IR (Convolver.cpp:101-134)

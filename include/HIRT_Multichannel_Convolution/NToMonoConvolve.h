@@ -36,7 +36,7 @@ namespace HISSTools
         ConvolveError reset(uint32_t inChan)
         {
             if (inChan >= mNumInChans) return CONVOLVE_ERR_IN_CHAN_OUT_OF_RANGE;
-            return b200::to_error(hb_matrix_reset(mMatrix.handle()));
+            return b200::to_error(hb_matrix_reset_pair(mMatrix.handle(), 0, inChan, 0));     // that input's convolver only (NToMonoConvolve.cpp:28-33)
         }
         void setResetOffset(intptr_t offset = -1) { hb_matrix_set_reset_offset(mMatrix.handle(), offset); }
 

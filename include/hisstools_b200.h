@@ -118,6 +118,17 @@ int hb_conv_set_reset_offset(hb_conv *c, intptr_t offset);
  * element type of `ir` (HB_F32 or HB_F64; converted to the engine's type as Convolver.cpp:126-134
  * does for double IRs).  ir == NULL or length <= offset clears the pair.  Triggers reset(). */
 int hb_conv_set_ir(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length);
+/* set() on an engine that is running, restarting THIS pair only -- what the reference does (MonoConvolve::set resets one object,
+ * MonoConvolve.cpp:118-140, while the other pairs of a Convolver keep playing).  The pair's spectra are hidden and come back one
+ * partition per hop, partition p at the hop where the frame it meets is the first one recorded after the call, so the new response
+ * starts from silence and never meets earlier input (up to the fft_size / 2 samples before the call that share its first frame;
+ * the block finished before the call is still delivered with the old response).  While a pair is coming back, hops run one by
+ * one with all partitions in one launch.  Falls back to hb_conv_set_ir (whole stream restarts) when the stream is not running yet,
+ * the new response needs a longer delay line than the engine has, or the FFT size is above the one-CTA limit. */
+int hb_conv_set_ir_live(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length);
+/* reset of one pair (Convolver::reset(in, out), Convolver.cpp:88-97): the pair forgets its input history as above, keeping its response;
+ * on an engine that is not running, or where it cannot be done in place, the whole stream restarts (hb_conv_reset) */
+int hb_conv_reset_pair(hb_conv *c, uint32_t group, uint32_t in, uint32_t out);
 /* same, `d_ir` in device memory in the engine's dtype.  Synchronises: work enqueued earlier on ANY stream of the device
  * (whatever produced d_ir) is waited for before the transforms start, and the call returns when the spectra are in place
  * (d_ir may be reused at once). */
@@ -265,6 +276,9 @@ int hb_matrix_set_reset_offset(hb_matrix *m, intptr_t offset);
 int hb_matrix_resize(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out, uintptr_t length);
 int hb_matrix_set(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out, const void *ir, int ir_dtype, uintptr_t length, int request_resize);
 int hb_matrix_reset(hb_matrix *m);
+/* Convolver::reset(inChan, outChan) (Convolver.cpp:88-97): restarts that pair only (every part and the head; hb_conv_reset_pair).
+ * hb_matrix_set / hb_matrix_resize on a running matrix likewise restart only the pair they change (hb_conv_set_ir_live). */
+int hb_matrix_reset_pair(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out);
 /* MonoConvolve::process / NToMonoConvolve::process / Convolver::process (MonoConvolve.cpp:179-201,
  * NToMonoConvolve.cpp:35-43, Convolver.cpp:138-154): ins = groups*ins planar host rows (NULL row =
  * inactive input, silence), outs = groups*outs planar host rows (NULL row = not wanted).

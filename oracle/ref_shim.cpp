@@ -203,6 +203,16 @@ SHIM int ref_matrix_set(void *p, uint32_t in, uint32_t out, const float *ir, uin
     m->pairs[idx]->setResetOffset(0);
     return err;
 }
+// MonoConvolve::reset of one pair (what Convolver::reset(in, out) forwards to, Convolver.cpp:88-97)
+SHIM int ref_matrix_reset_pair(void *p, uint32_t in, uint32_t out)
+{
+    auto *m = static_cast<RefMatrix *>(p);
+    size_t idx = m->parallel ? out : size_t(out) * m->nIn + in;
+    int err = m->pairs[idx]->reset();
+    m->pairs[idx]->setResetOffset(0);
+    return err;
+}
+
 // Load every pair of the matrix from a pool of `npool` impulse responses of `len` taps (pair (in, out) takes pool entry
 // (in + out) % npool), the rows dealt to `threads` host threads: set-up of the full-size timing runs, where 4096 pairs
 // set one after the other take longer than the timed steps.

@@ -174,6 +174,7 @@ def ref():
         sig("ref_matrix_destroy", None, V)
         sig("ref_matrix_set", C.c_int, V, C.c_uint32, C.c_uint32, c_f32p, UP)
         sig("ref_matrix_process", None, V, PP32, PP32, SZ)
+        sig("ref_matrix_reset_pair", C.c_int, V, C.c_uint32, C.c_uint32)
         sig("ref_matrix_set_pool_mt", C.c_int, V, PP32, C.c_uint32, UP, C.c_int)
         sig("ref_matrix_process_mt", None, V, PP32, PP32, SZ, C.c_int)
         sig("ref_matrix_time", C.c_double, V, PP32, PP32, SZ, C.c_int, C.c_int, C.c_int)

@@ -754,27 +754,111 @@ def test_process_skips_the_block_while_set_holds_the_object(hb):
     assert seen["busy"] > 0
 
 
-def test_reset_of_one_pair_restarts_the_whole_matrix_documented_difference(hb):
-    """Convolver::reset(in, out) restarts ONE MonoConvolve in the reference (Convolver.cpp:88-97).  Here the delay line of an
-    input is shared by all outputs, so the whole matrix restarts from silence: pinned, so that a change of
-    this behaviour is a decision and not an accident."""
-    n_in, n_out, B, L = 2, 2, 128, 1000
-    cv = hb.Convolver(n_in, n_out, False, 2 * B, maxLength=L)
-    cv.setResetOffset(0)
-    irs = [[ck.synth_ir(L, 70 + 2 * o + i) for i in range(n_in)] for o in range(n_out)]
+@pytest.mark.parametrize("schedule", ["auto", "overlapped", "serial"])
+def test_set_and_reset_of_one_pair_leave_the_other_pairs_running(hb, schedule):
+    """Convolver::set / reset(in, out) on a running matrix restart ONE MonoConvolve in the reference (Convolver.cpp:88-134,
+    MonoConvolve.cpp:118-152): that pair forgets its input history and, after set, answers with the new response; the other
+    pairs keep playing.  Here the delay line of an input is shared by all outputs, so the pair's partitions are hidden and come
+    back one per hop (hb_conv_set_ir_live).  Against the compiled reference's matrix of MonoConvolves with the same set / reset
+    at the same samples: everything must agree except the one block that was already finished when the call came (still
+    delivered with the old pair in it); the changed input is silent for one hop before the call, because the first frame after
+    the restart shares its overlap half with the samples before it."""
+    if ck.ref() is None:
+        pytest.skip("compiled reference not shipped")
+    lib = ck.ref()
+    n_in, n_out, B, L = 3, 2, 256, 3000
+    hops, t_set, t_reset = 30, 9, 19
+    irs = np.stack([np.stack([ck.synth_ir(L, 2300 + 10 * o + i) for i in range(n_in)]) for o in range(n_out)])
+    new_ir = ck.synth_ir(2000, 2399)
+    xs = np.stack([ck.synth_audio(B * hops, 2300 + i) for i in range(n_in)])
+    xs[1, (t_set - 1) * B:t_set * B] = 0                       # input 1 is silent for the hop before its pair (1, 0) is replaced
+    xs[2, (t_reset - 1) * B:t_reset * B] = 0                   # input 2 before pair (2, 1) is reset
+    # reference: rows of MonoConvolve(L, false, 512), one call per hop
+    m = lib.ref_matrix_create(n_in, n_out, L, 2 * B, 0)
     for o in range(n_out):
         for i in range(n_in):
-            assert cv.set(i, o, irs[o][i], L, False) == 0
-    xs = np.stack([ck.synth_audio(B * 24, 70 + i) for i in range(n_in)])
-    half = B * 12
-    y = np.zeros((n_out, B * 24), np.float32)
-    cv.process(xs[:, :half], y[:, :half], n_in, n_out, half)
-    assert cv.reset(1, 0) is not None
-    ya = np.zeros((n_out, half), np.float32)
-    cv.process(np.ascontiguousarray(xs[:, half:]), ya, n_in, n_out, half)
+            lib.ref_matrix_set(m, i, o, ck.fptr(irs[o, i]), L)
+    want = np.zeros((n_out, B * hops), np.float32)
+    P32 = ck.c_f32p
+    for k in range(hops):
+        if k == t_set:
+            assert lib.ref_matrix_set(m, 1, 0, ck.fptr(new_ir), len(new_ir)) == 0
+        if k == t_reset:
+            lib.ref_matrix_reset_pair(m, 2, 1)
+        xp = (P32 * n_in)(*[xs[i, k * B:].ctypes.data_as(P32) for i in range(n_in)])
+        yp = (P32 * n_out)(*[want[o, k * B:].ctypes.data_as(P32) for o in range(n_out)])
+        lib.ref_matrix_process(m, xp, yp, B)
+    lib.ref_matrix_destroy(m)
+    # ours: the same object through the Convolver mirror, calls of one and of several hops (hops go one by one while a pair returns)
+    cv = hb.Convolver(n_in, n_out, False, 2 * B, maxLength=L)
+    eng = cv.matrix.tail
+    eng.set_schedule(None if schedule == "auto" else schedule == "overlapped")
+    cv.setResetOffset(0)
     for o in range(n_out):
-        fresh = sum(ck.direct_convolve_delayed(irs[o][i], xs[i][half:], B) for i in range(n_in))
-        assert ck.rel_rms(ya[o], fresh) <= TOL32              # every pair restarted, also those of output 1
+        for i in range(n_in):
+            assert cv.set(i, o, irs[o, i], L, False) == 0
+    got = np.zeros((n_out, B * hops), np.float32)
+    k = 0
+    for nb in [1, 1, 3, 4, 1, 2, 4, 3, 1, 4, 6]:
+        if k == t_set:
+            assert cv.set(1, 0, new_ir, len(new_ir), False) == 0
+        if k == t_reset:
+            assert cv.reset(2, 1) == 0
+        yb = np.zeros((n_out, nb * B), np.float32)
+        cv.process(np.ascontiguousarray(xs[:, k * B:(k + nb) * B]), yb, n_in, n_out, nb * B)
+        got[:, k * B:(k + nb) * B] = yb
+        k += nb
+    assert k == hops
+    keep = np.ones(B * hops, bool)
+    keep[t_set * B:(t_set + 1) * B] = False
+    assert ck.rel_rms(got[0][keep], want[0][keep]) <= TOL32
+    assert ck.rel_rms(got[1][:t_reset * B], want[1][:t_reset * B]) <= TOL32            # output 1 is not touched by the set of pair (1, 0)
+    keep[:] = True
+    keep[t_reset * B:(t_reset + 1) * B] = False
+    assert ck.rel_rms(got[1][keep], want[1][keep]) <= TOL32
+    # the pair that was replaced really answers with the new response: long after the call its old response would still ring
+    assert ck.rel_rms(got[0][(t_set + 1) * B:], want[0][(t_set + 1) * B:]) <= TOL32
+
+
+def test_latency_zero_convolver_set_of_one_pair_against_the_reference_object(hb):
+    """The same on the shipped scheme: Convolver(2, 2, kLatencyZero) (direct-form head + four FFT sizes) against the reference's own
+    Convolver object, one pair replaced at a sample where every part is at a hop boundary."""
+    if ck.ref() is None:
+        pytest.skip("compiled reference not shipped")
+    lib = ck.ref()
+    n, L, T, total, blk = 2, 20000, 16384, 49152, 512
+    irs = [[ck.synth_ir(L, 2400 + 10 * o + i) for i in range(n)] for o in range(n)]
+    new_ir = ck.synth_ir(12000, 2499)
+    xs = np.stack([ck.synth_audio(total, 2400 + i) for i in range(n)])
+    xs[0, T - 8192:T] = 0                                       # input 0 silent for the longest hop before pair (0, 1) is replaced
+    h = lib.ref_conv_create(n, n, 0)
+    for o in range(n):
+        for i in range(n):
+            assert lib.ref_conv_set_f32(h, i, o, ck.fptr(irs[o][i]), L, 1) == 0
+    want = np.zeros((n, total), np.float32)
+    P32 = ck.c_f32p
+    for pos in range(0, total, blk):
+        if pos == T:
+            assert lib.ref_conv_set_f32(h, 0, 1, ck.fptr(new_ir), len(new_ir), 1) == 0
+        xp = (P32 * n)(*[xs[i, pos:].ctypes.data_as(P32) for i in range(n)])
+        yp = (P32 * n)(*[want[o, pos:].ctypes.data_as(P32) for o in range(n)])
+        lib.ref_conv_process_f32(h, xp, yp, n, n, blk)
+    lib.ref_conv_destroy(h)
+    cv = hb.Convolver(n, n, hb.kLatencyZero)
+    cv.setResetOffset(0)
+    for o in range(n):
+        for i in range(n):
+            assert cv.set(i, o, irs[o][i], L, True) == 0
+    got = np.zeros((n, total), np.float32)
+    for pos in range(0, total, blk):
+        if pos == T:
+            assert cv.set(0, 1, new_ir, len(new_ir), True) == 0
+        yb = np.zeros((n, blk), np.float32)
+        cv.process(np.ascontiguousarray(xs[:, pos:pos + blk]), yb, n, n, blk)
+        got[:, pos:pos + blk] = yb
+    assert ck.rel_rms(got[0], want[0]) <= TOL32                                        # output 0: untouched by the set of pair (0, 1)
+    assert ck.rel_rms(got[1][:T], want[1][:T]) <= TOL32
+    assert ck.rel_rms(got[1][T + 8192:], want[1][T + 8192:]) <= TOL32                  # after the blocks that were already finished
 
 
 @pytest.mark.parametrize("ins,outs,groups,B,L", [(1, 1, 1, 512, 4096), (8, 1, 1, 2048, 40000), (3, 2, 2, 128, 1000), (1, 1, 1, 1024, 65536)])
