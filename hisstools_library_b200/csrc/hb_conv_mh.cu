@@ -122,8 +122,10 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// NH = 8: three warpgroups are launched (168 registers each) and the registers are re-dealt with setmaxnreg -- the producer's
+// warpgroup keeps 40, the two consumer warpgroups take 232, which lets both operand sides of an item stay in registers
 template <int NH, int RB, int TBV, int IPS>
-__global__ void __launch_bounds__(288, 1) k_cmac_mh2(const Geom g, const Range rg, const float4 *__restrict__ H, const float4 *__restrict__ X,
+__global__ void __launch_bounds__(NH == 8 ? 384 : 288, 1) k_cmac_mh2(const Geom g, const Range rg, const float4 *__restrict__ H, const float4 *__restrict__ X,
                                                       float4 *__restrict__ S, const int nstages, const uint64_t set_stride)
 {
     constexpr int SPLIT = 8 / RB;
@@ -155,6 +157,13 @@ __global__ void __launch_bounds__(288, 1) k_cmac_mh2(const Geom g, const Range r
 
     if (producer)
     {
+        if (NH == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (tid >= 288)
+        {
+            // warps 9-11 only exist to make the producer's warpgroup whole: they keep the step barriers
+            for (uint32_t t = 0; t < nsteps; t++) __syncthreads();
+            return;
+        }
         // ---- producer warp: all 32 lanes walk the cursor (warp-uniform values), one elected lane issues ----
         MhCursor<SPLIT> prod;
         prod.seek(g, rg, u0);
@@ -198,6 +207,7 @@ __global__ void __launch_bounds__(288, 1) k_cmac_mh2(const Geom g, const Range r
     }
 
     // ---- consumer warps ----
+    if (NH == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // only the virtual tile matters on this side (where the partial segment goes)
     uint32_t c_vt = (uint32_t) (u0 / rg.upt);
     uint32_t c_left = rg.upt - (uint32_t) (u0 - uint64_t(c_vt) * rg.upt);     // items left in this virtual tile
@@ -250,7 +260,20 @@ __global__ void __launch_bounds__(288, 1) k_cmac_mh2(const Geom g, const Range r
     };
     auto mac_item = [&](uint32_t hs, uint32_t xs)
     {
-        if (RB <= NH)
+        if (NH == 8)
+        {
+            // 232 registers: all operands of the item are loaded up front, the FFMA2 stream never waits for shared memory
+            float4 hv[RB], xv[NH];
+#pragma unroll
+            for (int b = 0; b < RB; b++) hv[b] = load_h(hs, b);
+#pragma unroll
+            for (int j = 0; j < NH; j++) xv[j] = load_x(xs, j);
+#pragma unroll
+            for (int j = 0; j < NH; j++)
+#pragma unroll
+                for (int b = 0; b < RB; b++) cmac2(acc[j][b][0], acc[j][b][1], xv[j], hv[b]);
+        }
+        else if (RB <= NH)
         {
             float4 hv[RB];
 #pragma unroll
@@ -351,7 +374,7 @@ int launch_inst(const Geom &g, const Range &r, const void *H, const void *X, voi
     const size_t smem = size_t(nst) * mh2_stage_bytes(TBV, NH, RB) + size_t(nst) * 8;
     int rc = allow_smem(k_cmac_mh2<NH, RB, TBV, IPS>, smem);
     if (rc) return rc;
-    k_cmac_mh2<NH, RB, TBV, IPS><<<r.G, 288, smem, st>>>(g, r, (const float4 *) H, (const float4 *) X, (float4 *) S, nst, set_stride);
+    k_cmac_mh2<NH, RB, TBV, IPS><<<r.G, NH == 8 ? 384 : 288, smem, st>>>(g, r, (const float4 *) H, (const float4 *) X, (float4 *) S, nst, set_stride);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }

@@ -207,6 +207,7 @@ namespace
 int check(hb_matrix *m)
 {
     if (!m) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    if (m->multi) return HB_OK;               // a multi-device front leaves the caller's device alone: its shards select theirs
     return use_device(m->device);
 }
 
