@@ -326,7 +326,7 @@ void plan_geometry(hb_conv *c)
         c->mh_packed = c->mh_ok && c->dtype == HB_F32 && mh2_supported(g, 2) && !(env_scalar && atoi(env_scalar));
         // batches of hops on engines that are NOT HBM-bound (launch-latency-bound: one cluster launch or three kernels per hop):
         // a call that brings several hops runs their forward FFTs, multiply-accumulates and inverse FFTs as three launches
-        c->hb_max = (c->multi_hop && !c->mh_ok && (int) log2m <= single_cta_max_log2m(c) && g.P >= 1) ? c->extra_slots + 1 : 1;
+        c->hb_max = (c->multi_hop && !c->mh_ok && tail_bytes < (uint64_t(4) << 20) && (int) log2m <= single_cta_max_log2m(c) && g.P >= 1) ? c->extra_slots + 1 : 1;
         // hops one pass carries at most: 8 (half units) where the prepared delay-line tiles stay small beside the IR unit
         c->mh_max = !c->mh_ok ? 1 : (!c->mh_packed ? 4 : (mh2_supported(g, 8) ? 8 : (mh2_supported(g, 4) ? 4 : 2)));
     }

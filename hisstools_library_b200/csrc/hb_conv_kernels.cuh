@@ -89,12 +89,24 @@ struct Range
 // ---------------------------------------------------------------------------------------------
 // vector complex multiply-accumulate
 // ---------------------------------------------------------------------------------------------
+// float: two packed fma.rn.f32x2 (SASS FFMA2) per complex bin -- acc(re, im) += xr * (hr, hi); acc(re, im) += (-hi, hr) * xi.  The
+// broadcast of xr / xi, the swap of (hr, hi) and the negated half are operand modifiers of FFMA2 (R.F32, .LO_HI, .NP), so a bin costs
+// two instructions of the FMA pipe instead of four (a three-register FFMA issues at half rate on this part; hb_conv_mh.cu).
+__device__ __forceinline__ unsigned long long pk_f32x2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 __device__ __forceinline__ void cmac(float4 &a, const float4 x, const float4 h)
 {
-    a.x = fmaf(x.x, h.x, a.x); a.x = fmaf(-x.y, h.y, a.x);
-    a.y = fmaf(x.x, h.y, a.y); a.y = fmaf(x.y, h.x, a.y);
-    a.z = fmaf(x.z, h.z, a.z); a.z = fmaf(-x.w, h.w, a.z);
-    a.w = fmaf(x.z, h.w, a.w); a.w = fmaf(x.w, h.z, a.w);
+    unsigned long long a0 = pk_f32x2(a.x, a.y), a1 = pk_f32x2(a.z, a.w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(pk_f32x2(x.x, x.x)), "l"(pk_f32x2(h.x, h.y)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(pk_f32x2(x.z, x.z)), "l"(pk_f32x2(h.z, h.w)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(pk_f32x2(-h.y, h.x)), "l"(pk_f32x2(x.y, x.y)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(pk_f32x2(-h.w, h.z)), "l"(pk_f32x2(x.w, x.w)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.z), "=f"(a.w) : "l"(a1));
 }
 __device__ __forceinline__ void cmac(double2 &a, const double2 x, const double2 h)
 {
