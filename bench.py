@@ -18,14 +18,17 @@ the cross-device form of NToMonoConvolve.cpp:39-42.  Total work is f
 Printed JSON (one line, rank 0):
   value      whole-job M output-samples/s, inputs resident in HBM, CUDA events on the launching stream with the
              engine's look-ahead stream joined before the closing event (steady state), max over ranks
-  e2e        the same metric through the host-pointer C-ABI call (host<->device copies inside the timed region)
+  e2e        the same metric through the host-pointer C-ABI call (host<->device copies inside the timed region): hb_conv_process
+             at N = 1; at N > 1 hb_matrix_process on ONE multi-device matrix (hb_matrix_create_multi) driven by rank 0 alone --
+             the reference's one object / one process(ins, outs) call over all N GPUs -- while the other ranks wait on the host
+             (the per-rank figure, pinned H2D + ShardedConvolver + D2H in every process, is kept as e2e.per_rank_processes)
   roofline   the dominant multiply-accumulate launch (the tail launch of the overlapped schedule):
              its algorithmic bytes / its mean duration measured with CUDA events inside the library on the
              stream it is launched on, against MEASURED_PEAKS.json; hop_frac = bytes per hop / whole hop period
   parity     relative RMS error of the benchmarked engine against the compiled reference (oracle/_ref) on the same
              synthetic stream, P + 16 blocks, computed OUTSIDE the timed regions (tolerance 1e-5 float, 1e-12 double)
-  multi_hop_reuse  the same engine fed 4 / 8 blocks per call (every IR spectrum read once per call): reported
-             separately, the per-hop byte figure does not apply to it
+  multi_hop_reuse  the same engine fed 4 / 8 blocks per call (every IR spectrum read once per call; launch-latency-bound
+             engines: 8 / 64 blocks per call sharing their launches): reported separately, the per-hop byte figure does not apply
   cpu_baseline  the unmodified reference (oracle/_ref, compiled from /root/reference by oracle/Makefile)
              timed on this box's host cores on a bounded sample of the same workload (rank 0, N = 1)
 
