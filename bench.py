@@ -353,6 +353,9 @@ def run_ours(args):
         eng.set_fft_path(args.fft_path)
     if args.tail_streams:
         eng.set_tail_streams(args.tail_streams)
+    # the input rows of every timed call sit complete in HBM before the call is made (the pool below), which is what mode 2 declares:
+    # fused engines (configs 1-3) may then run consecutive single-block calls side by side.  Config 4 / 5 are not fused engines.
+    eng.set_hop_overlap(args.hop_overlap)
     gen = torch.Generator(device=dev)
     decay = torch.exp(-6.9 * torch.arange(taps, device=dev, dtype=torch.float64) / taps).to(tdt)
     for g in range(l_groups):
@@ -375,14 +378,18 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
+    # (pointers looked up once: a block of configs 1-3 takes a few microseconds, as long as a handful of Python attribute calls)
+    x_ptrs = [t.data_ptr() for t in x_pool]
+    y_ptr, y_ld, s_ptr = y_part.data_ptr(), y_part.stride(0), stream.cuda_stream
+
     def block(k, y=None):
         """one block of B samples per channel through the device-resident entry point"""
-        x = x_pool[k % n_pool]
         if sharded is not None:
-            sharded.process_device(x, y_shard if y is None else y, n, stream.cuda_stream)
+            sharded.process_device(x_pool[k % n_pool], y_shard if y is None else y, n, s_ptr)
+        elif y is None:
+            eng.process_device(x_ptrs[k % n_pool], n, y_ptr, y_ld, n, False, s_ptr)
         else:
-            out = y_part if y is None else y
-            eng.process_device(x.data_ptr(), n, out.data_ptr(), out.stride(0), n, False, stream.cuda_stream)
+            eng.process_device(x_ptrs[k % n_pool], n, y.data_ptr(), y.stride(0), n, False, s_ptr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -394,21 +401,26 @@ def run_ours(args):
     for k in range(8):
         block(k)
     barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record(stream)
-    for k in range(16):
-        block(k)
-    eng.join(stream.cuda_stream)
-    c1.record(stream)
-    barrier()
-    t_block = c0.elapsed_time(c1) / 16 * 1e-3
+    t_block = 0.0
+    for n_cal in (16, 512, 4096):
+        # (blocks of a few microseconds -- overlapping fused hops -- need more than 16 of them to show their steady rate)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for k in range(n_cal):
+            block(k)
+        eng.join(stream.cuda_stream)
+        c1.record(stream)
+        barrier()
+        t_block = c0.elapsed_time(c1) / n_cal * 1e-3
+        if t_block * n_cal > 5e-3:
+            break
     if args.blocks_per_step > 0:
         R = args.blocks_per_step
     else:
         tb = torch.tensor([t_block], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        R = int(min(8192, max(1, math.ceil(args.min_seconds / (max(args.steps, 1) * float(tb.item()))))))
+        R = int(min(65536, max(1, math.ceil(args.min_seconds / (max(args.steps, 1) * float(tb.item()))))))
     warm_steps = max(args.warmup, 3)
 
     k = 0
@@ -651,6 +663,8 @@ def run_ours(args):
                            "window": "CUDA events on the launching stream; the engine's look-ahead (tail) stream is joined before the closing event"},
                 "engine": {"sharding": mode, "local_inputs": l_ins, "outputs": outs, "groups": l_groups, "schedule": eng.schedule,
                            "tail_streams": tail_streams,
+                           "hop_overlap": ("consecutive single-block calls overlap (hb_conv_set_hop_overlap mode %d: input rows complete before each call)" % args.hop_overlap
+                                           if args.hop_overlap else "every hop behind the previous one") if eng.schedule == "fused" else "n/a (not a fused engine)",
                            "transforms": {1: "one CTA each", 2: "cluster of 8 CTAs each (DSMEM)", 3: "four-step chains"}.get(eng.fft_path, "?"),
                            "l2": "inputs larger than L2: %.2f GiB of IR spectra per rank streamed every block" % (bytes_per_hop / 2 ** 30)
                                  if bytes_per_hop > 256e6 else "working set %.1f MiB is L2-resident (not an HBM-roofline case)" % (bytes_per_hop / 2 ** 20),
@@ -845,6 +859,8 @@ def main():
     ap.add_argument("--fft-path", type=int, default=0, choices=[0, 1, 2, 3],
                     help="transforms: 0 automatic, 1 one CTA each, 2 cluster of 8 CTAs each, 3 four-step chains (hb_conv_set_fft_path)")
     ap.add_argument("--tail-streams", type=int, default=0, choices=[0, 1, 2], help="overlapped schedule: streams the tail launches alternate between (0: library default)")
+    ap.add_argument("--hop-overlap", type=int, default=2, choices=[0, 1, 2],
+                    help="fused engines (configs 1-3): 0 every hop behind the previous one, 2 consecutive calls overlap (hb_conv_set_hop_overlap)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"], help="multi-GPU sum of partial outputs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-multi-hop", action="store_true", help="skip the multi-hop reuse leg")

@@ -71,6 +71,7 @@ SIGNATURES = {
     "hb_matrix_set": (C.c_int, [V, U32, U32, U32, V, C.c_int, UP, C.c_int]),
     "hb_matrix_reset": (C.c_int, [V]),
     "hb_matrix_reset_pair": (C.c_int, [V, U32, U32, U32]),
+    "hb_matrix_set_hop_overlap": (C.c_int, [V, C.c_int]),
     "hb_matrix_process": (C.c_int, [V, C.POINTER(V), C.POINTER(V), UP, C.c_int]),
     "hb_matrix_process_dev": (C.c_int, [V, V, UP, V, UP, UP, C.c_int, V]),
     "hb_matrix_parts": (U32, [V]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "hb_conv_get_trace": (C.c_int, [V, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_conv_set_schedule": (C.c_int, [V, C.c_int]),
     "hb_conv_set_tail_streams": (C.c_int, [V, C.c_int]),
+    "hb_conv_set_hop_overlap": (C.c_int, [V, C.c_int]),
     "hb_conv_tail_streams": (C.c_int, [V]),
     "hb_conv_schedule": (C.c_int, [V]),
     "hb_conv_bytes_per_launch": (C.c_uint64, [V]),

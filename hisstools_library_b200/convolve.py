@@ -188,6 +188,10 @@ class _Engine:
         (the fused single-launch hop where it applies, else overlapped / serial by size)."""
         return _abi.check(_abi.lib().hb_conv_set_schedule(self._h, 2 if overlapped is None else (1 if overlapped else 0)))
 
+    def set_hop_overlap(self, mode=1):
+        """fused hops: 0 never overlap consecutive calls, 1 on the engine's own stream, 2 on any stream (hb_conv_set_hop_overlap)"""
+        return _abi.check(_abi.lib().hb_conv_set_hop_overlap(self._h, int(mode)))
+
     def set_tail_streams(self, streams=1):
         """overlapped schedule: 2 = tails of consecutive hops on alternating streams (hb_conv_set_tail_streams)"""
         return _abi.check(_abi.lib().hb_conv_set_tail_streams(self._h, int(streams)))
@@ -396,6 +400,10 @@ class _Matrix:
         ip = (C.c_void_p * len(in_rows))(*[None if r is None else r.ctypes.data for r in in_rows])
         op = (C.c_void_p * len(out_rows))(*[None if r is None else r.ctypes.data for r in out_rows])
         return _abi.check(_abi.lib().hb_matrix_process(self._h, ip, op, int(n), 1 if accumulate else 0)) == _abi.HB_OK
+
+    def set_hop_overlap(self, mode=1):
+        """hb_matrix_set_hop_overlap: fused parts may run consecutive device calls side by side (0 never, 1 own stream, 2 any)"""
+        return _abi.check(_abi.lib().hb_matrix_set_hop_overlap(self._h, int(mode)))
 
     def process_device(self, in_ptr, in_ld, out_ptr, out_ld, n, accumulate=False, stream=0):
         code = _abi.lib().hb_matrix_process_dev(self._h, C.c_void_p(in_ptr), int(in_ld), C.c_void_p(out_ptr), int(out_ld),

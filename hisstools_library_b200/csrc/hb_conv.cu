@@ -111,6 +111,12 @@ struct hb_conv
     bool split = false;             // overlapped schedule in effect for the current geometry (needs P >= 2)
     bool fused = false;             // fused single-launch hop in effect (hb_conv_fused.cuh)
     uint32_t fused_cs = 1;          // its cluster size
+    // consecutive fused hops that overlap (hb_conv_fused.cuh, "chained"; hb_conv_set_hop_overlap)
+    int hop_overlap = 1;            // 0 never, 1 on the engine's own stream, 2 on any stream (the caller's rows are complete when a call is made)
+    DevBuf d_chain;                 // the three counters of the hop chain (+ padding)
+    unsigned long long chain_n = 0; // fused hops launched since the counters were zeroed
+    bool chain_ok = false;          // the last thing this engine enqueued was a fused hop, on chain_stream
+    cudaStream_t chain_stream = nullptr;
     Range r_full{}, r_head{}, r_tail{};
     DevBuf d_St[2];                 // tail partial segments, double-buffered over hops
     cudaStream_t s_tail = nullptr, s_tail_b = nullptr;
@@ -326,7 +332,10 @@ void plan_geometry(hb_conv *c)
         c->mh_packed = c->mh_ok && c->dtype == HB_F32 && mh2_supported(g, 2) && !(env_scalar && atoi(env_scalar));
         // batches of hops on engines that are NOT HBM-bound (launch-latency-bound: one cluster launch or three kernels per hop):
         // a call that brings several hops runs their forward FFTs, multiply-accumulates and inverse FFTs as three launches
-        c->hb_max = (c->multi_hop && !c->mh_ok && tail_bytes < (uint64_t(4) << 20) && (int) log2m <= single_cta_max_log2m(c) && g.P >= 1) ? c->extra_slots + 1 : 1;
+        // (spectra that stay in L2 between the hops of a batch: fused engines, and whatever else streams less than 48 MiB per hop;
+        // an engine that streams more from HBM gains nothing from sharing launches -- config 5 -- and goes hop by hop)
+        c->hb_max = (c->multi_hop && !c->mh_ok && (c->fused || tail_bytes < (uint64_t(48) << 20)) && (int) log2m <= single_cta_max_log2m(c) && g.P >= 1)
+                        ? c->extra_slots + 1 : 1;
         // hops one pass carries at most: 8 (half units) where the prepared delay-line tiles stay small beside the IR unit
         c->mh_max = !c->mh_ok ? 1 : (!c->mh_packed ? 4 : (mh2_supported(g, 8) ? 8 : (mh2_supported(g, 4) ? 4 : 2)));
     }
@@ -691,14 +700,14 @@ int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t
 }
 
 // the whole hop in one cluster launch (hb_conv_fused.cuh); eligibility is decided in plan_geometry
-template <class T>
-int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, const InvIO<T> &io, cudaStream_t st)
+template <class T, int MAXT>
+int launch_fused_t(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, const InvIO<T> &io, cudaStream_t st)
 {
     const Geom &g = c->g;
     constexpr int EPT = 8;
     const uint32_t B = g.B, cs = c->fused_cs;
     const size_t smem = (size_t(padded_elems<HB_PADSH>(B)) + 2 * size_t(B)) * sizeof(Cx<T>);
-    auto kernel = k_hop_fused<T, EPT>;
+    auto kernel = k_hop_fused<T, EPT, MAXT>;
     int rc = allow_smem(kernel, smem);
     if (rc) return rc;
     if (cs > 8)
@@ -714,6 +723,18 @@ int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, siz
     FusedArgs fa;
     fa.cs = cs;
     fa.tail_items = g.P > 2 ? g.ins * (g.P - 2) : 0;
+    // chained: this hop follows a fused hop of this engine directly (nothing else was enqueued in between by the engine, and
+    // nothing by the caller if the stream is the caller's -- which is what hop_overlap = 2 declares) and may run beside it
+    const bool overlap_allowed = c->hop_overlap == 2 || (c->hop_overlap == 1 && st == c->stream);
+    fa.chained = (overlap_allowed && c->chain_ok && c->chain_stream == st && c->chain_n > 0) ? 1u : 0u;
+    // only hops that a chained hop may follow take part in the count (the fences of the counter updates cost a strict hop about a
+    // microsecond): chain_n numbers those, and a chained hop always follows one of them directly
+    fa.bump = overlap_allowed ? 1u : 0u;
+    fa.writers = g.groups * std::min<uint32_t>(cs, g.ins);
+    fa.clusters = g.groups * g.outs;
+    fa.depth = std::min<uint32_t>(g.R - g.P, 8u);
+    fa.n = overlap_allowed ? ++c->chain_n : 0;
+    fa.sync = (unsigned long long *) c->d_chain.p;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(g.groups * g.outs * cs);
@@ -734,7 +755,16 @@ int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, siz
                                (const T *) c->d_Hnyq, (T *) c->d_Xnyq, io.yout, io.ld, io.off, io.add_result,
                                io.carry_src, io.carry_src_ld, io.carry_dst, io.carry_dst_ld, io.add_carry, (const Cx<T> *) c->d_tw, c->tw_log2));
     HB_LAUNCH_CHECK();
+    c->chain_ok = overlap_allowed;
+    c->chain_stream = st;
     return HB_OK;
+}
+
+template <class T>
+int launch_fused(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, size_t new_ld, T *save, size_t save_ld, const InvIO<T> &io, cudaStream_t st)
+{
+    return c->g.B / 8 <= 256 ? launch_fused_t<T, 256>(c, prev, prev_ld, newest, new_ld, save, save_ld, io, st)
+                             : launch_fused_t<T, 512>(c, prev, prev_ld, newest, new_ld, save, save_ld, io, st);
 }
 
 template <class T, int EPT>
@@ -980,6 +1010,10 @@ int do_reset(hb_conv *c, cudaStream_t st)
     HB_CUDA(cudaMemsetAsync(c->d_Xnyq, 0, size_t(g.groups) * g.ins * g.R * sizeof(T), st));
     c->rw = c->reset_offset < 0 ? 0 : uintptr_t(c->reset_offset) % g.B;
     c->g.slot = 0;
+    if ((rc = c->d_chain.ensure(64))) return rc;
+    HB_CUDA(cudaMemsetAsync(c->d_chain.p, 0, 64, st));
+    c->chain_n = 0;
+    c->chain_ok = false;
     // staging rows start as silence: previous hop, pending samples and previous result block
     if (c->xin_ld) HB_CUDA(cudaMemsetAsync(c->d_xin[c->cur].p, 0, size_t(g.groups) * g.ins * c->xin_ld * sizeof(T), st));
     if (c->yout_ld) HB_CUDA(cudaMemsetAsync(c->d_yout[c->cur].p, 0, size_t(g.groups) * g.outs * c->yout_ld * sizeof(T), st));
@@ -1094,6 +1128,7 @@ int launch_hop(hb_conv *c, cudaStream_t st, const T *prev, size_t prev_ld, const
     const bool revealing = !c->reveals.empty();
     if (revealing && (r = advance_reveals<T>(c, st))) return r;
     if (pe) HB_CUDA(cudaEventRecord(pe[0], st));
+    if (revealing || pe || !c->fused || peer.world) c->chain_ok = false;      // something else sits between this hop and the last fused one
     if (c->fused && !peer.world)
     {
         if ((r = launch_fused<T>(c, prev, prev_ld, newest, new_ld, save, save_ld, io, st))) return r;
@@ -1217,6 +1252,7 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
                 continue;
             }
             // ---- multi-hop reuse: nb hops over ONE pass of the IR spectra (k_cmac_tma_mh) ----
+            c->chain_ok = false;
             // a tail launched ahead for the first of these hops is not used: the batch covers all partitions itself
             if (c->split && c->tail_valid) HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
             c->tail_valid = false;
@@ -1268,6 +1304,7 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
     }
 
     if ((rc = ensure_staging<T>(c, B + rw + n, (nh + 1) * B, true, st))) return rc;
+    c->chain_ok = false;                                              // row copies sit between the hops of this path
 
     // bring the retained heads to offset 0 of the other row set when they sit further in
     if (c->x_tail || c->y_tail)
@@ -1644,6 +1681,7 @@ extern "C" int hb_conv_set_fft_size(hb_conv *c, uintptr_t fft_size)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     return apply_fft_size(c, fft_size);
 }
 
@@ -1651,6 +1689,7 @@ extern "C" int hb_conv_set_length(hb_conv *c, uintptr_t length)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->length = std::min(length, c->max_length);
     return length > c->max_length ? ERR_PARTITION_LENGTH_TOO_LARGE : ERR_NONE;
 }
@@ -1659,6 +1698,7 @@ extern "C" int hb_conv_set_offset(hb_conv *c, uintptr_t offset)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->offset = offset;
     return ERR_NONE;
 }
@@ -1667,6 +1707,7 @@ extern "C" int hb_conv_set_reset_offset(hb_conv *c, intptr_t offset)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->reset_offset = offset;
     return ERR_NONE;
 }
@@ -1692,6 +1733,7 @@ extern "C" int hb_conv_reset_pair(hb_conv *c, uint32_t group, uint32_t in, uint3
     if (rc) return rc;
     if (group >= c->groups || in >= c->ins || out >= c->outs) { set_error("hb_conv_reset_pair: bad argument"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     const size_t pair = (size_t(group) * c->outs + out) * c->ins + in;
     const uint32_t np = c->nparts[pair];
     const bool live = c->dtype == HB_F64 ? live_possible<double>(c, np) : live_possible<float>(c, np);
@@ -1716,6 +1758,7 @@ int set_ir_host(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const voi
     if (rc) return rc;
     if (group >= c->groups || in >= c->ins || out >= c->outs || (ir_dtype != HB_F32 && ir_dtype != HB_F64)) { set_error("hb_conv_set_ir: bad argument"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     // cpp:192: nothing to load when the IR ends before the offset
     uintptr_t len = (!ir || length <= c->offset) ? 0 : length - c->offset;
     uintptr_t take = len;
@@ -1759,6 +1802,7 @@ extern "C" int hb_conv_set_ir_dev(hb_conv *c, uint32_t group, uint32_t in, uint3
     if (rc) return rc;
     if (group >= c->groups || in >= c->ins || out >= c->outs) { set_error("hb_conv_set_ir_dev: bad argument"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     // d_ir may have been produced on any stream of the caller (the transforms run on the engine's own non-blocking
     // stream, which is not ordered after any of them): wait for everything enqueued on the device so far
     HB_CUDA(cudaDeviceSynchronize());
@@ -1777,6 +1821,7 @@ extern "C" int hb_conv_resize(hb_conv *c, uintptr_t max_length)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->s_tail) HB_CUDA(cudaStreamSynchronize(c->s_tail));       // a tail launched ahead reads the spectra freed below
     if (c->s_tail_b) HB_CUDA(cudaStreamSynchronize(c->s_tail_b));
@@ -1824,6 +1869,7 @@ extern "C" int hb_conv_reset(hb_conv *c)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->need_reset = true;
     return ERR_NONE;
 }
@@ -1841,7 +1887,11 @@ extern "C" int hb_conv_process_dev(hb_conv *c, const void *d_in, uintptr_t in_ld
     if ((!d_in || !d_out) && num_samples) { set_error("hb_conv_process_dev: null buffer"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
     cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
-    if (c->blk_valid && (rc = drain_deferred(c))) return rc;        // host-pointer calls were in flight on this handle
+    if (c->blk_valid)
+    {
+        c->chain_ok = false;
+        if ((rc = drain_deferred(c))) return rc;                    // host-pointer calls were in flight on this handle
+    }
     c->blk_valid = false;
     return core_dispatch(c, d_in, in_ld, d_out, out_ld, num_samples, accumulate, st);
 }
@@ -2046,6 +2096,7 @@ extern "C" int hb_conv_process(hb_conv *c, const void *const *ins, void *const *
     if (rc) return rc;
     if ((!ins || !outs) && n) { set_error("hb_conv_process: null buffer"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     // (a rank of the fused multi-GPU exchange takes part in every hop, loaded or not: its peers wait for its blocks)
     if (!c->P && !c->peers_attached) return HB_ERR_NO_IR;
     if (!n) return HB_OK;
@@ -2080,6 +2131,7 @@ extern "C" int hb_conv_shard_export(hb_conv *c, uint32_t world, uint32_t rank, v
         return HB_ERR_BAD_ARG;
     }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (c->d_inbox) { set_error("hb_conv_shard_export: already exported"); return HB_ERR_BAD_ARG; }
     static_assert(sizeof(cudaIpcMemHandle_t) == HB_IPC_HANDLE_BYTES, "IPC handle size");
     const size_t slot = (size_t(1) << c->max_fft_log2) >> 1;
@@ -2105,6 +2157,7 @@ extern "C" int hb_conv_shard_attach(hb_conv *c, const void *handles)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (!handles || !c->d_inbox || c->peers_attached) { set_error("hb_conv_shard_attach: export first, attach once"); return HB_ERR_BAD_ARG; }
     for (uint32_t r = 0; r < c->shard_world; r++)
     {
@@ -2132,6 +2185,7 @@ extern "C" int hb_conv_shard_attach_local(hb_conv *c, hb_conv *const *peers)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (!peers || !c->d_inbox || c->peers_attached) { set_error("hb_conv_shard_attach_local: export first, attach once"); return HB_ERR_BAD_ARG; }
     for (uint32_t r = 0; r < c->shard_world; r++)
     {
@@ -2163,6 +2217,7 @@ extern "C" int hb_conv_shard_status(hb_conv *c, uint32_t *late_ranks)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (!c->d_inbox || !late_ranks) { set_error("hb_conv_shard_status: not a sharded engine"); return HB_ERR_BAD_ARG; }
     HB_CUDA(cudaDeviceSynchronize());
     HB_CUDA(cudaMemcpy(late_ranks, (const char *) c->d_inbox + c->inbox_data_bytes + INBOX_LATE_OFF, sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -2188,9 +2243,20 @@ extern "C" int hb_conv_join(hb_conv *c, void *stream)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
     // the only work an engine keeps in flight outside the caller's stream: the tail launched ahead for the next hop
     if (c->split && c->tail_valid) HB_CUDA(cudaStreamWaitEvent(st, c->ev_tail[c->tail_par], 0));
+    return HB_OK;
+}
+
+extern "C" int hb_conv_set_hop_overlap(hb_conv *c, int mode)
+{
+    if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    if (mode < 0 || mode > 2) { set_error("hop overlap mode must be 0 (never), 1 (the engine's own stream) or 2 (any stream)"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
+    c->hop_overlap = mode;
     return HB_OK;
 }
 
@@ -2199,6 +2265,7 @@ extern "C" int hb_conv_set_tuning(hb_conv *c, int ctas_per_sm, int variant)
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     if (variant != 0 && variant != 1) { set_error("variant must be 0 (direct loads) or 1 (TMA ring)"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : (variant == 1 ? 1 : 2);
     c->variant = variant;
     c->need_reset = true;           // partial-segment geometry depends on the grid
@@ -2210,6 +2277,7 @@ extern "C" int hb_conv_set_tail_streams(hb_conv *c, int streams)
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     if (streams < 0 || streams > 2) { set_error("tail streams must be 0 (automatic), 1 or 2"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->tail_streams_req = streams;
     c->need_reset = true;
     return HB_OK;
@@ -2219,6 +2287,7 @@ extern "C" int hb_conv_set_schedule(hb_conv *c, int overlapped)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (overlapped < 0 || overlapped > 3) { set_error("schedule must be 0 (serial), 1 (overlapped), 2 (automatic) or 3 (fused where eligible)"); return HB_ERR_BAD_ARG; }
     c->schedule = overlapped;
     c->need_reset = true;           // the partial-segment sets depend on the schedule
@@ -2229,6 +2298,7 @@ extern "C" int hb_conv_set_fft_path(hb_conv *c, int path)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (path < 0 || path > 3) { set_error("fft path must be 0 (automatic), 1 (one CTA per transform), 2 (cluster of 8 CTAs) or 3 (four-step)"); return HB_ERR_BAD_ARG; }
     c->fft_path = path;
     c->need_reset = true;           // the tail grid depends on where the FFT CTAs run
@@ -2247,6 +2317,7 @@ extern "C" int hb_conv_set_multi_hop(hb_conv *c, int enable)
 {
     if (!c) { set_error("null handle"); return HB_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     c->multi_hop = enable ? 1 : 0;
     c->need_reset = true;
     return HB_OK;
@@ -2257,6 +2328,7 @@ extern "C" int hb_conv_set_trace(hb_conv *c, int enable)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     HB_CUDA(cudaDeviceSynchronize());
     if (!enable) { c->d_trace.release(); return HB_OK; }
     const size_t bytes = size_t(TRACE_HOPS) * TRACE_KINDS * 2 * TRACE_CTAS * sizeof(unsigned long long);
@@ -2270,6 +2342,7 @@ extern "C" int hb_conv_get_trace(hb_conv *c, uint64_t *out, uint64_t *hop)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if (!c->d_trace.p || !out) { set_error("hb_conv_get_trace: tracing is off"); return HB_ERR_BAD_ARG; }
     HB_CUDA(cudaDeviceSynchronize());
     HB_CUDA(cudaMemcpy(out, c->d_trace.p, size_t(TRACE_HOPS) * TRACE_KINDS * 2 * TRACE_CTAS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -2282,6 +2355,7 @@ extern "C" int hb_conv_set_host_pipeline(hb_conv *c, int pipelined)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     if ((rc = drain_deferred(c))) return rc;
     c->blk_valid = false;
@@ -2294,6 +2368,7 @@ extern "C" int hb_conv_set_profiling(hb_conv *c, int enable)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if ((rc = drain_profile(c))) return rc;
     c->profiling = enable != 0;
     for (int k = 0; k < 5; k++) c->prof_ms[k] = 0;
@@ -2306,6 +2381,7 @@ extern "C" int hb_conv_get_profile(hb_conv *c, double *ms, uint64_t *hops)
     int rc = check_handle(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(c->lock);
+    c->chain_ok = false;
     if ((rc = drain_profile(c))) return rc;
     if (ms) for (int k = 0; k < 5; k++) ms[k] = c->prof_ms[k];
     if (hops) *hops = c->prof_hops;

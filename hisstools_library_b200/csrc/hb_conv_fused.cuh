@@ -15,15 +15,26 @@
 // schedules are unchanged.
 //
 // Programmatic dependent launch (round 2).  Back-to-back hops of a stream are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization and the kernel is ordered in two phases around griddepcontrol.wait:
-//   before the wait  what does not depend on the previous hop: twiddles into shared memory, the newest input block into
-//                    registers, and the products of partitions p >= 2 -- they meet spectra that are at least two hops old,
-//                    written by kernels that had completed before this one could start (a kernel releases its successor only
-//                    after its own wait has returned);
-//   after the wait   the previous block (saved by the previous hop), the forward FFT, partitions 0 and 1 (p = 1 meets the
-//                    spectrum the previous hop wrote), the reduction, the inverse FFT and the store.
-// So the launch latency of hop t+1 and most of its L2 round trips run beside the critical part of hop t.  Without the launch
-// attribute (or with anything else between two hops in the stream) the wait returns at once and the kernel is what it was.
+// cudaLaunchAttributeProgrammaticStreamSerialization.  The kernel runs in one of two orders (FusedArgs::chained):
+//
+//  strict   (any stream; what a caller gets who only promises stream order for its rows)
+//           before griddepcontrol.wait: twiddles into shared memory and the products of partitions p >= 2 -- they meet spectra
+//           that are at least two hops old, written by kernels that had completed before this one could start (a strict kernel
+//           releases its successor only after its own wait has returned);  after it: the caller's rows, the forward FFT,
+//           partitions 0 and 1, the reduction, the inverse FFT and the store.
+//  chained  (the engine's own stream, or a caller that declares its rows complete when the call is made:
+//           hb_conv_set_hop_overlap)  no wait up front.  The hop depends on its predecessors through three counters in
+//           device memory (FusedArgs::sync), bumped by every hop of either kind:
+//             [0] input blocks saved      -> the previous block of this hop's frame
+//             [1] spectra stored          -> partition 1 (previous hop's spectrum), partitions >= 2 (two hops back and older)
+//             [2] hops finished           -> the delay-line slot this hop overwrites is no longer read (at most `depth` hops
+//                                            are in flight), and -- through griddepcontrol.wait just before the store -- hops
+//                                            leave their blocks in stream order.
+//           It builds its frame and releases its successor at once, transforms, and only then waits for the spectra it
+//           multiplies with: the forward FFT of hop t+1 does not wait for anything hop t computes, so consecutive hops run
+//           side by side on different SMs and a stream of single-block calls is bound by the launch rate, not by the
+//           latency of one hop.  Spectra and saved blocks written by a hop that may still be running are read with
+//           ld.global.cg (L2) after an acquire load of the counter.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -37,16 +48,52 @@ namespace cg = cooperative_groups;
 struct FusedArgs
 {
     uint32_t cs;               // cluster size
-    uint32_t tail_items;       // ins * (P - 2): the products of partitions p >= 2 (p = 1 waits for the previous hop)
+    uint32_t tail_items;       // ins * (P - 2): the products of partitions p >= 2
+    uint32_t chained;          // 1: consecutive hops overlap (counters); 0: griddepcontrol.wait first
+    uint32_t bump;             // 1: this hop counts (a chained hop may follow it); 0: nothing on this stream will look at the counters
+    uint32_t writers;          // CTAs per hop that bump sync[0] and sync[1]: groups * min(cs, ins)
+    uint32_t clusters;         // CTAs per hop that bump sync[2]: groups * outs
+    uint32_t depth;            // hops that may be in flight behind the one whose delay-line slot is reused
+    unsigned long long n;      // number of this hop since the counters were zeroed (1, 2, ...)
+    unsigned long long *sync;  // [0] blocks saved, [1] spectra stored, [2] hops finished
 };
 
-template <class T, int EPT>
-__global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs fa,
+// one thread's wait for a counter of the hop chain (the hop that bumps it was launched earlier on this stream and is resident
+// or finished, so the wait is short; a wait of seconds means a broken chain and stops the context instead of hanging the device)
+__device__ __forceinline__ void chain_wait(const unsigned long long *p, unsigned long long target)
+{
+    if (!target) return;
+    unsigned long long v, t0 = 0;
+    for (uint32_t spins = 0;; spins++)
+    {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= target) return;
+        if ((spins & 255u) == 255u)
+        {
+            const unsigned long long t = global_ns();
+            if (!t0) t0 = t;
+            else if (t - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void chain_bump(unsigned long long *p)
+{
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
+}
+
+__device__ __forceinline__ Cx<float> ld_l2(const Cx<float> *p) { const float2 v = __ldcg(reinterpret_cast<const float2 *>(p)); return cx<float>(v.x, v.y); }
+__device__ __forceinline__ Cx<double> ld_l2(const Cx<double> *p) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(p)); return cx<double>(v.x, v.y); }
+
+// MAXT: 256 for spectra of up to 2048 bins (the whole register file of a thread is available), 512 above
+template <class T, int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArgs fa,
                                                    const T *__restrict__ prev, size_t prev_ld, const T *__restrict__ newest, size_t new_ld,
                                                    T *__restrict__ save, size_t save_ld,
-                                                   const Cx<T> *__restrict__ H, Cx<T> *__restrict__ X, const T *__restrict__ Hnyq, T *__restrict__ Xnyq,
-                                                   T *__restrict__ yout, size_t ld, size_t off, int add_result,
-                                                   const T *__restrict__ carry_src, size_t carry_src_ld, T *__restrict__ carry_dst, size_t carry_dst_ld, int add_carry,
+                                                   const Cx<T> *__restrict__ H, Cx<T> *X, const T *__restrict__ Hnyq, T *Xnyq,
+                                                   T *yout, size_t ld, size_t off, int add_result,
+                                                   const T *carry_src, size_t carry_src_ld, T *carry_dst, size_t carry_dst_ld, int add_carry,
                                                    const Cx<T> *__restrict__ tw, int tw_log2)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -64,43 +111,32 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     Cx<T> *xch = stw + B;                                       // this rank's partial spectrum, read by rank 0
     __shared__ T red[40];
     __shared__ T nyq_part;
+    const bool chained = fa.chained != 0;
+    const unsigned long long n1 = fa.n >= 1 ? (fa.n - 1) * fa.writers : 0;      // what the previous hop leaves in sync[0] and sync[1]
+    const unsigned long long n2 = fa.n >= 2 ? (fa.n - 2) * fa.writers : 0;
     trace_mark(g, 0, 0);
 
-    // twiddles of this transform size into shared memory (published by the first barrier below)
-    {
-        Cx<T> twr[EPT];
-        twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
-        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
-    }
-    const Cx<T> *twl = stw;
-    const int twl_log2 = (int) g.log2n;
-
+    // Two running sums, so that the samples do not depend on the order the kernel runs in: `acc` / `nyq` take partitions 0 and 1
+    // (in input order), the products of partitions >= 2 are summed on their own and parked in this rank's exchange row.
     Cx<T> acc[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; e++) acc[e] = cx<T>(T(0), T(0));
-    T nyq = T(0);
+    T nyq = T(0), nyq_tail = T(0);
 
-    // ================= before the wait: nothing here depends on the previous hop =================
-    // the newest block of the first input this rank transforms (the caller's rows are complete before the launch)
-    // (float only: the double instance has no registers to carry values across the transform -- 128 at 512 threads)
-    constexpr bool EARLY = sizeof(T) == 4;
-    T na[EARLY ? EPT : 1], nbv[EARLY ? EPT : 1];
-    if (EARLY && rank < g.ins)
-    {
-        const T *pn = newest + size_t(grp * g.ins + rank) * new_ld;
-#pragma unroll
-        for (int e = 0; e < EPT; e++)
-        {
-            const uint32_t k = tid + e * nthr, j = 2 * k;
-            if (k < B && j < B) { na[e] = pn[j]; nbv[e] = pn[j + 1]; }
-        }
-    }
-    trace_mark(g, 1, 0);
+    // twiddles of this transform size: fetched now, put into shared memory further down (published by the first barrier after that)
+    Cx<T> twr[EPT];
+    twiddle_stage_load<T, EPT>(twr, tw, tw_log2, (int) g.log2n);
+    const Cx<T> *twl = stw;
+    const int twl_log2 = (int) g.log2n;
+
     // this rank's share of the (input, partition >= 2) products: spectra that are at least two hops old
-    if (P > 2)
+    auto tail_products = [&]()
     {
+        Cx<T> t[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; e++) t[e] = cx<T>(T(0), T(0));
         const uint32_t q0 = (uint32_t) ((uint64_t(rank) * fa.tail_items) / cs), q1 = (uint32_t) ((uint64_t(rank + 1) * fa.tail_items) / cs);
-        const uint32_t pm2 = P - 2;
+        const uint32_t pm2 = P > 2 ? P - 2 : 1;
         for (uint32_t q = q0; q < q1; q++)
         {
             const uint32_t in = q / pm2, p = 2 + (q - in * pm2);
@@ -114,7 +150,7 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
             for (int e = 0; e < EPT; e++)
             {
                 const uint32_t k = tid + e * nthr;
-                if (k < B) { hv[e] = hp[k]; xv[e] = xp[k]; }
+                if (k < B) { hv[e] = hp[k]; xv[e] = ld_l2(xp + k); }
             }
 #pragma unroll
             for (int e = 0; e < EPT; e++)
@@ -122,50 +158,84 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 const uint32_t k = tid + e * nthr;
                 if (k < B)
                 {
-                    acc[e].x = fma(xv[e].x, hv[e].x, acc[e].x); acc[e].x = fma(-xv[e].y, hv[e].y, acc[e].x);
-                    acc[e].y = fma(xv[e].x, hv[e].y, acc[e].y); acc[e].y = fma(xv[e].y, hv[e].x, acc[e].y);
+                    t[e].x = fma(xv[e].x, hv[e].x, t[e].x); t[e].x = fma(-xv[e].y, hv[e].y, t[e].x);
+                    t[e].y = fma(xv[e].x, hv[e].y, t[e].y); t[e].y = fma(xv[e].y, hv[e].x, t[e].y);
                 }
             }
-            if (tid == 0) nyq += Xnyq[size_t(ch) * R + sl] * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
+            if (tid == 0) nyq_tail += __ldcg(Xnyq + size_t(ch) * R + sl) * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
         }
-    }
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B) xch[k] = t[e];                       // each thread parks and later fetches its own bins
+        }
+    };
 
-    // ================= the previous hop must be complete from here on; release the next one =================
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-    if (rank == 0 && carry_dst)
+    // hand the block computed by the previous hop to the caller (the output-ring read of PartitionedConvolve.cpp:307): fetched as
+    // early as the order allows, stored once the loads of the frame are under way
+    Cx<T> cv[EPT / 2];
+    auto carry_load = [&]()
     {
-        // hand the block computed by the previous hop to the caller (the output-ring read of PartitionedConvolve.cpp:307)
+        if (!carry_dst) return;
         const T *cs_ = carry_src + size_t(cl) * carry_src_ld;
+#pragma unroll
+        for (int e = 0; e < EPT / 2; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B / 2) cv[e] = cx<T>(__ldcg(cs_ + 2 * k), __ldcg(cs_ + 2 * k + 1));
+        }
+    };
+    auto carry_store = [&]()
+    {
+        if (!carry_dst) return;
         T *cd = carry_dst + size_t(cl) * carry_dst_ld;
-        for (uint32_t k = tid; k < B; k += nthr) cd[k] = add_carry ? cd[k] + cs_[k] : cs_[k];
-    }
+#pragma unroll
+        for (int e = 0; e < EPT / 2; e++)
+        {
+            const uint32_t k = tid + e * nthr;
+            if (k < B / 2)
+            {
+                if (add_carry) { cd[2 * k] += cv[e].x; cd[2 * k + 1] += cv[e].y; }
+                else { cd[2 * k] = cv[e].x; cd[2 * k + 1] = cv[e].y; }
+            }
+        }
+    };
 
-    // ---- inputs this rank transforms: forward FFT, newest FDL slot, partitions 0 and 1 ----
+    if (!chained)
+    {
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
+        tail_products();
+        trace_mark(g, 1, 0);
+        // ================= the previous hop must be complete from here on; release the next one =================
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (rank == 0) carry_load();
+    }
+    else
+    {
+        if (tid == 0) chain_wait(fa.sync + 0, n1);                                                 // the previous block is saved
+        if (tid == 32 && fa.n > fa.depth + 1) chain_wait(fa.sync + 2, (fa.n - 1 - fa.depth) * fa.clusters);   // the slot written below is free
+        if (rank >= g.ins) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");         // no rows of the caller's to read
+        twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
+    }
+    trace_mark(g, 4, 0);
+
+    // ---- inputs this rank transforms: forward FFT, newest FDL slot, partition 0 ----
+    constexpr bool KEEP = sizeof(T) == 4;                       // float: the rows of partitions 0 and 1 are fetched ahead of the transform
+    Cx<T> h0v[KEEP ? EPT : 1], h1v[KEEP ? EPT : 1], x1v[KEEP ? EPT : 1];   // (x1v: strict order only -- the previous hop's spectrum is complete)
+    uint32_t sl1 = g.slot + 1;
+    if (sl1 >= R) sl1 -= R;
     for (uint32_t in = rank; in < g.ins; in += cs)
     {
         const uint32_t ch = grp * g.ins + in;
         const T *pn = newest + size_t(ch) * new_ld, *pp = prev + size_t(ch) * prev_ld;
         T *ps = (save && writer) ? save + size_t(ch) * save_ld : nullptr;
-        // partition 1 meets the spectrum the previous hop wrote: fetched now, used after the transform
-        Cx<T> x1[EPT], h1[EPT];
-        T xn1 = T(0), hn1 = T(0);
-        uint32_t sl1 = g.slot + 1;
-        if (sl1 >= R) sl1 -= R;
-        const Cx<T> *hp1 = H + (((size_t(tile) * g.ins + in) * g.Pcap + 1) * g.OT + row) * B;
-        const Cx<T> *xp1 = X + (size_t(ch) * R + sl1) * B;
-        if (EARLY && P > 1)
-        {
-#pragma unroll
-            for (int e = 0; e < EPT; e++)
-            {
-                const uint32_t k = tid + e * nthr;
-                if (k < B) { h1[e] = hp1[k]; x1[e] = xp1[k]; }
-            }
-        }
-        if (P > 1 && tid == 0) { xn1 = Xnyq[size_t(ch) * R + sl1]; hn1 = Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + 1]; }
-        __syncthreads();                                        // s is free (previous input's spectrum consumed)
+        const bool last_in = in + cs >= g.ins;
+        // unit (tile, in, p) holds OT rows of B bins; this output is row `row` of it
+        const Cx<T> *h0 = H + ((size_t(tile) * g.ins + in) * g.Pcap * g.OT + row) * B;
+        const T *hnq = Hnyq + (size_t(cl) * g.ins + in) * g.Pcap;
+        __syncthreads();                                        // s is free (previous input's spectrum consumed); the chain waits are over
 #pragma unroll
         for (int e = 0; e < EPT; e++)
         {
@@ -175,22 +245,43 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                 T a, b;
                 if (j < B)
                 {
-                    if (EARLY && in == rank) { a = na[EARLY ? e : 0]; b = nbv[EARLY ? e : 0]; }      // loaded before the wait
-                    else { a = pn[j]; b = pn[j + 1]; }
+                    a = pn[j]; b = pn[j + 1];
                     if (ps) { ps[j] = a; ps[j + 1] = b; }
                 }
-                else { a = pp[j - B]; b = pp[j - B + 1]; }
+                else { a = __ldcg(pp + (j - B)); b = __ldcg(pp + (j - B + 1)); }
                 s[sidx<HB_PADSH>(k)] = cx<T>(a, b);
             }
         }
         __syncthreads();
+        if (last_in)
+        {
+            // every row this CTA reads from the previous hop's save area is in shared memory and its own blocks are saved
+            if (tid == 0 && writer && fa.bump) chain_bump(fa.sync + 0);
+            if (chained) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            else if (rank == 0) carry_store();
+        }
+        if (KEEP)
+        {
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+            {
+                const uint32_t k = tid + e * nthr;
+                if (k < B)
+                {
+                    h0v[KEEP ? e : 0] = h0[k];
+                    if (P > 1 && last_in)
+                    {
+                        h1v[KEEP ? e : 0] = h0[size_t(g.OT) * B + k];
+                        if (!chained) x1v[KEEP ? e : 0] = ld_l2(X + (size_t(ch) * R + sl1) * B + k);
+                    }
+                }
+            }
+        }
         block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
         block_real_split<T, EPT, HB_PADSH>(s, B, (int) g.log2n, false, twl, twl_log2);
         __syncthreads();
+        if (last_in) trace_mark(g, 4, 1);
         Cx<T> *xrow = X + (size_t(ch) * R + g.slot) * B;
-        // unit (tile, in, p) holds OT rows of B bins; this output is row `row` of it
-        const Cx<T> *h0 = H + ((size_t(tile) * g.ins + in) * g.Pcap * g.OT + row) * B;
-        const T *hnq = Hnyq + (size_t(cl) * g.ins + in) * g.Pcap;
 #pragma unroll
         for (int e = 0; e < EPT; e++)
         {
@@ -206,33 +297,53 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
                     z.y = T(0);
                 }
                 if (writer) xrow[k] = z;
-                const Cx<T> h = h0[k];
+                const Cx<T> h = KEEP ? h0v[KEEP ? e : 0] : h0[k];
                 acc[e].x = fma(z.x, h.x, acc[e].x); acc[e].x = fma(-z.y, h.y, acc[e].x);
                 acc[e].y = fma(z.x, h.y, acc[e].y); acc[e].y = fma(z.y, h.x, acc[e].y);
             }
         }
+    }
+    if (writer && rank < g.ins && fa.bump)
+    {
+        __syncthreads();                                        // every thread's spectrum stores precede the bump
+        if (tid == 0) chain_bump(fa.sync + 1);
+    }
+
+    if (chained)
+    {
+        trace_mark(g, 1, 0);
+        if (tid == 0) chain_wait(fa.sync + 1, n2);              // spectra up to two hops back are stored
+        __syncthreads();
+        tail_products();
         if (P > 1)
         {
-            if (!EARLY)
-            {
-#pragma unroll
-                for (int e = 0; e < EPT; e++)
-                {
-                    const uint32_t k = tid + e * nthr;
-                    if (k < B) { h1[e] = hp1[k]; x1[e] = xp1[k]; }
-                }
-            }
+            if (tid == 0) chain_wait(fa.sync + 1, n1);          // the previous hop's spectrum is stored
+            __syncthreads();
+        }
+    }
+
+    // ---- partition 1 meets the spectrum the previous hop wrote ----
+    if (P > 1)
+    {
+        for (uint32_t in = rank; in < g.ins; in += cs)
+        {
+            const uint32_t ch = grp * g.ins + in;
+            const bool kept = KEEP && in + cs >= g.ins;          // the last input's row was fetched ahead
+            const Cx<T> *hp1 = H + (((size_t(tile) * g.ins + in) * g.Pcap + 1) * g.OT + row) * B;
+            const Cx<T> *xp1 = X + (size_t(ch) * R + sl1) * B;
 #pragma unroll
             for (int e = 0; e < EPT; e++)
             {
                 const uint32_t k = tid + e * nthr;
                 if (k < B)
                 {
-                    acc[e].x = fma(x1[e].x, h1[e].x, acc[e].x); acc[e].x = fma(-x1[e].y, h1[e].y, acc[e].x);
-                    acc[e].y = fma(x1[e].x, h1[e].y, acc[e].y); acc[e].y = fma(x1[e].y, h1[e].x, acc[e].y);
+                    const Cx<T> h = kept ? h1v[KEEP ? e : 0] : hp1[k];
+                    const Cx<T> x = (kept && !chained) ? x1v[KEEP ? e : 0] : ld_l2(xp1 + k);
+                    acc[e].x = fma(x.x, h.x, acc[e].x); acc[e].x = fma(-x.y, h.y, acc[e].x);
+                    acc[e].y = fma(x.x, h.y, acc[e].y); acc[e].y = fma(x.y, h.x, acc[e].y);
                 }
             }
-            if (tid == 0) nyq += xn1 * hn1;
+            if (tid == 0) nyq += __ldcg(Xnyq + size_t(ch) * R + sl1) * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + 1];
         }
     }
 
@@ -242,9 +353,9 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     for (int e = 0; e < EPT; e++)
     {
         const uint32_t k = tid + e * nthr;
-        if (k < B) xch[k] = acc[e];
+        if (k < B) { const Cx<T> t = xch[k]; acc[e] = cx<T>(t.x + acc[e].x, t.y + acc[e].y); xch[k] = acc[e]; }
     }
-    const T nyq_sum = block_sum<T>(nyq, red);
+    const T nyq_sum = block_sum<T>(nyq_tail + nyq, red);
     if (tid == 0) nyq_part = nyq_sum;
     cluster.sync();
     trace_mark(g, 2, 0);                                        // first cluster barrier passed
@@ -289,6 +400,15 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
     __syncthreads();
     block_fft<T, EPT, HB_PADSH>(s, (int) g.log2n - 1, twl, twl_log2);
     trace_mark(g, 3, 0);                                        // inverse transform done
+
+    // chained: the previous hop (and with it every hop before) has finished -- its block may be handed on, the staging row it
+    // read may be overwritten, and blocks reach the caller's rows in stream order
+    if (chained)
+    {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        carry_load();
+        carry_store();
+    }
     const T scale = T(1) / T(size_t(4) << g.log2n);
     T *dst = yout + size_t(cl) * ld + off;
 #pragma unroll
@@ -301,6 +421,11 @@ __global__ void __launch_bounds__(512) k_hop_fused(const Geom g, const FusedArgs
             if (add_result) { dst[2 * k] += z.y * scale; dst[2 * k + 1] += z.x * scale; }
             else { dst[2 * k] = z.y * scale; dst[2 * k + 1] = z.x * scale; }
         }
+    }
+    if (fa.bump)
+    {
+        __syncthreads();
+        if (tid == 0) chain_bump(fa.sync + 2);
     }
     trace_mark(g, 0, 1);
 }

@@ -191,6 +191,8 @@ struct hb_matrix
     void *d_head_age = nullptr;
     bool head_age_dirty = false;
     bool running = false;                    // a block has been processed since the last whole reset
+    int hop_overlap = 1;                     // hb_matrix_set_hop_overlap: 0 never, 1 on the matrix's own stream, 2 on any stream
+    int parts_overlap = -1;                  // what the parts were last told (hb_conv_set_hop_overlap: 0 or 2)
     // host-call staging
     cudaStream_t stream = nullptr;
     DevBuf d_in, d_out, d_ir;
@@ -994,8 +996,27 @@ extern "C" int hb_matrix_process_dev(hb_matrix *m, const void *d_in, uintptr_t i
     if (!g.owns_lock()) return HB_ERR_BUSY;
     if (!n) return HB_OK;
     cudaStream_t st = stream ? (cudaStream_t) stream : m->stream;
+    // consecutive fused hops of a part may overlap where the rows of a call are complete when it is made: the matrix's own
+    // stream (nothing can order them behind the caller's work there), or any stream if the caller says so
+    const int overlap = (m->hop_overlap == 2 || (m->hop_overlap == 1 && !stream)) ? 2 : 0;
+    if (overlap != m->parts_overlap)
+    {
+        for (hb_conv *p : m->parts) hb_conv_set_hop_overlap(p, overlap);
+        m->parts_overlap = overlap;
+    }
     return m->dtype == HB_F64 ? process_rows<double>(m, (const double *) d_in, in_ld, (double *) d_out, out_ld, n, accumulate, st)
                               : process_rows<float>(m, (const float *) d_in, in_ld, (float *) d_out, out_ld, n, accumulate, st);
+}
+
+extern "C" int hb_matrix_set_hop_overlap(hb_matrix *m, int mode)
+{
+    if (!m) { set_error("null handle"); return HB_ERR_BAD_ARG; }
+    if (mode < 0 || mode > 2) { set_error("hop overlap mode must be 0, 1 or 2"); return HB_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> g(m->lock);
+    m->hop_overlap = mode;
+    if (m->multi)
+        for (MultiShard &s : m->multi->sh) hb_matrix_set_hop_overlap(s.m, mode);
+    return HB_OK;
 }
 
 extern "C" int hb_matrix_process(hb_matrix *m, const void *const *ins, void *const *outs, uintptr_t n, int accumulate)

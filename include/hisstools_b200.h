@@ -213,6 +213,14 @@ int hb_conv_set_schedule(hb_conv *c, int overlapped);
  * 3 GiB or less.  Takes effect with a reset.  hb_conv_tail_streams: the number in effect. */
 int hb_conv_set_tail_streams(hb_conv *c, int streams);
 int hb_conv_tail_streams(const hb_conv *c);
+/* Fused hops only: may consecutive single-hop calls run side by side?  A hop needs the block the previous call saved and the
+ * spectra of earlier hops, not the previous hop's output, so hop t+1 can transform its frame while hop t still multiplies -- if its
+ * input rows may be read before the stream has finished what precedes the launch.  mode 1 (default): only for calls on the engine's
+ * own stream (`stream` = NULL), where rows cannot be ordered behind the caller's work anyway and must be complete when the call is
+ * made; mode 2: on any stream -- the caller declares that the input rows of a call are complete when it is made and that nothing
+ * the engine has to wait for is enqueued between two calls; mode 0: never.  Outputs are written in stream order in every mode and
+ * the samples are the same; only the time between back-to-back calls changes (profiles/r2_small_hops.txt). */
+int hb_conv_set_hop_overlap(hb_conv *c, int mode);
 /* schedule in effect after the last reset: 0 serial (also whenever only one partition is loaded), 1 overlapped, 2 fused */
 int hb_conv_schedule(const hb_conv *c);
 /* algorithmic bytes of the dominant multiply-accumulate launch: hb_conv_bytes_per_hop in the serial schedule; in
@@ -279,6 +287,9 @@ int hb_matrix_reset(hb_matrix *m);
 /* Convolver::reset(inChan, outChan) (Convolver.cpp:88-97): restarts that pair only (every part and the head; hb_conv_reset_pair).
  * hb_matrix_set / hb_matrix_resize on a running matrix likewise restart only the pair they change (hb_conv_set_ir_live). */
 int hb_matrix_reset_pair(hb_matrix *m, uint32_t group, uint32_t in, uint32_t out);
+/* hb_conv_set_hop_overlap for the parts of a matrix, applied to hb_matrix_process_dev calls: 1 (default) = calls on the matrix's
+ * own stream (`stream` = NULL), 2 = any stream (input rows complete when the call is made), 0 = never. */
+int hb_matrix_set_hop_overlap(hb_matrix *m, int mode);
 /* MonoConvolve::process / NToMonoConvolve::process / Convolver::process (MonoConvolve.cpp:179-201,
  * NToMonoConvolve.cpp:35-43, Convolver.cpp:138-154): ins = groups*ins planar host rows (NULL row =
  * inactive input, silence), outs = groups*outs planar host rows (NULL row = not wanted).

@@ -897,3 +897,143 @@ def test_hop_batches_on_small_engines(hb, ins, outs, groups, B, L):
         assert ck.rel_rms(res[True][r], res[False][r]) <= 2e-6
     truth = sum(ck.direct_convolve_delayed_fft(irs[0][0][i], xs[i], B) for i in range(ins))
     assert ck.rel_rms(res[True][0], truth) <= TOL32
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("ins,outs,groups,B,L", [(1, 1, 1, 512, 4096), (1, 1, 1, 1024, 65536), (8, 1, 1, 2048, 131072), (3, 1, 2, 256, 5000),
+                                                 (1, 1, 1, 64, 64), (1, 1, 1, 128, 256), (2, 3, 1, 512, 3000), (20, 1, 1, 128, 1024)])
+def test_fused_hops_overlap_between_calls(hb, dtype, ins, outs, groups, B, L):
+    """Back-to-back single-block device calls on a fused engine (hb_conv_set_hop_overlap): mode 0 keeps every hop behind the
+    previous one; mode 2 (the caller's rows are complete when a call is made) and the engine's own stream in mode 1 let hop t+1
+    transform its frame while hop t still multiplies, ordered by the counters of hb_conv_fused.cuh.  300 calls with distinct
+    input and output rows per call: the samples are bit-identical in all three, and what the reference / float64 direct
+    convolution gives; BASELINE configs 1-3, one and two partitions, several outputs, more inputs than ranks in the cluster."""
+    import torch
+    from hisstools_library_b200.convolve import _Engine
+    if dtype == np.float64 and ins * L > 500000:
+        pytest.skip("not a fused engine in double")
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    tol = TOL32 if dtype == np.float32 else TOL64
+    hops = 300
+    n = hops * B
+    irs = [[[ck.synth_ir(L, 3100 + 100 * g + 10 * o + i).astype(dtype) for i in range(ins)] for o in range(outs)] for g in range(groups)]
+    xs = np.stack([ck.synth_audio(n, 3100 + r) for r in range(groups * ins)]).astype(dtype)
+    x = torch.from_numpy(xs).cuda()
+    res = {}
+    for mode, own in ((0, False), (2, False), (1, True), (1, False)):
+        e = _Engine(dtype, groups, ins, outs, 2 * B, L, 0, 0, 0)
+        e.set_reset_offset(0)
+        e.set_hop_overlap(mode)
+        for g in range(groups):
+            for o in range(outs):
+                for i in range(ins):
+                    e.set_ir(g, i, o, irs[g][o][i], L)
+        y = torch.zeros((groups * outs, n), dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for h in range(hops):
+                e.process_device(x.data_ptr() + h * B * x.element_size(), n, y.data_ptr() + h * B * y.element_size(), n, B, False,
+                                 0 if own else stream.cuda_stream)
+            if h == hops - 1:
+                e.join(stream.cuda_stream)
+        torch.cuda.synchronize()
+        assert e.schedule == "fused"
+        res[(mode, own)] = y.cpu().numpy()
+        e.close()
+    base = res[(0, False)]
+    for key in ((2, False), (1, True), (1, False)):
+        assert np.array_equal(res[key], base), key
+    for g in range(groups):
+        for o in range(outs):
+            truth = sum(ck.direct_convolve_delayed_fft(irs[g][o][i], xs[g * ins + i], B) for i in range(ins))
+            assert ck.rel_rms(base[g * outs + o], truth) <= tol * (1 if dtype == np.float32 else 10)
+
+
+def test_fused_hops_overlap_ragged_calls_and_resets(hb):
+    """Mode 2 with everything that interrupts a chain of overlapping hops: ragged calls through the staging rows, calls of several
+    blocks (hop batches), a reset, a new impulse response on the running engine, host-pointer calls in between -- bit-identical to
+    the same sequence in mode 0."""
+    import torch
+    from hisstools_library_b200.convolve import _Engine
+    B, L, ins = 256, 4000, 2
+    irs = [ck.synth_ir(L, 3300 + i) for i in range(ins)]
+    irs2 = [ck.synth_ir(L // 2, 3400 + i) for i in range(ins)]
+    calls = [B] * 20 + [100, B - 100] + [B] * 5 + [3 * B] + [B] * 7 + [17] + [B] * 9 + [2 * B - 17] + [B] * 30
+    n = sum(calls)
+    xs = np.stack([ck.synth_audio(n, 3300 + r) for r in range(ins)])
+    x = torch.from_numpy(xs).cuda()
+    res = {}
+    for mode in (0, 2):
+        e = _Engine(np.float32, 1, ins, 1, 2 * B, L, 0, 0, 0)
+        e.set_reset_offset(0)
+        e.set_hop_overlap(mode)
+        for i in range(ins):
+            e.set_ir(0, i, 0, irs[i], L)
+        y = torch.zeros((1, n), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        pos = 0
+        with torch.cuda.stream(stream):
+            for k, m in enumerate(calls):
+                if k == 30:
+                    torch.cuda.synchronize()
+                    e.reset()
+                if k == 45:
+                    torch.cuda.synchronize()
+                    e.set_ir_live(0, 1, 0, irs2[1], L // 2)
+                if k in (50, 51):
+                    torch.cuda.synchronize()
+                    yo = [np.zeros(m, np.float32)]
+                    e.process([np.ascontiguousarray(xs[r, pos:pos + m]) for r in range(ins)], yo, m)
+                    y[0, pos:pos + m] = torch.from_numpy(yo[0]).cuda()
+                    torch.cuda.synchronize()
+                else:
+                    e.process_device(x.data_ptr() + pos * 4, n, y.data_ptr() + pos * 4, n, m, False, stream.cuda_stream)
+                pos += m
+        torch.cuda.synchronize()
+        res[mode] = y.cpu().numpy()
+        e.close()
+    assert np.array_equal(res[0], res[2])
+
+
+@pytest.mark.parametrize("scheme,ins,outs,L", [((False, 1024, 0, 0, 0), 1, 1, 20000), ((False, 512, 0, 0, 0), 4, 2, 6000),
+                                               ((False, 256, 1024, 4096, 16384), 2, 1, 40000), ((True, 256, 1024, 4096, 16384), 1, 1, 30000)])
+def test_matrix_device_calls_overlap_between_calls(hb, scheme, ins, outs, L):
+    """hb_matrix_set_hop_overlap: device calls of one block on a matrix -- a uniform MonoConvolve / Convolver, the reference's
+    short-latency scheme (three fixed parts and the tail, every one a fused engine here) and the zero-latency one with its
+    direct-form head between the parts -- with the matrix's own stream (mode 1), any stream (mode 2) and no overlap (mode 0):
+    bit-identical samples, equal to float64 direct convolution."""
+    import torch
+    from hisstools_library_b200.convolve import _Matrix
+    blk = 256
+    hops = 200
+    n = hops * blk
+    irs = [[ck.synth_ir(L, 3500 + 10 * o + i) for i in range(ins)] for o in range(outs)]
+    xs = np.stack([ck.synth_audio(n, 3500 + r) for r in range(ins)])
+    x = torch.from_numpy(xs).cuda()
+    res = {}
+    for mode, own in ((0, False), (2, False), (1, True)):
+        m = _Matrix(1, ins, outs, L, scheme, np.float32, 0)
+        m.setResetOffset(0)
+        m.set_hop_overlap(mode)
+        for o in range(outs):
+            for i in range(ins):
+                assert int(m.set(0, i, o, irs[o][i], L, True)) == 0
+        y = torch.zeros((outs, n), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for h in range(hops):
+                assert m.process_device(x.data_ptr() + h * blk * 4, n, y.data_ptr() + h * blk * 4, n, blk, False, 0 if own else stream.cuda_stream)
+        torch.cuda.synchronize()
+        res[(mode, own)] = y.cpu().numpy()
+        m.close()
+    base = res[(0, False)]
+    assert np.array_equal(res[(2, False)], base)
+    assert np.array_equal(res[(1, True)], base)
+    lat = 0 if scheme[0] else scheme[1] // 2
+    for o in range(outs):
+        truth = sum(np.convolve(xs[i].astype(np.float64), irs[o][i].astype(np.float64))[:n] for i in range(ins))
+        truth = np.concatenate([np.zeros(lat), truth])[:n]
+        assert ck.rel_rms(base[o], truth) <= TOL32
