@@ -130,6 +130,9 @@ __global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArg
     const int twl_log2 = (int) g.log2n;
 
     // this rank's share of the (input, partition >= 2) products: spectra that are at least two hops old
+    // (these loads come from L2 and a product needs a few instructions: what a rank spends here is the latency of its loads, so
+    // the rows of U items are fetched together -- as many as the registers of this instance hold)
+    constexpr int U = MAXT == 256 ? (sizeof(T) == 4 ? 4 : 2) : 1;
     auto tail_products = [&]()
     {
         Cx<T> t[EPT];
@@ -137,32 +140,55 @@ __global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArg
         for (int e = 0; e < EPT; e++) t[e] = cx<T>(T(0), T(0));
         const uint32_t q0 = (uint32_t) ((uint64_t(rank) * fa.tail_items) / cs), q1 = (uint32_t) ((uint64_t(rank + 1) * fa.tail_items) / cs);
         const uint32_t pm2 = P > 2 ? P - 2 : 1;
-        for (uint32_t q = q0; q < q1; q++)
+        for (uint32_t qb = q0; qb < q1; qb += U)
+        {
+            Cx<T> hv[U][EPT], xv[U][EPT];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const uint32_t q = qb + u;
+                if (q < q1)
+                {
+                    const uint32_t in = q / pm2, p = 2 + (q - in * pm2);
+                    const uint32_t ch = grp * g.ins + in;
+                    uint32_t sl = g.slot + p;
+                    if (sl >= R) sl -= R;
+                    const Cx<T> *hp = H + (((size_t(tile) * g.ins + in) * g.Pcap + p) * g.OT + row) * B;
+                    const Cx<T> *xp = X + (size_t(ch) * R + sl) * B;
+#pragma unroll
+                    for (int e = 0; e < EPT; e++)
+                    {
+                        const uint32_t k = tid + e * nthr;
+                        if (k < B) { hv[u][e] = hp[k]; xv[u][e] = ld_l2(xp + k); }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (qb + u < q1)
+                {
+#pragma unroll
+                    for (int e = 0; e < EPT; e++)
+                    {
+                        const uint32_t k = tid + e * nthr;
+                        if (k < B)
+                        {
+                            t[e].x = fma(xv[u][e].x, hv[u][e].x, t[e].x); t[e].x = fma(-xv[u][e].y, hv[u][e].y, t[e].x);
+                            t[e].y = fma(xv[u][e].x, hv[u][e].y, t[e].y); t[e].y = fma(xv[u][e].y, hv[u][e].x, t[e].y);
+                        }
+                    }
+                }
+            }
+        }
+        // the Nyquist products of these items, one item per thread (summed over the block further down)
+        for (uint32_t q = q0 + tid; q < q1; q += nthr)
         {
             const uint32_t in = q / pm2, p = 2 + (q - in * pm2);
             const uint32_t ch = grp * g.ins + in;
             uint32_t sl = g.slot + p;
             if (sl >= R) sl -= R;
-            const Cx<T> *hp = H + (((size_t(tile) * g.ins + in) * g.Pcap + p) * g.OT + row) * B;
-            const Cx<T> *xp = X + (size_t(ch) * R + sl) * B;
-            Cx<T> hv[EPT], xv[EPT];
-#pragma unroll
-            for (int e = 0; e < EPT; e++)
-            {
-                const uint32_t k = tid + e * nthr;
-                if (k < B) { hv[e] = hp[k]; xv[e] = ld_l2(xp + k); }
-            }
-#pragma unroll
-            for (int e = 0; e < EPT; e++)
-            {
-                const uint32_t k = tid + e * nthr;
-                if (k < B)
-                {
-                    t[e].x = fma(xv[e].x, hv[e].x, t[e].x); t[e].x = fma(-xv[e].y, hv[e].y, t[e].x);
-                    t[e].y = fma(xv[e].x, hv[e].y, t[e].y); t[e].y = fma(xv[e].y, hv[e].x, t[e].y);
-                }
-            }
-            if (tid == 0) nyq_tail += __ldcg(Xnyq + size_t(ch) * R + sl) * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
+            nyq_tail += __ldcg(Xnyq + size_t(ch) * R + sl) * Hnyq[(size_t(cl) * g.ins + in) * g.Pcap + p];
         }
 #pragma unroll
         for (int e = 0; e < EPT; e++)
@@ -356,31 +382,56 @@ __global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArg
         if (k < B) { const Cx<T> t = xch[k]; acc[e] = cx<T>(t.x + acc[e].x, t.y + acc[e].y); xch[k] = acc[e]; }
     }
     const T nyq_sum = block_sum<T>(nyq_tail + nyq, red);
-    if (tid == 0) nyq_part = nyq_sum;
-    cluster.sync();
-    trace_mark(g, 2, 0);                                        // first cluster barrier passed
-    if (rank == 0)
+    if (cs == 1)
     {
-        T nyq_total = nyq_sum;
-        for (uint32_t r = 1; r < cs; r++)
-        {
-            const Cx<T> *rx = cluster.map_shared_rank(xch, r);
-#pragma unroll
-            for (int e = 0; e < EPT; e++)
-            {
-                const uint32_t k = tid + e * nthr;
-                if (k < B) { const Cx<T> v = rx[k]; acc[e].x += v.x; acc[e].y += v.y; }
-            }
-            nyq_total += *cluster.map_shared_rank(&nyq_part, r);
-        }
+        // a single CTA: the sums are complete in registers (block_sum's barriers separate the last reads of s from these writes)
 #pragma unroll
         for (int e = 0; e < EPT; e++)
         {
             const uint32_t k = tid + e * nthr;
-            if (k < B) s[sidx<HB_PADSH>(k)] = k ? acc[e] : cx<T>(acc[e].x, nyq_total);
+            if (k < B) s[sidx<HB_PADSH>(k)] = k ? acc[e] : cx<T>(acc[e].x, nyq_sum);
+        }
+        __syncthreads();
+        trace_mark(g, 2, 0);
+    }
+    else
+    {
+    if (tid == 0) nyq_part = nyq_sum;
+    cluster.sync();
+    trace_mark(g, 2, 0);                                        // first cluster barrier passed
+    // Every rank sums its slice of the bins over all ranks (in rank order, whoever does it) and stores it into rank 0's work array:
+    // the reads through distributed shared memory are spread over the SMs of the cluster instead of queueing on one.
+    {
+        __shared__ T nq[16];
+        T nyq_total = T(0);
+        if (rank == 0)
+        {
+            if (tid < cs) nq[tid] = *cluster.map_shared_rank(&nyq_part, tid);
+            __syncthreads();
+            for (uint32_t r = 0; r < cs; r++) nyq_total += nq[r];
+        }
+        const uint32_t lo = (uint32_t) (uint64_t(rank) * B / cs), hi = (uint32_t) (uint64_t(rank + 1) * B / cs);
+        Cx<T> *s0 = cluster.map_shared_rank(s, 0);
+        constexpr int RB = sizeof(T) == 4 ? 8 : 4;                  // reads in flight per bin
+        for (uint32_t k = lo + tid; k < hi; k += nthr)
+        {
+            Cx<T> a = cx<T>(T(0), T(0));
+            for (uint32_t r0 = 0; r0 < cs; r0 += RB)
+            {
+                Cx<T> v[RB];
+#pragma unroll
+                for (int j = 0; j < RB; j++)
+                    if (r0 + j < cs) v[j] = cluster.map_shared_rank(xch, r0 + j)[k];
+#pragma unroll
+                for (int j = 0; j < RB; j++)
+                    if (r0 + j < cs) { a.x += v[j].x; a.y += v[j].y; }
+            }
+            if (k == 0) a.y = nyq_total;
+            s0[sidx<HB_PADSH>(k)] = a;
         }
     }
     cluster.sync();                                             // remote shared memory may go away from here on
+    }
     trace_mark(g, 2, 1);                                        // reduction done
     if (rank != 0) { trace_mark(g, 0, 1); return; }
 
