@@ -12,4 +12,4 @@ from .fft import (Split, Setup, hisstools_create_setup, hisstools_destroy_setup,
                   hisstools_unzip_zero)
 from .convolve import PartitionedConvolve, MonoConvolve, NToMonoConvolve, Convolver, partition_scheme   # noqa: F401
 from .spectral import spectral_processor, EdgeMode                                                   # noqa: F401
-from .audiofile import IAudioFile                                                                  # noqa: F401
+from .audiofile import IAudioFile, OAudioFile                                                                  # noqa: F401

@@ -89,6 +89,14 @@ SIGNATURES = {
     "hb_spectral_correlate_complex": (C.c_int, [V, V, V, V, UP, V, UP, V, UP, V, UP, C.c_int, C.POINTER(UP)]),
     "hb_audio_probe": (C.c_int, [C.c_char_p, V]),
     "hb_audio_read": (C.c_int, [C.c_char_p, U32, U32, C.c_int32, V, C.c_int, C.c_int]),
+    "hb_audio_read_raw": (C.c_int, [C.c_char_p, U32, U32, V]),
+    "hb_audio_writer_open": (C.c_int, [C.POINTER(V), C.c_char_p, C.c_int, C.c_int, U32, C.c_double, C.c_int]),
+    "hb_audio_writer_write": (C.c_int, [V, V, C.c_int, U32, C.c_int32]),
+    "hb_audio_writer_write_raw": (C.c_int, [V, V, U32]),
+    "hb_audio_writer_seek": (C.c_int, [V, U32]),
+    "hb_audio_writer_position": (U32, [V]),
+    "hb_audio_writer_info": (C.c_int, [V, V, C.POINTER(C.c_int)]),
+    "hb_audio_writer_close": (None, [V]),
     "hb_audio_decode_dev": (C.c_int, [V, V, C.c_uint64, C.c_int32, V, C.c_uint64, C.c_int, C.c_int, V]),
     "hb_conv_set_ir_file": (C.c_int, [V, U32, U32, U32, C.c_char_p, U32, C.c_int]),
     "hb_conv_dtype": (C.c_int, [V]),

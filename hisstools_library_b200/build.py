@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIBNAME = "libhisstools_b200.so"
-SOURCES = ["hb_fft.cu", "hb_conv.cu", "hb_conv_mh.cu", "hb_matrix.cu", "hb_spectral.cu", "hb_audio.cu"]
+SOURCES = ["hb_fft.cu", "hb_conv.cu", "hb_conv_mh.cu", "hb_matrix.cu", "hb_spectral.cu", "hb_audio.cu", "hb_audio_out.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "1886"]
 

@@ -1,7 +1,7 @@
 // AudioFile/IAudioFile.h -- B200 drop-in for the reading half of the reference's AudioFile component
 // (AudioFile/IAudioFile.h:30-54 + the BaseAudioFile getters, BaseAudioFile.h:64-90): WAV / AIFF / AIFC files
 // as the source of impulse responses for Convolver::set.  Header-only; forwards to hb_audio_* of hisstools_b200.h
-// (header parsing on the host, PCM decoding on the GPU).  readRaw and the writer (OAudioFile) are not provided.
+// (header parsing on the host, PCM decoding on the GPU).  The writer is AudioFile/OAudioFile.h.
 #ifndef HISSTOOLS_B200_IAUDIOFILE_H
 #define HISSTOOLS_B200_IAUDIOFILE_H
 
@@ -63,6 +63,12 @@ namespace HISSTools
         void seek(FrameCount position = 0) { mPosition = position; }
         FrameCount getPosition() { return mPosition; }
 
+        void readRaw(void* output, FrameCount numFrames)
+        {
+            if (!mOpen || !numFrames) return;
+            if (hb_audio_read_raw(mPath.c_str(), mPosition, numFrames, output) < 0) throw std::runtime_error(hb_last_error());
+            mPosition += numFrames;
+        }
         void readInterleaved(double* output, FrameCount numFrames) { read(output, numFrames, -1, HB_F64); }
         void readInterleaved(float* output, FrameCount numFrames) { read(output, numFrames, -1, HB_F32); }
         void readChannel(double* output, FrameCount numFrames, uint16_t channel) { read(output, numFrames, channel, HB_F64); }

@@ -397,6 +397,31 @@ int hb_audio_read(const char *path, uint32_t first_frame, uint32_t frames, int32
  * writes that channel to d_out[0 .. frames), channel < 0 writes every channel c to row d_out + c * ld (planar). */
 int hb_audio_decode_dev(const hb_audio_info *info, const void *d_raw, uint64_t frames, int32_t channel, void *d_out, uint64_t ld,
                         int out_dtype, int device, void *stream);
+/* seek(first_frame) then readRaw(out, frames): IAudioFile.cpp:74-88 -- the frames as the file stores them (host memory,
+ * frames x channels x bytes per sample).  Host code only. */
+int hb_audio_read_raw(const char *path, uint32_t first_frame, uint32_t frames, void *out);
+
+/* ---- OAudioFile (AudioFile/OAudioFile.h:18-30): the writer.  Host code only; files are byte-identical to the reference's. ----
+ * open(path, type, format, channels, sr[, endianness]): OAudioFile.cpp:41-71.  file_type 1 AIFF (written as AIFC, :58), 2 AIFC,
+ * 3 WAVE; pcm_format 0 int8 .. 3 int32, 4 float32, 5 float64 (BaseAudioFile.h:23-33); big_endian -1 = the type's default (WAVE
+ * little, AIFC big), 0 little (RIFF, or AIFC with little-endian samples -- tagged "NONE" as the reference tags it), 1 big (RIFX).
+ * Always returns a handle; a file that could not be opened shows in hb_audio_writer_info (is_open 0, error flag 4). */
+typedef struct hb_audio_writer hb_audio_writer;
+int hb_audio_writer_open(hb_audio_writer **w, const char *path, int file_type, int pcm_format, uint32_t channels, double rate, int big_endian);
+/* writeInterleaved (channel < 0: frames x channels samples) / writeChannel (channel >= 0: frames samples into that channel, the
+ * other channels keep what they hold, silence past the old end): OAudioFile.cpp:102-120, 587-682.  in_dtype HB_F32 / HB_F64.
+ * Integer formats round half away from zero and wrap instead of clipping (:566-576); 8-bit WAVE is unsigned and clipped (:578-585). */
+int hb_audio_writer_write(hb_audio_writer *w, const void *in, int in_dtype, uint32_t frames, int32_t channel);
+/* writeRaw: frames as the file stores them (OAudioFile.h:30) */
+int hb_audio_writer_write_raw(hb_audio_writer *w, const void *raw, uint32_t frames);
+/* seek / getPosition in frames (OAudioFile.cpp:84-96) */
+int hb_audio_writer_seek(hb_audio_writer *w, uint32_t frame);
+uint32_t hb_audio_writer_position(hb_audio_writer *w);
+/* the BaseAudioFile getters of the open file (frames written so far, error flags) and isOpen() */
+int hb_audio_writer_info(const hb_audio_writer *w, hb_audio_info *info, int *is_open);
+/* close() and release the handle */
+void hb_audio_writer_close(hb_audio_writer *w);
+
 /* file -> spectra without a host float array: channel `channel` of the file becomes the impulse response of pair
  * (group, in, out) of a uniform engine (hb_conv_set_ir_dev on the decoded device row). */
 int hb_conv_set_ir_file(hb_conv *c, uint32_t group, uint32_t in, uint32_t out, const char *path, uint32_t channel, int device);

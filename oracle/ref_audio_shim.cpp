@@ -66,3 +66,43 @@ static int audio_read(const char *path, uint32_t first, uint32_t frames, int cha
 
 SHIM int ref_audio_read_f32(const char *path, uint32_t first, uint32_t frames, int channel, float *out) { return audio_read<float>(path, first, frames, channel, out); }
 SHIM int ref_audio_read_f64(const char *path, uint32_t first, uint32_t frames, int channel, double *out) { return audio_read<double>(path, first, frames, channel, out); }
+
+// ---- the writer as a session (tests/test_audio_writer.py: files written call by call by the reference and by hb_audio_writer_*) ----
+SHIM void *ref_oaudio_open(const char *path, int type, int pcm, int channels, double rate, int big_endian)
+{
+    OAudioFile *f = new OAudioFile;
+    if (big_endian < 0)
+        f->open(path, static_cast<BaseAudioFile::FileType>(type), static_cast<BaseAudioFile::PCMFormat>(pcm), (uint16_t) channels, rate);
+    else
+        f->open(path, static_cast<BaseAudioFile::FileType>(type), static_cast<BaseAudioFile::PCMFormat>(pcm), (uint16_t) channels, rate,
+                big_endian ? BaseAudioFile::kAudioFileBigEndian : BaseAudioFile::kAudioFileLittleEndian);
+    return f;
+}
+SHIM void ref_oaudio_write_f64(void *h, const double *in, uint32_t frames, int channel)
+{
+    OAudioFile *f = static_cast<OAudioFile *>(h);
+    if (channel < 0) f->writeInterleaved(in, frames); else f->writeChannel(in, frames, (uint16_t) channel);
+}
+SHIM void ref_oaudio_write_f32(void *h, const float *in, uint32_t frames, int channel)
+{
+    OAudioFile *f = static_cast<OAudioFile *>(h);
+    if (channel < 0) f->writeInterleaved(in, frames); else f->writeChannel(in, frames, (uint16_t) channel);
+}
+SHIM void ref_oaudio_write_raw(void *h, const char *in, uint32_t frames) { static_cast<OAudioFile *>(h)->writeRaw(in, frames); }
+SHIM void ref_oaudio_seek(void *h, uint32_t frame) { static_cast<OAudioFile *>(h)->seek(frame); }
+SHIM uint32_t ref_oaudio_position(void *h) { return static_cast<OAudioFile *>(h)->getPosition(); }
+SHIM uint32_t ref_oaudio_frames(void *h) { return static_cast<OAudioFile *>(h)->getFrames(); }
+SHIM int ref_oaudio_flags(void *h) { return static_cast<OAudioFile *>(h)->getErrorFlags(); }
+SHIM int ref_oaudio_is_open(void *h) { return static_cast<OAudioFile *>(h)->isOpen(); }
+SHIM int ref_oaudio_file_type(void *h) { return static_cast<OAudioFile *>(h)->getFileType(); }
+SHIM void ref_oaudio_close(void *h) { delete static_cast<OAudioFile *>(h); }
+
+// seek(first) then readRaw: the frames as stored
+SHIM int ref_audio_read_raw(const char *path, uint32_t first, uint32_t frames, void *out)
+{
+    IAudioFile f(path);
+    if (!f.isOpen() || f.getIsError()) return f.getErrorFlags() ? f.getErrorFlags() : -1;
+    f.seek(first);
+    f.readRaw(out, frames);
+    return 0;
+}

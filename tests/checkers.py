@@ -232,6 +232,27 @@ def ref_audio():
         lib.ref_audio_read_f32.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, c_f32p]
         lib.ref_audio_read_f64.restype = C.c_int
         lib.ref_audio_read_f64.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, c_f64p]
+        if hasattr(lib, "ref_oaudio_open"):
+            lib.ref_oaudio_open.restype = C.c_void_p
+            lib.ref_oaudio_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+            lib.ref_oaudio_write_f64.restype = None
+            lib.ref_oaudio_write_f64.argtypes = [C.c_void_p, c_f64p, C.c_uint32, C.c_int]
+            lib.ref_oaudio_write_f32.restype = None
+            lib.ref_oaudio_write_f32.argtypes = [C.c_void_p, c_f32p, C.c_uint32, C.c_int]
+            lib.ref_oaudio_write_raw.restype = None
+            lib.ref_oaudio_write_raw.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+            lib.ref_oaudio_seek.restype = None
+            lib.ref_oaudio_seek.argtypes = [C.c_void_p, C.c_uint32]
+            for name in ("ref_oaudio_position", "ref_oaudio_frames"):
+                getattr(lib, name).restype = C.c_uint32
+                getattr(lib, name).argtypes = [C.c_void_p]
+            for name in ("ref_oaudio_flags", "ref_oaudio_is_open", "ref_oaudio_file_type"):
+                getattr(lib, name).restype = C.c_int
+                getattr(lib, name).argtypes = [C.c_void_p]
+            lib.ref_oaudio_close.restype = None
+            lib.ref_oaudio_close.argtypes = [C.c_void_p]
+            lib.ref_audio_read_raw.restype = C.c_int
+            lib.ref_audio_read_raw.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _ref_audio = lib
     return _ref_audio
 

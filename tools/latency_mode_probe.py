@@ -40,6 +40,16 @@ def main():
         e1.record(st)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        # end to end: host rows in, host rows out (hb_matrix_process: what Convolver::process costs a caller), wall clock
+        xh = [np.ascontiguousarray(r) for r in x.cpu().numpy()]
+        yh = [np.zeros(n, np.float32) for _ in range(outs)]
+        for _ in range(3):
+            m.process(xh, yh, n, False)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.process(xh, yh, n, False)
+        ms_host = (time.perf_counter() - t0) / steps * 1e3
+        print("%-18s end to end from host rows: %.3f ms per block = %.1f M output-samples/s" % (name, ms_host, outs * n / ms_host / 1e3))
         print("%-18s %dx%d, %d taps, blocks of %d: %.3f ms per block = %.1f M output-samples/s  (IR load %.1f s; parts %s, head %d taps; schedules %s)" %
               (name, ins, outs, taps, n, ms, outs * n / ms / 1e3, t_set, [e.fft_size for e in m.engines], m.head_taps, [e.schedule for e in m.engines]))
         m.close()
