@@ -138,6 +138,7 @@ struct hb_conv
     int fft_path = 0;               // hb_conv_set_fft_path: 0 automatic, 1 one CTA per transform, 2 cluster of 8 CTAs, 3 four-step
     BigScratch big;                 // four-step scratch for FFT sizes above the single-CTA limit (hb_conv_big.cuh)
     DevBuf d_nyq;
+    DevBuf d_part;                  // fused multi-GPU exchange at four-step sizes: this rank's partial blocks before delivery
 
     // deferred host-pointer path of hb_conv_process: the block finished by a hop is fetched to pinned host
     // memory while the caller is away; a later call only waits on an event that completed long ago
@@ -377,7 +378,7 @@ void free_device(hb_conv *c)
     c->d_H = c->d_X = c->d_Hnyq = c->d_Xnyq = c->d_tw = nullptr;
     c->d_S.release();
     c->d_St[0].release(); c->d_St[1].release(); c->d_trace.release();
-    c->big.release(); c->d_nyq.release(); c->d_Smh.release();
+    c->big.release(); c->d_nyq.release(); c->d_Smh.release(); c->d_part.release(); c->d_chain.release();
     if (c->s_tail) cudaStreamDestroy(c->s_tail);
     if (c->s_tail_b) cudaStreamDestroy(c->s_tail_b);
     c->s_tail_b = nullptr;
@@ -692,8 +693,17 @@ int launch_inv(hb_conv *c, const SegSets &sets, const InvIO<T> &io, cudaStream_t
 {
     if (is_big<T>(c))
     {
-        if (peer.world) { set_error("the fused multi-GPU exchange is not implemented for FFT sizes above the single-CTA limit"); return HB_ERR_UNSUPPORTED; }
-        return launch_inv_big<T>(c, sets, io, st);
+        if (!peer.world) return launch_inv_big<T>(c, sets, io, st);
+        // fused multi-GPU exchange: the chain leaves the partial blocks of all outputs in a local buffer, k_shard_deliver hands them on
+        const Geom &g = c->g;
+        const size_t rows = size_t(g.groups) * g.outs;
+        int rc = c->d_part.ensure(rows * g.B * sizeof(T));
+        if (rc) return rc;
+        const InvIO<T> local = {(T *) c->d_part.p, g.B, 0, 0, nullptr, 0, nullptr, 0, 0};
+        if ((rc = launch_inv_big<T>(c, sets, local, st))) return rc;
+        k_shard_deliver<T><<<(unsigned) rows, 256, 0, st>>>((const T *) c->d_part.p, g.B, peer, g.B);
+        HB_LAUNCH_CHECK();
+        return HB_OK;
     }
     if (nh == 1 && ib.last_j < 0 && !peer.world && use_cluster_fft(c)) return launch_inv_cl<T>(c, sets, io, st);
     HB_EPT_DISPATCH(c->g.log2n - 1, return launch_inv_ept<T, EPT>(c, sets, io, st, peer, nh, ib));

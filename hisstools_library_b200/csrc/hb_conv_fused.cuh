@@ -59,7 +59,7 @@ struct FusedArgs
 };
 
 // one thread's wait for a counter of the hop chain (the hop that bumps it was launched earlier on this stream and is resident
-// or finished, so the wait is short; a wait of seconds means a broken chain and stops the context instead of hanging the device)
+// or finished, so the wait is short; a wait of half a minute means a broken chain and stops the context instead of hanging the device)
 __device__ __forceinline__ void chain_wait(const unsigned long long *p, unsigned long long target)
 {
     if (!target) return;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void chain_wait(const unsigned long long *p, unsigned
         {
             const unsigned long long t = global_ns();
             if (!t0) t0 = t;
-            else if (t - t0 > 2000000000ull) __trap();
+            else if (t - t0 > 30000000000ull) __trap();            // 30 s
         }
     }
 }

@@ -1026,6 +1026,27 @@ __global__ void __launch_bounds__(256) k_shard_silence(const PeerOut peer, uint3
     }
 }
 
+// The fused exchange at FFT sizes above the single-CTA limit: the inverse transform is a chain of launches (hb_conv_big.cuh) whose
+// last kernel has many CTAs per row, so it leaves this rank's partial blocks in a local buffer and this kernel -- one CTA per output
+// channel, as the epilogue of k_inv -- delivers each block to its owner's inbox and counts the arrival.
+template <class T>
+__global__ void __launch_bounds__(256) k_shard_deliver(const T *__restrict__ part, size_t ld, const PeerOut peer, uint32_t B)
+{
+    const uint32_t ch = blockIdx.x;
+    const uint32_t owner = ch / peer.outs_local, o_loc = ch - owner * peer.outs_local;
+    const uint32_t par = peer.parity % HB_INBOX_DEPTH;
+    T *pd = reinterpret_cast<T *>(peer.data[owner]) + ((size_t(par) * peer.world + peer.rank) * peer.outs_local + o_loc) * peer.slot;
+    const T *src = part + size_t(ch) * ld;
+    for (uint32_t k = threadIdx.x; k < B; k += blockDim.x) pd[k] = src[k];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        atomicAdd_system(peer.count[owner] + par * peer.world + peer.rank, 1u);
+    }
+}
+
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;

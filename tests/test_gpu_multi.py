@@ -69,6 +69,34 @@ def test_multi_device_matrix_matches_one_device(world, scheme, exchange, delay):
         assert ck.rel_rms(outs[False][o], truth) <= TOL32
 
 
+def test_multi_device_matrix_with_partitions_above_one_cta():
+    """A uniform scheme of 65536-point FFTs (32768-sample partitions: above the one-CTA transform limit, so the transforms are
+    four-step chains) keeps the fused exchange: the chain leaves this rank's partial blocks in a local buffer and k_shard_deliver
+    hands them to their owners.  4 x 4 matrix on two GPUs against one GPU and float64 direct convolution, ragged calls."""
+    if 2 not in _worlds():
+        pytest.skip("needs 2 GPUs")
+    import hisstools_library_b200 as hb
+    n_in = n_out = 4
+    B, L = 32768, 70000
+    irs = [[ck.synth_ir(L, 1500 + 10 * o + i) for i in range(n_in)] for o in range(n_out)]
+    xs = np.stack([ck.synth_audio(B * 4 + 1234, 1500 + i) for i in range(n_in)])
+    sizes = [B, 5000, B - 5000, 2 * B, 1234]
+    outs = {}
+    for devices in (None, [0, 1]):
+        cv = hb.Convolver(n_in, n_out, False, 2 * B, maxLength=L, devices=devices)
+        cv.setResetOffset(0)
+        for o in range(n_out):
+            for i in range(n_in):
+                assert cv.set(i, o, irs[o][i], L, False) == 0
+        if devices is not None:
+            assert cv.matrix.exchange == "fused"
+        outs[devices is None] = _stream(cv, xs, n_out, sizes)
+    for o in range(n_out):
+        assert ck.rel_rms(outs[False][o], outs[True][o]) <= 2e-6
+        truth = sum(ck.direct_convolve_delayed_fft(irs[o][i], xs[i], B) for i in range(n_in))
+        assert ck.rel_rms(outs[False][o], truth) <= TOL32
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_device_parallel_banks_and_double(world):
     """Convolver(numIO, ...) dealt to the GPUs bank by bank (no exchange), double engine included."""
