@@ -115,6 +115,16 @@ struct MhCursor
 // IPS = work items per step: one CTA-wide barrier per step.  A step has fixed costs (the barrier and its skew, the exposed
 // shared-memory latency behind it, the preparation of the next tiles: ~600 cycles measured) against 128 FFMA2 per warp and
 // item (>= 512 cycles of the FMA pipe), so the 16 KiB half-unit items of NH = 8 are taken two per step.
+// The step barrier of the warp-specialised part: producer, idle and consumer warps arrive from different places in the code, which
+// __syncthreads() does not allow formally (compute-sanitizer synccheck: "divergent threads in block") although it is the same
+// hardware barrier; a named barrier with an explicit thread count is the form made for this.
+__device__ __forceinline__ void step_barrier()
+{
+    // (barrier.sync without .aligned: the lanes of the producer warp may not have reconverged behind the elected lane's copies)
+    __syncwarp();
+    asm volatile("barrier.sync 1, %0;" ::"r"(blockDim.x) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(NH == 8 ? 384 : 288, 1) k_cmac_mh2(const Geom 
         if (tid >= 288)
         {
             // warps 9-11 only exist to make the producer's warpgroup whole: they keep the step barriers
-            for (uint32_t t = 0; t < nsteps; t++) __syncthreads();
+            for (uint32_t t = 0; t < nsteps; t++) step_barrier();
             return;
         }
         // ---- producer warp: all 32 lanes walk the cursor (warp-uniform values), one elected lane issues ----
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(NH == 8 ? 384 : 288, 1) k_cmac_mh2(const Geom 
             // stage (t + nstages - 1) % nstages was drained in step t-1 (barrier at the end of that step)
             if (issued < nsteps) issue(stage ? stage - 1 : nstages - 1);
             if (++stage == (uint32_t) nstages) stage = 0;
-            __syncthreads();
+            step_barrier();
         }
         return;
     }
@@ -338,7 +348,7 @@ __global__ void __launch_bounds__(NH == 8 ? 384 : 288, 1) k_cmac_mh2(const Geom 
             }
         }
         if (++stage == (uint32_t) nstages) { stage = 0; parity ^= 1; }
-        __syncthreads();                                              // stage t is free for the producer
+        step_barrier();                                               // stage t is free for the producer
     }
     trace_mark(g, rg.kind, 1);
 }
