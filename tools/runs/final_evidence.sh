@@ -1,5 +1,5 @@
 #!/bin/bash
-# Run on the GPU box (under gpurun): the round's final captures and bench lines.  usage: tools/final_evidence.sh <tag>
+# Run on the GPU box (under gpurun): the round's final captures and bench lines.  usage: tools/runs/final_evidence.sh <tag>
 TAG=${1:-r1f}
 mkdir -p gpurun_out
 bash tools/profile_gpu.sh $TAG c5 c4

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools/sweep_gpu.sh <tag>   -- schedule / ring-depth comparison on one GPU (bench lines under gpurun_out/)
+# usage: tools/runs/sweep_gpu.sh <tag>   -- schedule / ring-depth comparison on one GPU (bench lines under gpurun_out/)
 TAG=${1:-rX}
 mkdir -p gpurun_out
 run() { # name, env..., -- args
