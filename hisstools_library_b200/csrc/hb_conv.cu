@@ -117,6 +117,9 @@ struct hb_conv
     unsigned long long chain_n = 0; // fused hops launched since the counters were zeroed
     bool chain_ok = false;          // the last thing this engine enqueued was a fused hop, on chain_stream
     cudaStream_t chain_stream = nullptr;
+    struct ByteRange { const char *b = nullptr, *e = nullptr; };
+    ByteRange chain_out[16];        // rows the last fused hops write (block handed over + block kept): a hop whose input rows touch one of
+    uint32_t chain_out_pos = 0;     // them is fed by a hop that may still be running and keeps the strict order
     Range r_full{}, r_head{}, r_tail{};
     DevBuf d_St[2];                 // tail partial segments, double-buffered over hops
     cudaStream_t s_tail = nullptr, s_tail_b = nullptr;
@@ -737,6 +740,21 @@ int launch_fused_t(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     // nothing by the caller if the stream is the caller's -- which is what hop_overlap = 2 declares) and may run beside it
     const bool overlap_allowed = c->hop_overlap == 2 || (c->hop_overlap == 1 && st == c->stream);
     fa.chained = (overlap_allowed && c->chain_ok && c->chain_stream == st && c->chain_n > 0) ? 1u : 0u;
+    // a call fed with the output rows of one of the last calls (the engine in a feedback loop) relies on stream order for its input
+    {
+        const size_t rows_in = size_t(g.groups) * g.ins, rows_out = size_t(g.groups) * g.outs;
+        const char *ib = (const char *) newest, *ie = (const char *) (newest + (rows_in - 1) * new_ld + B);
+        for (const hb_conv::ByteRange &r : c->chain_out)
+            if (r.b && ib < r.e && r.b < ie) fa.chained = 0;
+        auto note = [&](const T *p, size_t ld)
+        {
+            hb_conv::ByteRange &r = c->chain_out[c->chain_out_pos++ % 16];
+            r.b = (const char *) p;
+            r.e = p ? (const char *) (p + (rows_out - 1) * ld + B) : nullptr;
+        };
+        note(io.carry_dst, io.carry_dst_ld);
+        note(io.yout ? io.yout + io.off : nullptr, io.ld);
+    }
     // only hops that a chained hop may follow take part in the count (the fences of the counter updates cost a strict hop about a
     // microsecond): chain_n numbers those, and a chained hop always follows one of them directly
     fa.bump = overlap_allowed ? 1u : 0u;
@@ -1335,6 +1353,7 @@ int process_core(hb_conv *c, const T *d_in, size_t in_ld, T *d_out, size_t out_l
         if ((rc = hop(xin + h * B, c->xin_ld, xin + (h + 1) * B, c->xin_ld, nullptr, 0, io))) return rc;
     }
     if (d_out && (rc = launch_rows<T>(d_out, out_ld, yout + rw, c->yout_ld, n, rows_out, accumulate, st))) return rc;
+    c->chain_ok = false;
 
     c->rw = (rw + n) - nh * B;
     c->x_tail = nh * B;

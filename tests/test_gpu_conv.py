@@ -1037,3 +1037,40 @@ def test_matrix_device_calls_overlap_between_calls(hb, scheme, ins, outs, L):
         truth = sum(np.convolve(xs[i].astype(np.float64), irs[o][i].astype(np.float64))[:n] for i in range(ins))
         truth = np.concatenate([np.zeros(lat), truth])[:n]
         assert ck.rel_rms(base[o], truth) <= TOL32
+
+
+def test_fused_hops_fed_with_their_own_output_keep_stream_order(hb):
+    """An engine in a feedback loop -- the output rows of call t are the input rows of call t+1, nothing else in between -- relies on
+    stream order for its input: such calls are recognised by their row addresses and keep the strict order even where overlapping
+    hops are allowed (mode 2, and the engine's own stream in mode 1).  Bit-identical to mode 0."""
+    import torch
+    from hisstools_library_b200.convolve import _Engine
+    B, L, hops = 256, 1500, 60
+    ir = (ck.synth_ir(L, 3600) * 0.2).astype(np.float32)
+    first = ck.synth_audio(B, 3600)
+    res = {}
+    for mode, own in ((0, False), (2, False), (1, True)):
+        e = _Engine(np.float32, 1, 1, 1, 2 * B, L, 0, 0, 0)
+        e.set_reset_offset(0)
+        e.set_hop_overlap(mode)
+        e.set_ir(0, 0, 0, ir, L)
+        ring = torch.zeros((3, B), dtype=torch.float32, device="cuda")
+        ring[0] = torch.from_numpy(first).cuda()
+        keep = torch.zeros((hops, B), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for t in range(hops):
+                e.process_device(ring[t % 3].data_ptr(), B, ring[(t + 1) % 3].data_ptr(), B, B, False, 0 if own else stream.cuda_stream)
+                if t % 7 == 6:
+                    # now and then look at the rows (on the engine's own stream the caller has to wait for it first)
+                    torch.cuda.synchronize()
+                    keep[t] = ring[(t + 1) % 3]
+                    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        res[(mode, own)] = (keep.cpu().numpy(), ring.cpu().numpy())
+        e.close()
+    for key in ((2, False), (1, True)):
+        assert np.array_equal(res[key][0], res[(0, False)][0])
+        assert np.array_equal(res[key][1], res[(0, False)][1])
+    assert np.abs(res[(0, False)][1]).max() > 0
