@@ -116,6 +116,7 @@ struct hb_conv
     DevBuf d_chain;                 // the three counters of the hop chain (+ padding)
     unsigned long long chain_n = 0; // fused hops launched since the counters were zeroed
     bool chain_ok = false;          // the last thing this engine enqueued was a fused hop, on chain_stream
+    bool last_hop_chained = false;  // the last fused hop launched ran in the chained order (it did not wait for its predecessor up front)
     cudaStream_t chain_stream = nullptr;
     struct ByteRange { const char *b = nullptr, *e = nullptr; };
     ByteRange chain_out[16];        // rows the last fused hops write (block handed over + block kept): a hop whose input rows touch one of
@@ -758,6 +759,7 @@ int launch_fused_t(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     // only hops that a chained hop may follow take part in the count (the fences of the counter updates cost a strict hop about a
     // microsecond): chain_n numbers those, and a chained hop always follows one of them directly
     fa.bump = overlap_allowed ? 1u : 0u;
+    fa.tail_early = c->last_hop_chained ? 0u : 1u;
     fa.writers = g.groups * std::min<uint32_t>(cs, g.ins);
     fa.clusters = g.groups * g.outs;
     fa.depth = std::min<uint32_t>(g.R - g.P, 8u);
@@ -785,6 +787,7 @@ int launch_fused_t(hb_conv *c, const T *prev, size_t prev_ld, const T *newest, s
     HB_LAUNCH_CHECK();
     c->chain_ok = overlap_allowed;
     c->chain_stream = st;
+    c->last_hop_chained = fa.chained != 0;
     return HB_OK;
 }
 

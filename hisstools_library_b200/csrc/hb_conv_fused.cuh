@@ -20,7 +20,8 @@
 //  strict   (any stream; what a caller gets who only promises stream order for its rows)
 //           before griddepcontrol.wait: twiddles into shared memory and the products of partitions p >= 2 -- they meet spectra
 //           that are at least two hops old, written by kernels that had completed before this one could start (a strict kernel
-//           releases its successor only after its own wait has returned);  after it: the caller's rows, the forward FFT,
+//           releases its successor only after its own wait has returned; behind a chained hop, which does not wait, these
+//           products run after the wait as well: FusedArgs::tail_early);  after it: the caller's rows, the forward FFT,
 //           partitions 0 and 1, the reduction, the inverse FFT and the store.
 //  chained  (the engine's own stream, or a caller that declares its rows complete when the call is made:
 //           hb_conv_set_hop_overlap)  no wait up front.  The hop depends on its predecessors through three counters in
@@ -51,6 +52,8 @@ struct FusedArgs
     uint32_t tail_items;       // ins * (P - 2): the products of partitions p >= 2
     uint32_t chained;          // 1: consecutive hops overlap (counters); 0: griddepcontrol.wait first
     uint32_t bump;             // 1: this hop counts (a chained hop may follow it); 0: nothing on this stream will look at the counters
+    uint32_t tail_early;       // strict order: 1 = the products of partitions >= 2 run before the wait (the hop before this one was strict
+                               // too, so the spectra two hops back are complete when this kernel starts); 0 = after it
     uint32_t writers;          // CTAs per hop that bump sync[0] and sync[1]: groups * min(cs, ins)
     uint32_t clusters;         // CTAs per hop that bump sync[2]: groups * outs
     uint32_t depth;            // hops that may be in flight behind the one whose delay-line slot is reused
@@ -231,11 +234,14 @@ __global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArg
     if (!chained)
     {
         twiddle_stage_store<T, EPT>(stw, twr, (int) g.log2n);
-        tail_products();
+        if (fa.tail_early) tail_products();
         trace_mark(g, 1, 0);
         // ================= the previous hop must be complete from here on; release the next one =================
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        // (a hop that a chained one may follow releases it only once the saved block is in shared memory, as a chained hop does:
+        // the successor saves its own block over it)
+        if (!fa.bump || rank >= g.ins) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (!fa.tail_early) tail_products();
         if (rank == 0) carry_load();
     }
     else
@@ -283,8 +289,8 @@ __global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArg
         {
             // every row this CTA reads from the previous hop's save area is in shared memory and its own blocks are saved
             if (tid == 0 && writer && fa.bump) chain_bump(fa.sync + 0);
-            if (chained) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-            else if (rank == 0) carry_store();
+            if (fa.bump) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            if (!chained && rank == 0) carry_store();
         }
         if (KEEP)
         {

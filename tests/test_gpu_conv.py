@@ -1074,3 +1074,46 @@ def test_fused_hops_fed_with_their_own_output_keep_stream_order(hb):
         assert np.array_equal(res[key][0], res[(0, False)][0])
         assert np.array_equal(res[key][1], res[(0, False)][1])
     assert np.abs(res[(0, False)][1]).max() > 0
+
+
+@pytest.mark.parametrize("ins,B,L", [(1, 1024, 65536), (8, 2048, 131072), (1, 512, 4096)])
+def test_fused_hops_strict_and_overlapping_hops_interleaved(hb, ins, B, L):
+    """Strict hops directly behind overlapping ones and the other way round, back to back in one stream: every few calls something
+    ends the chain without enqueuing anything (hb_conv_join, a mode change, a getter that takes the lock), so the next hop runs in the
+    strict order while its predecessors may still be in flight (its products of partitions >= 2 then wait as well).  400 calls on
+    engines with 8 to 64 partitions on clusters of up to 16: bit-identical to mode 0."""
+    import torch
+    from hisstools_library_b200.convolve import _Engine
+    hops = 400
+    n = hops * B
+    irs = [ck.synth_ir(L, 3700 + i) for i in range(ins)]
+    xs = np.stack([ck.synth_audio(n, 3700 + r) for r in range(ins)])
+    x = torch.from_numpy(xs).cuda()
+    res = {}
+    for mode in (0, 2):
+        e = _Engine(np.float32, 1, ins, 1, 2 * B, L, 0, 0, 0)
+        e.set_reset_offset(0)
+        e.set_hop_overlap(mode)
+        for i in range(ins):
+            e.set_ir(0, i, 0, irs[i], L)
+        y = torch.zeros((1, n), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for h in range(hops):
+                if mode and h % 3 == 2:
+                    e.join(stream.cuda_stream)
+                if mode and h % 50 == 25:
+                    e.set_hop_overlap(0)
+                if mode and h % 50 == 30:
+                    e.set_hop_overlap(2)
+                if mode and h % 7 == 0:
+                    assert e.tail_streams >= 0
+                e.process_device(x.data_ptr() + h * B * 4, n, y.data_ptr() + h * B * 4, n, B, False, stream.cuda_stream)
+        torch.cuda.synchronize()
+        assert e.schedule == "fused"
+        res[mode] = y.cpu().numpy()
+        e.close()
+    assert np.array_equal(res[0], res[2])
+    truth = sum(ck.direct_convolve_delayed_fft(irs[i], xs[i], B) for i in range(ins))
+    assert ck.rel_rms(res[0][0], truth) <= TOL32
