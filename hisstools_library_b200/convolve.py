@@ -209,9 +209,9 @@ class _Engine:
         return int(_abi.lib().hb_conv_bytes_per_launch(self._h))
 
     def process(self, in_rows, out_rows, n, accumulate=False):
-        """in_rows / out_rows: lists of contiguous 1-D arrays of the engine dtype (>= n samples)."""
-        ip = (C.c_void_p * len(in_rows))(*[r.ctypes.data for r in in_rows])
-        op = (C.c_void_p * len(out_rows))(*[r.ctypes.data for r in out_rows])
+        """in_rows / out_rows: lists of contiguous 1-D arrays of the engine dtype (>= n samples); None = silent input / unwanted output."""
+        ip = (C.c_void_p * len(in_rows))(*[None if r is None else r.ctypes.data for r in in_rows])
+        op = (C.c_void_p * len(out_rows))(*[None if r is None else r.ctypes.data for r in out_rows])
         return _abi.check(_abi.lib().hb_conv_process(self._h, ip, op, int(n), 1 if accumulate else 0))
 
     def process_device(self, in_ptr, in_ld, out_ptr, out_ld, n, accumulate=False, stream=0):

@@ -1117,3 +1117,39 @@ def test_fused_hops_strict_and_overlapping_hops_interleaved(hb, ins, B, L):
     assert np.array_equal(res[0], res[2])
     truth = sum(ck.direct_convolve_delayed_fft(irs[i], xs[i], B) for i in range(ins))
     assert ck.rel_rms(res[0][0], truth) <= TOL32
+
+
+@pytest.mark.parametrize("dtype,groups,ins,outs,B", [(np.float64, 16, 1, 1, 8192), (np.float32, 1, 64, 8, 4096), (np.float32, 1, 6, 40, 4096)])
+def test_host_calls_with_large_rows(hb, dtype, groups, ins, outs, B):
+    """Host-pointer calls of one block that carry a MiB each way (rows copied by the helper threads, calls pipelined behind the
+    one-hop latency): config 5's and config 4's row shapes with short IRs, and a matrix whose outputs but not its inputs reach
+    the size, against float64 direct convolution; accumulate, null rows and a ragged call in between."""
+    from hisstools_library_b200.convolve import _Engine
+    L = 3 * B + 100
+    tol = TOL32 if dtype == np.float32 else TOL64
+    hops = 7
+    n = hops * B
+    irs = [[[ck.synth_ir(L, 3800 + 100 * g + 10 * o + i).astype(dtype) for i in range(ins)] for o in range(outs)] for g in range(groups)]
+    xs = np.stack([ck.synth_audio(n, 3800 + r) for r in range(groups * ins)]).astype(dtype)
+    xs[1] = 0                                                # this row is passed as a null pointer
+    e = _Engine(dtype, groups, ins, outs, 2 * B, L, 0, 0, 0)
+    e.set_reset_offset(0)
+    for g in range(groups):
+        for o in range(outs):
+            for i in range(ins):
+                e.set_ir(g, i, o, irs[g][o][i], L)
+    y = np.zeros((groups * outs, n), dtype)
+    calls = [B, B, 1000, B - 1000, B, B, B, B]
+    pos = 0
+    for k, m in enumerate(calls):
+        rows_in = [None if r == 1 else np.ascontiguousarray(xs[r, pos:pos + m]) for r in range(groups * ins)]
+        yo = [np.full(m, 0.5, dtype) if k == 4 else np.zeros(m, dtype) for _ in range(groups * outs)]
+        e.process(rows_in, yo, m, accumulate=(k == 4))
+        for r in range(groups * outs):
+            y[r, pos:pos + m] = yo[r] - (0.5 if k == 4 else 0.0)
+        pos += m
+    e.close()
+    for g in range(groups):
+        for o in range(0, outs, max(1, outs // 4)):
+            truth = sum(ck.direct_convolve_delayed_fft(irs[g][o][i], xs[g * ins + i], B) for i in range(ins))
+            assert ck.rel_rms(y[g * outs + o], truth) <= tol * (1 if dtype == np.float32 else 10) * (3 if dtype == np.float32 else 1)
