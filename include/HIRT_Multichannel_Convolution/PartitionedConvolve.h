@@ -57,6 +57,10 @@ namespace HISSTools
             return true;
         }
 
+        // may consecutive processDevice calls of one block run side by side on the GPU?  0 never, 1 (default) on the object's own
+        // stream (stream = nullptr), 2 on any stream -- the caller's rows are complete when a call is made (hb_conv_set_hop_overlap)
+        void setHopOverlap(int mode) { hisstools_b200_detail::check(hb_conv_set_hop_overlap(mHandle, mode)); }
+
         hb_conv *handle() { return mHandle; }
 
     private:
