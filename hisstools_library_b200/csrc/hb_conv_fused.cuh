@@ -7,10 +7,11 @@
 //   (with several outputs every output's cluster transforms the inputs for itself -- a few microseconds of redundant
 //   arithmetic instead of a grid-wide dependency -- and only output 0's cluster stores the spectra into the delay line)
 //   every rank  forward FFT of the inputs it owns (rank = input mod cluster size) into the newest FDL slot, partition 0
-//               against that fresh spectrum, then its share of the (input, partition >= 1) products against spectra that
-//               are already in the delay line -- all accumulated in registers, one complex bin set per thread;
-//   cluster barrier; rank 0 adds the other ranks' partial spectra and Nyquist sums straight out of their shared memory
-//               (distributed shared memory), then inverse split, inverse FFT, scale 1/(4N), first B samples out.
+//               against that fresh spectrum, partition 1 of those inputs, and its share of the (input, partition >= 2)
+//               products against spectra that are already in the delay line (the rows of several items fetched together:
+//               these loads come from L2 and their latency is what a rank spends) -- accumulated in registers;
+//   cluster barrier; every rank sums its slice of the bins over all ranks' partial spectra (distributed shared memory, in rank
+//               order) and stores it into rank 0's work array; rank 0: inverse split, inverse FFT, scale 1/(4N), first B samples out.
 // Layouts are the engine's own (hb_conv_kernels.cuh) with OT = 1 and one bin tile, so IR loading and the other
 // schedules are unchanged.
 //
@@ -25,7 +26,7 @@
 //           partitions 0 and 1, the reduction, the inverse FFT and the store.
 //  chained  (the engine's own stream, or a caller that declares its rows complete when the call is made:
 //           hb_conv_set_hop_overlap)  no wait up front.  The hop depends on its predecessors through three counters in
-//           device memory (FusedArgs::sync), bumped by every hop of either kind:
+//           device memory (FusedArgs::sync), bumped by every hop that a chained one may follow (FusedArgs::bump), strict or chained:
 //             [0] input blocks saved      -> the previous block of this hop's frame
 //             [1] spectra stored          -> partition 1 (previous hop's spectrum), partitions >= 2 (two hops back and older)
 //             [2] hops finished           -> the delay-line slot this hop overwrites is no longer read (at most `depth` hops
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(MAXT) k_hop_fused(const Geom g, const FusedArg
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     Cx<T> *s = reinterpret_cast<Cx<T> *>(smem_raw);             // FFT work array (padded)
     Cx<T> *stw = s + padded_elems<HB_PADSH>(B);                 // twiddles of this size
-    Cx<T> *xch = stw + B;                                       // this rank's partial spectrum, read by rank 0
+    Cx<T> *xch = stw + B;                                       // this rank's partial spectrum, read by every rank of the cluster
     __shared__ T red[40];
     __shared__ T nyq_part;
     const bool chained = fa.chained != 0;
