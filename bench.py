@@ -412,6 +412,11 @@ def run_ours(args):
         c1.record(stream)
         barrier()
         t_block = c0.elapsed_time(c1) / n_cal * 1e-3
+        # every rank takes the same decision (the slowest rank's time), or their barriers would no longer pair up
+        tc = torch.tensor([t_block], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        t_block = float(tc.item())
         if t_block * n_cal > 5e-3:
             break
     if args.blocks_per_step > 0:
