@@ -2051,9 +2051,30 @@ void gather_rows(hb_conv *c, const void *const *ins, char *dst, size_t n)
 // earlier hop (rw + n <= B; the reference reads its output ring before it transforms, PartitionedConvolve.cpp:307
 // before :352-360): copy the outputs from the host copy of that block, enqueue this call's work and return
 // without waiting for it.  A hop completed by this call is fetched to the other host block behind an event.
+// HB_HOST_TRACE=1 (experiments): where a pipelined host call spends its time -- summed per phase, printed when the process exits
+struct HostTrace
+{
+    bool on = false;
+    double us[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t calls = 0;
+    HostTrace() { const char *e = getenv("HB_HOST_TRACE"); on = e && atoi(e); }
+    ~HostTrace()
+    {
+        if (on && calls)
+            fprintf(stderr, "[hb host trace] %llu calls, us per call: wait for the pinned input buffer %.1f, gather %.1f, enqueue upload + hop %.1f, "
+                            "enqueue download %.1f, wait for the finished block %.1f, scatter %.1f\n", (unsigned long long) calls,
+                    us[0] / calls, us[1] / calls, us[2] / calls, us[3] / calls, us[4] / calls, us[5] / calls);
+    }
+    static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
+HostTrace g_host_trace;
+
 int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size_t n, int accumulate)
 {
     const size_t es = c->esize(), B = c->g.B, rw = c->rw;
+    HostTrace &ht = g_host_trace;
+    double tm = ht.on ? HostTrace::now() : 0;
+    auto lap = [&](int k) { if (ht.on) { const double t = HostTrace::now(); ht.us[k] += t - tm; tm = t; } };
     const size_t rows_in = host_rows_in(c), rows_out = host_rows_out(c);
     int rc;
     for (int k = 0; k < 2; k++)
@@ -2090,7 +2111,9 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
         HB_CUDA(cudaEventSynchronize(c->ev_inq[q]));                        // the pinned buffer has been uploaded
         c->inq_pending[q] = false;
     }
+    lap(0);
     gather_rows(c, ins, (char *) c->h_inq[q].p, n);
+    lap(1);
     if (c->done_pending[q]) HB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_done[q], 0));   // kernels of two calls ago have read d_inq[q]
     HB_CUDA(cudaMemcpyAsync(c->d_inq[q].p, c->h_inq[q].p, rows_in * n * es, cudaMemcpyHostToDevice, c->s_h2d));
     HB_CUDA(cudaEventRecord(c->ev_inq[q], c->s_h2d));
@@ -2101,6 +2124,7 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
     HB_CUDA(cudaEventRecord(c->ev_done[q], c->stream));
     c->done_pending[q] = true;
     c->blk_valid = true;                    // process_core ran no reset here: ensure_ready was called by the caller
+    lap(2);
     if (rw + n == B)
     {
         const int nb = have ^ 1;
@@ -2111,13 +2135,17 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
         c->blk_pending[nb] = true;
         c->blk_cur = nb;
     }
+    lap(3);
     // 2. the outputs of this call: samples rw .. rw+n of the block an earlier hop finished
     if (c->blk_pending[have])
     {
         HB_CUDA(cudaEventSynchronize(c->ev_blk[have]));
         c->blk_pending[have] = false;
     }
+    lap(4);
     scatter_rows(c, outs, (const char *) c->h_blk[have].p, B, rw, n, accumulate);
+    lap(5);
+    if (ht.on) ht.calls++;
     return HB_OK;
 }
 } // namespace

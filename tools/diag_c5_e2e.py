@@ -64,7 +64,10 @@ def run(tail_streams, pipeline, profile, calls=300):
     eng.close()
 
 
-run(0, True, False)
-run(1, True, False)
-run(0, True, True)
-run(0, False, False)
+if len(sys.argv) > 1 and sys.argv[1] == "trace":
+    run(0, True, False, calls=2000)          # with HB_HOST_TRACE=1 in the environment: the host-side phases are printed at exit
+else:
+    run(0, True, False)
+    run(1, True, False)
+    run(0, True, True)
+    run(0, False, False)
