@@ -149,6 +149,7 @@ struct hb_conv
     bool deferred = true;
     PinnedBuf h_blk[2], h_inq[2];
     DevBuf d_inq[2];
+    DevBuf d_blk[2];                // large finished blocks are packed on the device first: one contiguous download instead of a pitched one
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;      // copies run beside the hop kernels, not between them
     cudaEvent_t ev_blk[2] = {nullptr, nullptr}, ev_inq[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool done_pending[2] = {false, false};
@@ -399,7 +400,7 @@ void free_device(hb_conv *c)
     c->d_inbox = nullptr; c->peers_attached = false; c->peers_local = false; c->shard_world = 0;
     for (int k = 0; k < 2; k++)
     {
-        c->h_blk[k].release(); c->h_inq[k].release(); c->d_inq[k].release();
+        c->h_blk[k].release(); c->h_inq[k].release(); c->d_inq[k].release(); c->d_blk[k].release();
         if (c->ev_blk[k]) cudaEventDestroy(c->ev_blk[k]);
         if (c->ev_inq[k]) cudaEventDestroy(c->ev_inq[k]);
         if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
@@ -2114,6 +2115,8 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
     lap(0);
     gather_rows(c, ins, (char *) c->h_inq[q].p, n);
     lap(1);
+    // (the upload stays a copy-engine transfer: forward kernels that read a MiB of rows straight from the pinned buffer took 112 us
+    // instead of 12, profiles/r2_c5_e2e_diag.txt)
     if (c->done_pending[q]) HB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_done[q], 0));   // kernels of two calls ago have read d_inq[q]
     HB_CUDA(cudaMemcpyAsync(c->d_inq[q].p, c->h_inq[q].p, rows_in * n * es, cudaMemcpyHostToDevice, c->s_h2d));
     HB_CUDA(cudaEventRecord(c->ev_inq[q], c->s_h2d));
@@ -2121,16 +2124,29 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
     c->inq_cur = q ^ 1;
     HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_inq[q], 0));
     if ((rc = host_dispatch(c, c->d_inq[q].p, n, nullptr, 0, n, 0, c->stream))) return rc;
+    // A MiB-sized block leaves the device as ONE contiguous copy of a packed block (k_rows behind the inverse transforms, a few
+    // microseconds): the pitched copy out of the staging rows took about 45 us for 16 rows of 64 KiB, twice the contiguous one, and
+    // that copy sits on the round trip block t-1 -> caller -> block t+1 that bounds a host-fed stream (profiles/r2_c5_e2e_diag.txt)
+    const int nb = have ^ 1;
+    const bool packed = rw + n == B && rows_out * B * es >= (size_t(256) << 10) && c->yout_ld != B;
+    if (packed)
+    {
+        if ((rc = c->d_blk[nb].ensure(rows_out * B * es))) return rc;
+        const char *src = (const char *) c->d_yout[c->cur].p + c->y_tail * es;
+        rc = c->dtype == HB_F64 ? launch_rows<double>((double *) c->d_blk[nb].p, B, (const double *) src, c->yout_ld, B, rows_out, 0, c->stream)
+                                : launch_rows<float>((float *) c->d_blk[nb].p, B, (const float *) src, c->yout_ld, B, rows_out, 0, c->stream);
+        if (rc) return rc;
+    }
     HB_CUDA(cudaEventRecord(c->ev_done[q], c->stream));
     c->done_pending[q] = true;
     c->blk_valid = true;                    // process_core ran no reset here: ensure_ready was called by the caller
     lap(2);
     if (rw + n == B)
     {
-        const int nb = have ^ 1;
         const char *src = (const char *) c->d_yout[c->cur].p + c->y_tail * es;
         HB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_done[q], 0));
-        HB_CUDA(cudaMemcpy2DAsync(c->h_blk[nb].p, B * es, src, c->yout_ld * es, B * es, rows_out, cudaMemcpyDeviceToHost, c->s_d2h));
+        if (packed) HB_CUDA(cudaMemcpyAsync(c->h_blk[nb].p, c->d_blk[nb].p, rows_out * B * es, cudaMemcpyDeviceToHost, c->s_d2h));
+        else HB_CUDA(cudaMemcpy2DAsync(c->h_blk[nb].p, B * es, src, c->yout_ld * es, B * es, rows_out, cudaMemcpyDeviceToHost, c->s_d2h));
         HB_CUDA(cudaEventRecord(c->ev_blk[nb], c->s_d2h));
         c->blk_pending[nb] = true;
         c->blk_cur = nb;
@@ -2141,6 +2157,9 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
     {
         HB_CUDA(cudaEventSynchronize(c->ev_blk[have]));
         c->blk_pending[have] = false;
+        // that block came out of the hop of the previous call, whose kernels had read the upload of that call: the other pinned input
+        // buffer is free without asking its event (a cudaEventSynchronize on a finished event still costs several microseconds)
+        c->inq_pending[q ^ 1] = false;
     }
     lap(4);
     scatter_rows(c, outs, (const char *) c->h_blk[have].p, B, rw, n, accumulate);
