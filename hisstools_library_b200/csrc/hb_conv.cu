@@ -2115,10 +2115,23 @@ int process_deferred(hb_conv *c, const void *const *ins, void *const *outs, size
     lap(0);
     gather_rows(c, ins, (char *) c->h_inq[q].p, n);
     lap(1);
-    // (the upload stays a copy-engine transfer: forward kernels that read a MiB of rows straight from the pinned buffer took 112 us
-    // instead of 12, profiles/r2_c5_e2e_diag.txt)
+    // (forward kernels that read a MiB of rows straight from the pinned buffer themselves took 112 us instead of 12: the rows are
+    // brought to the device first)
     if (c->done_pending[q]) HB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_done[q], 0));   // kernels of two calls ago have read d_inq[q]
-    HB_CUDA(cudaMemcpyAsync(c->d_inq[q].p, c->h_inq[q].p, rows_in * n * es, cudaMemcpyHostToDevice, c->s_h2d));
+    // A MiB-sized upload is done by a copy kernel that reads the pinned rows (mapped host memory) instead of the copy engine: while a
+    // tail launch saturates HBM a copy-engine transfer lands only when that launch ends, and the forward FFTs -- and with them the next
+    // tail -- start late (profiles/r2_c5_e2e_diag.txt: 106 -> 102 us per call at config 5).  HB_UPLOAD_KERNEL=0: copy engine always.
+    static const char *env_upk = getenv("HB_UPLOAD_KERNEL");
+    if (!(env_upk && !atoi(env_upk)) && rows_in * n * es >= (size_t(256) << 10))
+    {
+        void *mapped = nullptr;
+        HB_CUDA(cudaHostGetDevicePointer(&mapped, c->h_inq[q].p, 0));
+        rc = c->dtype == HB_F64 ? launch_rows<double>((double *) c->d_inq[q].p, n, (const double *) mapped, n, n, rows_in, 0, c->s_h2d)
+                                : launch_rows<float>((float *) c->d_inq[q].p, n, (const float *) mapped, n, n, rows_in, 0, c->s_h2d);
+        if (rc) return rc;
+    }
+    else
+        HB_CUDA(cudaMemcpyAsync(c->d_inq[q].p, c->h_inq[q].p, rows_in * n * es, cudaMemcpyHostToDevice, c->s_h2d));
     HB_CUDA(cudaEventRecord(c->ev_inq[q], c->s_h2d));
     c->inq_pending[q] = true;
     c->inq_cur = q ^ 1;
