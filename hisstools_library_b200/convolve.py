@@ -631,6 +631,11 @@ class Convolver:
         """Device-resident rows of the engine dtype: in [numIns][in_ld], out [numOuts][out_ld]."""
         return self._m.process_device(in_ptr, in_ld, out_ptr, out_ld, numSamples, False, stream)
 
+    def set_hop_overlap(self, mode=1):
+        """may consecutive process_device calls of one block run side by side on the GPU?  0 never, 1 on the object's own stream
+        (stream=0), 2 on any stream -- the rows of a call are complete when it is made (hb_matrix_set_hop_overlap)"""
+        return self._m.set_hop_overlap(mode)
+
     @property
     def matrix(self):
         return self._m
